@@ -1,0 +1,164 @@
+/*
+ * meb200.h — C ABI of the B200-native sparse-convolution hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers + sizes + the CUDA
+ * stream to launch on (as `void*`, i.e. a cudaStream_t), allocates nothing the caller
+ * did not hand in, and returns 0 on success or a negative MEB200_ERR_* code; the text
+ * of the last failure on the calling thread is available from meb200_last_error().
+ * No torch / C++ types appear in any signature.
+ *
+ * These are the calls the reference's FFI for this path would bind.  The reference's
+ * boundary is the pybind module `MinkowskiEngineBackend._C` (pybind/extern.hpp); each
+ * function below names the reference interface it stands in for.  The Python host in
+ * `minkowskiengine_b200/` binds them through ctypes.
+ *
+ * Conventions
+ *   coords      int32 [n, ncols] row-major, ncols = D+1, column 0 = batch index
+ *               (reference: src/coordinate.hpp:36-61, MinkowskiSparseTensor.py:293-345)
+ *   table       uint32 [capacity] open-addressing hash table of ROW INDICES into the
+ *               coords array it was built over (0xFFFFFFFF = empty); capacity is a
+ *               power of two from meb200_hash_capacity()
+ *   nbr tables  int32 [K, n] "neighbour tables", k-major: nbr[k*n + r] = the row on
+ *               the other side reached from row r through kernel offset k, or -1
+ *   features    [n, C] row-major; dtype codes MEB200_F32 / MEB200_BF16 / MEB200_F16
+ *   weights     [K, Cin, Cout] row-major (reference: MinkowskiConvolution.py:264-279)
+ */
+#ifndef MEB200_H_
+#define MEB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MEB200_OK 0
+#define MEB200_ERR_INVALID (-1) /* bad argument (shape, dtype, null pointer)        */
+#define MEB200_ERR_CUDA (-2)    /* a CUDA runtime call or kernel launch failed      */
+#define MEB200_ERR_UNSUPPORTED (-3) /* valid request this build has no kernel for   */
+
+#define MEB200_F32 0
+#define MEB200_BF16 1
+#define MEB200_F16 2
+
+#define MEB200_MAX_NCOLS 8 /* D+1 <= 8, i.e. up to 7 spatial/temporal axes */
+
+#define MEB200_POOL_SUM 0 /* reference PoolingMode::LOCAL_SUM_POOLING (src/types.hpp:141) */
+#define MEB200_POOL_AVG 1 /* LOCAL_AVG_POOLING */
+#define MEB200_POOL_MAX 2 /* LOCAL_MAX_POOLING */
+
+/* ---- library ---------------------------------------------------------------------- */
+const char *meb200_last_error(void);
+/* Compile-time facts: "sm_100a", CUDA runtime version the library was built with.     */
+const char *meb200_build_arch(void);
+int meb200_cudart_version(void); /* reference: cudart_version(), pybind/extern.hpp:808-838 */
+/* Number of kernels this library has launched since load (bench.py's gpu_launches).   */
+uint64_t meb200_launch_count(void);
+
+/* ---- coordinate hashing (reference a1/a2: src/coordinate.hpp:223-349,
+ *      CoordinateMapCPU::insert_and_map coordinate_map_cpu.hpp:353-380,
+ *      CoordinateMapGPU::insert coordinate_map_gpu.cu:196-278) ------------------------ */
+
+/* Table capacity (power of two) used for n keys. */
+uint32_t meb200_hash_capacity(uint32_t n);
+
+/* Bytes of scratch the dedup pipeline needs for n candidate rows. */
+uint64_t meb200_insert_scratch_bytes(uint32_t n);
+
+/*
+ * Deduplicating insert with the CPU reference's semantics: among equal coordinates the
+ * FIRST row (smallest index) wins and unique rows are numbered by the rank of their
+ * first occurrence.
+ *   coords        [n, ncols] candidates          valid   optional uint8[n] (NULL = all)
+ *   table         [capacity] out, built over `unique_coords` (row ids are NEW ids)
+ *   unique_coords [n, ncols] out (first *h_num_unique rows are meaningful)
+ *   unique_index  int64 [n] out: original row of each unique row (first m meaningful)
+ *   inverse_map   int64 [n] out: new row id of every candidate (-1 where !valid)
+ *   scratch       meb200_insert_scratch_bytes(n) bytes
+ *   h_num_unique  HOST pointer; written after a stream synchronise (the one blocking
+ *                 point of map construction: the caller needs m to size tensors).
+ */
+int meb200_insert_and_map(const int32_t *coords, const uint8_t *valid, uint32_t n,
+                          uint32_t ncols, uint32_t *table, uint32_t capacity,
+                          int32_t *unique_coords, int64_t *unique_index,
+                          int64_t *inverse_map, void *scratch, uint32_t *h_num_unique,
+                          void *stream);
+
+/* Candidate generation for a strided map: out[i] = floor(c / ts_out) * ts_out per
+ * spatial axis, batch kept (reference a3: detail::stride_coordinate
+ * src/coordinate_map.hpp:58-76 — integer floor division here).
+ * out_tensor_stride: HOST int32[ncols-1]. */
+int meb200_stride_coords(const int32_t *coords, uint32_t n, uint32_t ncols,
+                         const int32_t *out_tensor_stride, int32_t *out, void *stream);
+
+/* Candidate generation for stride_region (reference: CoordinateMapCPU::stride_region
+ * coordinate_map_cpu.hpp:446-487): out[(i*K + k)] = coords[i] + offsets[k]; when
+ * `aligned_only` != 0 candidates not aligned to out_tensor_stride get valid = 0.
+ * offsets: DEVICE int32 [K, ncols-1]; out_tensor_stride: HOST int32[ncols-1]. */
+int meb200_region_coords(const int32_t *coords, uint32_t n, uint32_t ncols,
+                         const int32_t *offsets, uint32_t K,
+                         const int32_t *out_tensor_stride, int aligned_only,
+                         int32_t *out, uint8_t *valid, void *stream);
+
+/* Batch lookup: result[i] = row of query[i] in the map, or -1
+ * (reference: CoordinateMapCPU::find coordinate_map_cpu.hpp:388-412). */
+int meb200_map_find(const int32_t *map_coords, const uint32_t *table, uint32_t capacity,
+                    uint32_t ncols, const int32_t *query, uint32_t nq, int32_t *result,
+                    void *stream);
+
+/* ---- kernel map (reference a4/a5: kernel_region::coordinate_at kernel_region.hpp:198-247,
+ *      CoordinateMapCPU::kernel_map coordinate_map_cpu.hpp:569-670,
+ *      CoordinateMapGPU::kernel_map coordinate_map_gpu.cu:1549-1745) ------------------ */
+/*
+ * For every row x of the iterated map X and every offset k: probe map Y at
+ * X[x] + offsets[k].  x_nbr[k*nx + x] = y (or -1) and, when y_nbr != NULL,
+ * y_nbr[k*ny + y] = x (y_nbr must be pre-filled with -1 by the caller).
+ * offsets: DEVICE int32 [K, ncols-1] already scaled by dilation * tensor stride.
+ * d_num_pairs: optional DEVICE uint32 counter, incremented by the number of hits.
+ */
+int meb200_kernel_map(const int32_t *x_coords, uint32_t nx, const int32_t *y_coords,
+                      uint32_t ny, const uint32_t *y_table, uint32_t y_capacity,
+                      uint32_t ncols, const int32_t *offsets, uint32_t K, int32_t *x_nbr,
+                      int32_t *y_nbr, uint32_t *d_num_pairs, void *stream);
+
+/* ---- sparse convolution (reference a8/a9/a10: ConvolutionForwardKernelCPU /
+ *      ConvolutionBackwardKernelCPU src/convolution_kernel.hpp:33-144, GPU
+ *      src/convolution_kernel.cu:114-496,553-757) ------------------------------------ */
+/*
+ * out[o,:] = sum_k in[out_nbr[k,o],:] @ W[k]          (rows with out_nbr = -1 skipped)
+ * Output is fully written (no pre-zeroing needed, no atomics, deterministic).
+ * in_dtype: dtype of `in` and `weight`; out_dtype: dtype of `out` (F32 always allowed).
+ */
+int meb200_conv_forward(const void *in, int in_dtype, uint32_t n_in, uint32_t c_in,
+                        const void *weight, uint32_t K, uint32_t c_out,
+                        const int32_t *out_nbr, uint32_t n_out, void *out, int out_dtype,
+                        void *workspace, uint64_t workspace_bytes, void *stream);
+
+/* grad_in[i,:] = sum_k grad_out[in_nbr[k,i],:] @ W[k]^T   (fully written)
+ * grad_weight[k] = sum_o in[out_nbr[k,o],:]^T @ grad_out[o,:]   (fully written, fp32) */
+int meb200_conv_backward(const void *in, const void *grad_out, int dtype, uint32_t n_in,
+                         uint32_t c_in, const void *weight, uint32_t K, uint32_t c_out,
+                         const int32_t *out_nbr, const int32_t *in_nbr, uint32_t n_out,
+                         void *grad_in, int grad_in_dtype, float *grad_weight,
+                         void *workspace, uint64_t workspace_bytes, void *stream);
+
+/* Workspace the two calls above may use (0 is legal: slower fallbacks are chosen). */
+uint64_t meb200_conv_workspace_bytes(uint32_t n_in, uint32_t n_out, uint32_t c_in,
+                                     uint32_t c_out, uint32_t K, int dtype);
+
+/* ---- local pooling (reference a11: src/pooling_avg_kernel.hpp:40-150,
+ *      src/pooling_max_kernel.hpp:35-115, src/local_pooling_cpu.cpp:43-185) ---------- */
+/* aux: AVG -> num_nonzero [n_out] (feature dtype); MAX -> max_index int32 [n_out, C]
+ * (flat index row*C + c into `in`, -1 for rows without input); SUM -> unused (NULL ok). */
+int meb200_pool_forward(const void *in, int dtype, uint32_t n_in, uint32_t C,
+                        const int32_t *out_nbr, uint32_t K, uint32_t n_out, int mode,
+                        void *out, void *aux, void *stream);
+/* grad_in fully written for SUM/AVG; for MAX the caller zero-fills grad_in first. */
+int meb200_pool_backward(const void *grad_out, int dtype, uint32_t n_in, uint32_t C,
+                         const int32_t *in_nbr, uint32_t K, uint32_t n_out, int mode,
+                         const void *aux, void *grad_in, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEB200_H_ */

@@ -1,0 +1,640 @@
+"""Host-side mirror of the reference's native boundary `MinkowskiEngineBackend._C`
+(pybind/extern.hpp:515-838) for the sparse-convolution hot path.
+
+Same names, argument order and side effects as the reference's `...GPU` functions and
+`CoordinateMapManagerGPU_c10`, but the bodies are thin: they validate, keep the manager's
+bookkeeping (key naming / reuse / kernel-map cache — coordinate_map_manager.cpp:353-466,
+662-823) and hand device pointers to the C-ABI library (include/meb200.h).  All device
+work happens in libmeb200.so on torch's current CUDA stream; the only host<->device
+synchronisation is the unique-row count read when a NEW coordinate map is created.
+"""
+import ctypes
+import random
+import string
+
+import torch
+
+from . import _lib
+from .enums import (ConvolutionMode, MinkowskiAlgorithm, PoolingMode, RegionType)
+from .kernel_generator import region_offsets
+
+ERROR_MAP_NOT_FOUND = "CoordinateMap not found"  # reference: src/errors.hpp:33
+
+
+def _assert(cond, *msg):
+    """Reference ASSERT semantics (src/utils.hpp:141-150): RuntimeError with the message."""
+    if not cond:
+        raise RuntimeError(" ".join(str(m) for m in msg))
+
+
+def is_cuda_available():
+    return torch.cuda.is_available()
+
+
+def cuda_version():
+    return int(torch.version.cuda.replace(".", "")) * 10 if torch.version.cuda else 0
+
+
+def cudart_version():
+    return int(_lib.load().meb200_cudart_version())
+
+
+def get_gpu_memory_info():
+    return torch.cuda.mem_get_info()
+
+
+# ----------------------------------------------------------------------------------------
+class CoordinateMapKey:
+    """(tensor_stride, string_id) handle of a coordinate map
+    (reference: src/coordinate_map_key.hpp:44-157, pybind/extern.hpp:744-763)."""
+
+    __slots__ = ("_coordinate_size", "_tensor_stride", "_string_id", "_set")
+
+    def __init__(self, *args):
+        if len(args) == 1 and isinstance(args[0], int):
+            self._coordinate_size = args[0]
+            self._tensor_stride, self._string_id, self._set = None, "", False
+        elif len(args) == 2:
+            ts = [int(v) for v in args[0]]
+            self._coordinate_size = len(ts) + 1
+            self._tensor_stride, self._string_id, self._set = ts, str(args[1]), True
+        else:
+            raise TypeError("CoordinateMapKey(coordinate_size:int) or "
+                            "CoordinateMapKey(tensor_stride:list, string_id:str)")
+
+    def is_key_set(self):
+        return self._set
+
+    def get_coordinate_size(self):
+        return self._coordinate_size
+
+    def get_dimension(self):
+        return self._coordinate_size
+
+    def get_key(self):
+        _assert(self._set, "CoordinateMapKey: Key Not Set")
+        return (list(self._tensor_stride), self._string_id)
+
+    def set_key(self, *args):
+        if len(args) == 1:
+            ts, sid = args[0]
+        else:
+            ts, sid = args
+        ts = [int(v) for v in ts]
+        _assert(len(ts) + 1 == self._coordinate_size, "Invalid tensor stride size", ts,
+                "for coordinate size", self._coordinate_size)
+        self._tensor_stride, self._string_id, self._set = ts, str(sid), True
+
+    def get_tensor_stride(self):
+        _assert(self._set, "CoordinateMapKey: Key Not Set")
+        return list(self._tensor_stride)
+
+    def _tuple(self):
+        return (tuple(self._tensor_stride), self._string_id)
+
+    def __eq__(self, other):
+        if not isinstance(other, CoordinateMapKey):
+            return NotImplemented
+        if not (self._set and other._set):
+            return False
+        return self._coordinate_size == other._coordinate_size and self._tuple() == other._tuple()
+
+    def __hash__(self):
+        return hash(self._tuple()) if self._set else hash(self._coordinate_size)
+
+    def __repr__(self):
+        if not self._set:
+            return f"coordinate map key: unset (coordinate size {self._coordinate_size})"
+        s = "coordinate map key:" + "[" + ", ".join(str(v) for v in self._tensor_stride) + "]"
+        return s + (":" + self._string_id if self._string_id else "")
+
+
+# ----------------------------------------------------------------------------------------
+class _CoordinateMap:
+    """Device-resident coordinate map: unique int32 rows + open-addressing row-index table
+    (replaces CoordinateMapGPU, src/coordinate_map_gpu.cuh:61-317)."""
+
+    __slots__ = ("coords", "table", "capacity", "tensor_stride")
+
+    def __init__(self, coords, table, capacity, tensor_stride):
+        self.coords, self.table, self.capacity = coords, table, capacity
+        self.tensor_stride = tuple(tensor_stride)
+
+    @property
+    def size(self):
+        return self.coords.shape[0]
+
+    @property
+    def ncols(self):
+        return self.coords.shape[1]
+
+    @staticmethod
+    def build(candidates, tensor_stride, valid=None):
+        """Deduplicating insert of candidate rows -> (map, unique_index, inverse_map)."""
+        lib = _lib.load()
+        n, ncols = candidates.shape
+        dev = candidates.device
+        cap = int(lib.meb200_hash_capacity(n))
+        table = torch.empty(cap, dtype=torch.int32, device=dev)
+        uniq = torch.empty((n, ncols), dtype=torch.int32, device=dev)
+        uidx = torch.empty(n, dtype=torch.int64, device=dev)
+        inv = torch.empty(n, dtype=torch.int64, device=dev)
+        scratch = torch.empty(int(lib.meb200_insert_scratch_bytes(n)), dtype=torch.uint8,
+                              device=dev)
+        m = ctypes.c_uint32(0)
+        _lib.check(lib.meb200_insert_and_map(
+            _lib.ptr(candidates), _lib.ptr(valid), n, ncols, _lib.ptr(table), cap,
+            _lib.ptr(uniq), _lib.ptr(uidx), _lib.ptr(inv), _lib.ptr(scratch),
+            ctypes.byref(m), _lib.current_stream()))
+        m = int(m.value)
+        cmap = _CoordinateMap(uniq[:m], table, cap, tensor_stride)
+        return cmap, uidx[:m], inv
+
+
+class _KernelMap:
+    """k-major neighbour tables of one (in map, out map, kernel) triple.
+
+    out_nbr[k, o] = input row reached from output row o through offset k (or -1)
+    in_nbr [k, i] = output row that input row i feeds through offset k (or -1)
+    Replaces gpu_kernel_map's three flat arrays + host offset table (src/kernel_map.cuh:48-429);
+    `swapped()` is the reference's swap_in_out (kernel_map.cuh:191-241)."""
+
+    __slots__ = ("out_nbr", "in_nbr", "stride_pairs")
+
+    def __init__(self, out_nbr, in_nbr, stride_pairs=None):
+        self.out_nbr, self.in_nbr = out_nbr, in_nbr
+        self.stride_pairs = stride_pairs  # (in_rows, out_rows) when built as a stride map
+
+    @property
+    def K(self):
+        return self.out_nbr.shape[0]
+
+    @property
+    def n_out(self):
+        return self.out_nbr.shape[1]
+
+    @property
+    def n_in(self):
+        return self.in_nbr.shape[1]
+
+    def swapped(self):
+        sp = None if self.stride_pairs is None else (self.stride_pairs[1], self.stride_pairs[0])
+        return _KernelMap(self.in_nbr, self.out_nbr, sp)
+
+    def to_dict(self):
+        """{k: IntTensor[2, n_k]} as kernel_map_th returns (coordinate_map_manager.cpp:1395-1414);
+        pairs within an offset are ordered by output row (the reference order is unspecified)."""
+        if self.stride_pairs is not None:
+            i, o = self.stride_pairs
+            return {0: torch.stack([i.int(), o.int()])} if i.numel() else {}
+        out = {}
+        hit = self.out_nbr >= 0
+        counts = hit.sum(dim=1).tolist()
+        for k, c in enumerate(counts):
+            if c > 0:
+                o = torch.nonzero(hit[k]).flatten()
+                out[k] = torch.stack([self.out_nbr[k, o], o.int()])
+        return out
+
+
+_OFFSET_CACHE = {}
+
+
+def _device_offsets(region_type, kernel_size, dilation, tensor_stride, custom, device):
+    """[K, D] int32 offset table on `device` (cached: a network reuses a handful)."""
+    ckey = (region_type, tuple(kernel_size), tuple(dilation), tuple(tensor_stride),
+            None if custom is None or custom.numel() == 0 else tuple(map(tuple, custom.tolist())),
+            str(device))
+    t = _OFFSET_CACHE.get(ckey)
+    if t is None:
+        offs = region_offsets(region_type, list(kernel_size), list(dilation),
+                              list(tensor_stride), custom)
+        t = torch.tensor(offs, dtype=torch.int32).reshape(len(offs), len(kernel_size)).to(device)
+        _OFFSET_CACHE[ckey] = t
+    return t
+
+
+class CoordinateMapManagerGPU_c10:
+    """Owner of coordinate maps and kernel maps on one device
+    (reference: CoordinateMapManager, src/coordinate_map_manager.hpp:130-565)."""
+
+    def __init__(self, algorithm=MinkowskiAlgorithm.DEFAULT, num_threads=-1):
+        self.algorithm = algorithm
+        self.num_threads = num_threads  # accepted for signature parity; unused on GPU
+        self._maps = {}         # (tuple tensor_stride, str id) -> _CoordinateMap
+        self._kernel_maps = {}  # 8-tuple (types.hpp:183-192) -> _KernelMap
+        self._parents = {}      # out key -> (in key, int64 row of every in row in out map)
+        _lib.load()             # fail at construction if the native library is missing
+
+    # -- keys ------------------------------------------------------------------------
+    @staticmethod
+    def _k(key):
+        if isinstance(key, CoordinateMapKey):
+            ts, sid = key.get_key()
+            return (tuple(ts), sid)
+        return (tuple(key[0]), key[1])
+
+    def exists(self, key):
+        return self._k(key) in self._maps
+
+    def _get(self, key, what=""):
+        k = self._k(key)
+        _assert(k in self._maps, what, ERROR_MAP_NOT_FOUND)
+        return self._maps[k]
+
+    def get_random_string_id(self, tensor_stride, string_id=""):
+        ts = tuple(int(v) for v in tensor_stride)
+        while True:
+            r = "".join(random.choices(string.ascii_letters + string.digits, k=5))
+            key = (ts, (string_id + "-" + r) if string_id else r)
+            if key not in self._maps:
+                return key
+
+    def get_coordinate_map_keys(self, tensor_stride):
+        ts = tuple(int(v) for v in tensor_stride)
+        return [CoordinateMapKey(list(k[0]), k[1]) for k in self._maps if k[0] == ts]
+
+    def size(self, key):
+        return self._get(key).size
+
+    def get_coordinates(self, key):
+        return self._get(key).coords
+
+    # -- map creation ----------------------------------------------------------------
+    def insert_and_map(self, coordinates, tensor_stride, string_id=""):
+        """reference: coordinate_map_manager.cpp:353-399"""
+        _assert(coordinates.dim() == 2, "coordinates must be 2-dimensional")
+        _assert(coordinates.dtype == torch.int32, "coordinates must be an IntTensor")
+        _assert(coordinates.is_contiguous(), "coordinates must be contiguous")
+        _assert(coordinates.is_cuda,
+                "coordinates must be a CUDA tensor: minkowskiengine_b200 implements the GPU "
+                "coordinate manager only (no CPU backend, no fallback)")
+        ts = [int(v) for v in tensor_stride]
+        _assert(coordinates.size(1) - 1 == len(ts),
+                "The coordinate dimension (coordinate_size - 1):", coordinates.size(1) - 1,
+                " must match the size of tensor stride:", ts)
+        key = (tuple(ts), string_id)
+        if key in self._maps:
+            key = self.get_random_string_id(ts, string_id)
+        cmap, unique_index, inverse_map = _CoordinateMap.build(coordinates, ts)
+        self._maps[key] = cmap
+        if cmap.size == coordinates.size(0):
+            # no duplicates: the reference GPU path returns an empty inverse map here
+            # (coordinate_map_manager.cu:94-112) and Python substitutes arange
+            inverse_map = inverse_map[:0]
+        return CoordinateMapKey(list(key[0]), key[1]), (unique_index, inverse_map)
+
+    def _stride(self, in_key, kernel_stride, string_id=""):
+        """reference: coordinate_map_manager.cpp:406-429 -> (out key tuple, created?)"""
+        in_key = self._k(in_key)
+        _assert(in_key in self._maps, ERROR_MAP_NOT_FOUND)
+        _assert(len(kernel_stride) == len(in_key[0]), "stride size mismatch.")
+        out_ts = tuple(t * int(s) for t, s in zip(in_key[0], kernel_stride))
+        out_key = (out_ts, string_id if string_id else in_key[1])
+        if out_key in self._maps:
+            return out_key, False
+        in_map = self._maps[in_key]
+        lib = _lib.load()
+        cand = torch.empty_like(in_map.coords)
+        ts_arr = (ctypes.c_int32 * len(out_ts))(*out_ts)
+        _lib.check(lib.meb200_stride_coords(_lib.ptr(in_map.coords), in_map.size, in_map.ncols,
+                                            ts_arr, _lib.ptr(cand), _lib.current_stream()))
+        out_map, _, inverse = _CoordinateMap.build(cand, out_ts)
+        self._maps[out_key] = out_map
+        self._parents[out_key] = (in_key, inverse)
+        return out_key, True
+
+    def stride(self, key, stride, string_id=""):
+        out_key, _ = self._stride(key, [int(s) for s in stride], string_id)
+        return CoordinateMapKey(list(out_key[0]), out_key[1])
+
+    def _stride_region(self, in_key, region_type, kernel_size, dilation, custom_offsets,
+                       region_tensor_stride, out_tensor_stride, is_transpose,
+                       expand_coordinates):
+        """reference: coordinate_map_manager.cpp:435-466 + coordinate_map_cpu.hpp:446-487"""
+        in_key = self._k(in_key)
+        _assert(in_key in self._maps, ERROR_MAP_NOT_FOUND)
+        out_ts = tuple(int(v) for v in out_tensor_stride)
+        out_key = (out_ts, "")
+        exists = out_key in self._maps
+        if exists and not expand_coordinates:
+            return out_key, False
+        in_map = self._maps[in_key]
+        lib = _lib.load()
+        offs = _device_offsets(region_type, kernel_size, dilation, region_tensor_stride,
+                               custom_offsets, in_map.coords.device)
+        K = offs.shape[0]
+        n = in_map.size
+        cand = torch.empty((n * K, in_map.ncols), dtype=torch.int32, device=in_map.coords.device)
+        valid = torch.empty(n * K, dtype=torch.uint8, device=in_map.coords.device)
+        ts_arr = (ctypes.c_int32 * len(out_ts))(*out_ts)
+        _lib.check(lib.meb200_region_coords(
+            _lib.ptr(in_map.coords), n, in_map.ncols, _lib.ptr(offs), K, ts_arr,
+            0 if is_transpose else 1, _lib.ptr(cand), _lib.ptr(valid), _lib.current_stream()))
+        out_map, _, _ = _CoordinateMap.build(cand, out_ts, valid)
+        out_map.coords = out_map.coords.clone()  # drop the n*K candidate buffer
+        if exists:
+            out_key = self.get_random_string_id(out_ts, "")
+        self._maps[out_key] = out_map
+        return out_key, True
+
+    # -- kernel maps -----------------------------------------------------------------
+    def _probe(self, x_map, y_map, offsets):
+        """x-stationary probe: returns (x_nbr [K,nx], y_nbr [K,ny])."""
+        lib = _lib.load()
+        K = offsets.shape[0]
+        dev = x_map.coords.device
+        x_nbr = torch.empty((K, x_map.size), dtype=torch.int32, device=dev)
+        y_nbr = torch.full((K, y_map.size), -1, dtype=torch.int32, device=dev)
+        _lib.check(lib.meb200_kernel_map(
+            _lib.ptr(x_map.coords), x_map.size, _lib.ptr(y_map.coords), y_map.size,
+            _lib.ptr(y_map.table), y_map.capacity, x_map.ncols, _lib.ptr(offsets), K,
+            _lib.ptr(x_nbr), _lib.ptr(y_nbr), None, _lib.current_stream()))
+        return x_nbr, y_nbr
+
+    def _kernel_map(self, in_key, out_key, kernel_size, kernel_stride, kernel_dilation,
+                    region_type, offset, is_transpose, is_pool):
+        """reference: coordinate_map_manager.cpp:662-823 (cache key = types.hpp:183-192)"""
+        ik, ok = self._k(in_key), self._k(out_key)
+        ksize = tuple(int(v) for v in kernel_size)
+        kstride = tuple(int(v) for v in kernel_stride)
+        kdil = tuple(int(v) for v in kernel_dilation)
+        _assert(len(ksize) == len(kstride) == len(kdil), "kernel size mismatch")
+        cache_key = (ik, ok, ksize, kstride, kdil, region_type, bool(is_transpose), bool(is_pool))
+        km = self._kernel_maps.get(cache_key)
+        if km is not None:
+            return km
+        _assert(ik in self._maps, "in_map", ERROR_MAP_NOT_FOUND)
+        _assert(ok in self._maps, "out_map", ERROR_MAP_NOT_FOUND)
+        in_map, out_map = self._maps[ik], self._maps[ok]
+        _assert(len(ksize) + 1 == in_map.ncols, "kernel size mismatch")
+        custom = offset if region_type == RegionType.CUSTOM else None
+        dev = in_map.coords.device
+        stride_map = is_pool and kstride == ksize
+        if not is_transpose:
+            if stride_map:
+                # every input row -> its strided parent (coordinate_map_cpu.hpp:672-722);
+                # the floor cell [u, u + k*ts_in) is probed with non-centred offsets
+                offs = self._cell_offsets(ksize, in_map.tensor_stride, dev)
+                out_nbr, in_nbr = self._probe(out_map, in_map, offs)
+                km = _KernelMap(out_nbr, in_nbr, self._stride_pairs(ik, ok, in_map, out_map))
+            else:
+                offs = _device_offsets(region_type, ksize, kdil, in_map.tensor_stride, custom, dev)
+                out_nbr, in_nbr = self._probe(out_map, in_map, offs)
+                km = _KernelMap(out_nbr, in_nbr)
+        else:
+            swapped_key = (ok, ik, ksize, kstride, kdil, region_type, False, bool(is_pool))
+            fwd = self._kernel_maps.get(swapped_key)
+            if fwd is None:
+                # iterate the coarse input rows, probe the fine output map with offsets in
+                # output-stride units (coordinate_map_manager.cpp:789-811), i.e. the forward
+                # map of (out -> in); cached under the forward key as well
+                if stride_map:
+                    offs = self._cell_offsets(ksize, out_map.tensor_stride, dev)
+                    a, b = self._probe(in_map, out_map, offs)
+                    fwd = _KernelMap(a, b, self._stride_pairs(ok, ik, out_map, in_map))
+                else:
+                    offs = _device_offsets(region_type, ksize, kdil, out_map.tensor_stride,
+                                           custom, dev)
+                    a, b = self._probe(in_map, out_map, offs)
+                    fwd = _KernelMap(a, b)
+            km = fwd.swapped()
+        self._kernel_maps[cache_key] = km
+        return km
+
+    @staticmethod
+    def _cell_offsets(ksize, tensor_stride, dev):
+        # offsets i * ts, i in [0, k): the members of one stride cell
+        return _device_offsets(RegionType.CUSTOM, ksize, [1] * len(ksize), tensor_stride,
+                               _cell_table(ksize), dev)
+
+    def _stride_pairs(self, in_key, out_key, in_map, out_map):
+        """(in_rows, out_rows) of the stride map as the API reports it."""
+        par = self._parents.get(out_key)
+        if par is not None and par[0] == in_key:
+            inv = par[1]
+        else:
+            lib = _lib.load()
+            cand = torch.empty_like(in_map.coords)
+            ts = out_map.tensor_stride
+            ts_arr = (ctypes.c_int32 * len(ts))(*ts)
+            _lib.check(lib.meb200_stride_coords(_lib.ptr(in_map.coords), in_map.size,
+                                                in_map.ncols, ts_arr, _lib.ptr(cand),
+                                                _lib.current_stream()))
+            res = torch.empty(in_map.size, dtype=torch.int32, device=cand.device)
+            _lib.check(lib.meb200_map_find(_lib.ptr(out_map.coords), _lib.ptr(out_map.table),
+                                           out_map.capacity, out_map.ncols, _lib.ptr(cand),
+                                           in_map.size, _lib.ptr(res), _lib.current_stream()))
+            inv = res.long()
+        rows = torch.arange(in_map.size, dtype=torch.int64, device=inv.device)
+        keep = inv >= 0
+        return rows[keep], inv[keep]
+
+    def kernel_map(self, in_key, out_key, kernel_size, kernel_stride, kernel_dilation,
+                   region_type, offset, is_transpose, is_pool):
+        """Python-facing dict form (kernel_map_th, coordinate_map_manager.cpp:1395-1414)."""
+        return self._kernel_map(in_key, out_key, kernel_size, kernel_stride, kernel_dilation,
+                                region_type, offset, is_transpose, is_pool).to_dict()
+
+    def stride_map(self, in_key, out_key):
+        ik, ok = self._k(in_key), self._k(out_key)
+        in_map, out_map = self._get(ik), self._get(ok)
+        return self._stride_pairs(ik, ok, in_map, out_map)
+
+    def __repr__(self):
+        lines = [f"\t{list(k[0])}{':' + k[1] if k[1] else ''}:\tCoordinateMapGPU:{m.size}x{m.ncols}"
+                 for k, m in self._maps.items()]
+        return "\n".join(lines + [f"\tkernel maps: {len(self._kernel_maps)}"]) + "\n"
+
+
+def _cell_table(ksize):
+    import itertools
+    rows = []
+    for idx in itertools.product(*[range(k) for k in reversed(ksize)]):
+        rows.append(list(reversed(idx)))  # axis 0 fastest, like HYPER_CUBE
+    return torch.tensor(rows, dtype=torch.int32)
+
+
+CoordinateMapManagerGPU_default = CoordinateMapManagerGPU_c10
+
+
+# ----------------------------------------------------------------------------------------
+def _check_feats(in_feat, manager, in_key, name="in_feat"):
+    _assert(in_feat.is_cuda, f"{name} must be CUDA (this backend has no CPU path)")
+    _assert(in_feat.is_contiguous(), f"{name} must be contiguous")
+    _assert(in_feat.dim() == 2, f"{name}.dim():", in_feat.dim())
+    _assert(manager.exists(in_key), ERROR_MAP_NOT_FOUND)
+    _assert(in_feat.size(0) == manager.size(in_key), "Invalid in_feat size", in_feat.size(0),
+            "!=", manager.size(in_key))
+
+
+def _workspace(n_in, n_out, c_in, c_out, K, code, device):
+    nbytes = int(_lib.load().meb200_conv_workspace_bytes(n_in, n_out, c_in, c_out, K, code))
+    if nbytes == 0:
+        return None, 0
+    return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
+
+
+def _conv_forward(in_feat, kernel, km, out_dtype=None):
+    lib = _lib.load()
+    code = _lib.dtype_code(in_feat.dtype)
+    if kernel.dtype != in_feat.dtype:
+        kernel = kernel.to(in_feat.dtype)
+    kernel = kernel.contiguous()
+    K, c_in, c_out = kernel.shape
+    _assert(K == km.K, "kernel volume", K, "does not match the kernel map", km.K)
+    n_out, n_in = km.n_out, km.n_in
+    out = torch.empty((n_out, c_out), dtype=out_dtype or in_feat.dtype, device=in_feat.device)
+    ws, ws_bytes = _workspace(n_in, n_out, c_in, c_out, K, code, in_feat.device)
+    _lib.check(lib.meb200_conv_forward(
+        _lib.ptr(in_feat), code, n_in, c_in, _lib.ptr(kernel), K, c_out, _lib.ptr(km.out_nbr),
+        n_out, _lib.ptr(out), _lib.dtype_code(out.dtype), _lib.ptr(ws), ws_bytes,
+        _lib.current_stream()))
+    return out
+
+
+def _conv_backward(in_feat, grad_out, kernel, km):
+    lib = _lib.load()
+    code = _lib.dtype_code(in_feat.dtype)
+    if grad_out.dtype != in_feat.dtype:
+        grad_out = grad_out.to(in_feat.dtype)
+    grad_out = grad_out.contiguous()
+    w = kernel if kernel.dtype == in_feat.dtype else kernel.to(in_feat.dtype)
+    w = w.contiguous()
+    K, c_in, c_out = w.shape
+    n_out, n_in = km.n_out, km.n_in
+    grad_in = torch.empty((n_in, c_in), dtype=in_feat.dtype, device=in_feat.device)
+    grad_w = torch.empty((K, c_in, c_out), dtype=torch.float32, device=in_feat.device)
+    ws, ws_bytes = _workspace(n_in, n_out, c_in, c_out, K, code, in_feat.device)
+    _lib.check(lib.meb200_conv_backward(
+        _lib.ptr(in_feat), _lib.ptr(grad_out), code, n_in, c_in, _lib.ptr(w), K, c_out,
+        _lib.ptr(km.out_nbr), _lib.ptr(km.in_nbr), n_out, _lib.ptr(grad_in), code,
+        _lib.ptr(grad_w), _lib.ptr(ws), ws_bytes, _lib.current_stream()))
+    if grad_w.dtype != kernel.dtype:
+        grad_w = grad_w.to(kernel.dtype)
+    return grad_in, grad_w
+
+
+def ConvolutionForwardGPU(in_feat, kernel, kernel_size, kernel_stride, kernel_dilation,
+                          region_type, offset, expand_coordinates, convolution_mode, in_key,
+                          out_key, manager):
+    """reference: ConvolutionForwardGPU src/convolution_gpu.cu:45-159 (CPU twin
+    convolution_cpu.cpp:42-135).  Mutates `out_key` when it is unset."""
+    _assert(kernel.dim() == 3, "kernel.dim():", kernel.dim())
+    _assert(kernel.is_cuda, "kernel must be CUDA")
+    _check_feats(in_feat, manager, in_key)
+    _assert(in_feat.size(1) == kernel.size(1), "Input feature size and kernel size mismatch")
+    if not out_key.is_key_set():
+        if expand_coordinates:
+            ik = manager._k(in_key)
+            out_ts = [t * int(s) for t, s in zip(ik[0], kernel_stride)]
+            ok, _ = manager._stride_region(in_key, region_type, kernel_size, kernel_dilation,
+                                           offset, ik[0], out_ts, False, True)
+        else:
+            ok, _ = manager._stride(in_key, kernel_stride)
+        out_key.set_key(list(ok[0]), ok[1])
+    km = manager._kernel_map(in_key, out_key, kernel_size, kernel_stride, kernel_dilation,
+                             region_type, offset, False, False)
+    return _conv_forward(in_feat, kernel, km)
+
+
+def ConvolutionBackwardGPU(in_feat, grad_out_feat, kernel, kernel_size, kernel_stride,
+                           kernel_dilation, region_type, offset, convolution_mode, in_key,
+                           out_key, manager):
+    """reference: ConvolutionBackwardGPU src/convolution_gpu.cu:161-244"""
+    _check_feats(in_feat, manager, in_key)
+    _assert(manager.exists(out_key), ERROR_MAP_NOT_FOUND)
+    _assert(grad_out_feat.size(0) == manager.size(out_key), "Invalid grad_out size")
+    km = manager._kernel_map(in_key, out_key, kernel_size, kernel_stride, kernel_dilation,
+                             region_type, offset, False, False)
+    return _conv_backward(in_feat, grad_out_feat, kernel, km)
+
+
+def ConvolutionTransposeForwardGPU(in_feat, kernel, kernel_size, kernel_stride,
+                                   kernel_dilation, region_type, offset,
+                                   generate_new_coordinates, convolution_mode, in_key, out_key,
+                                   manager):
+    """reference: src/convolution_transpose_gpu.cu (CPU twin convolution_transpose_cpu.cpp:42-125)"""
+    _assert(kernel.dim() == 3, "kernel.dim():", kernel.dim())
+    _check_feats(in_feat, manager, in_key)
+    _assert(in_feat.size(1) == kernel.size(1), "Input feature size and kernel size mismatch")
+    if not out_key.is_key_set():
+        ik = manager._k(in_key)
+        for t, s in zip(ik[0], kernel_stride):
+            _assert(t % int(s) == 0, "Invalid up stride on tensor stride:", list(ik[0]),
+                    "kernel stride:", list(kernel_stride))
+        out_ts = [t // int(s) for t, s in zip(ik[0], kernel_stride)]
+        ok, _ = manager._stride_region(in_key, region_type, kernel_size, kernel_dilation, offset,
+                                       out_ts, out_ts, True, generate_new_coordinates)
+        out_key.set_key(list(ok[0]), ok[1])
+    km = manager._kernel_map(in_key, out_key, kernel_size, kernel_stride, kernel_dilation,
+                             region_type, offset, True, False)
+    return _conv_forward(in_feat, kernel, km)
+
+
+def ConvolutionTransposeBackwardGPU(in_feat, grad_out_feat, kernel, kernel_size, kernel_stride,
+                                    kernel_dilation, region_type, offset, convolution_mode,
+                                    in_key, out_key, manager):
+    _check_feats(in_feat, manager, in_key)
+    _assert(manager.exists(out_key), ERROR_MAP_NOT_FOUND)
+    km = manager._kernel_map(in_key, out_key, kernel_size, kernel_stride, kernel_dilation,
+                             region_type, offset, True, False)
+    return _conv_backward(in_feat, grad_out_feat, kernel, km)
+
+
+_POOL_CODE = {PoolingMode.LOCAL_SUM_POOLING: _lib.POOL_SUM,
+              PoolingMode.LOCAL_AVG_POOLING: _lib.POOL_AVG,
+              PoolingMode.LOCAL_MAX_POOLING: _lib.POOL_MAX}
+
+
+def LocalPoolingForwardGPU(in_feat, kernel_size, kernel_stride, kernel_dilation, region_type,
+                           offset, pooling_mode, in_key, out_key, manager):
+    """reference: LocalPoolingForwardGPU src/local_pooling_gpu.cu:46-137 (CPU twin
+    local_pooling_cpu.cpp:43-120) -> (out_feat, num_nonzero | max_index)"""
+    _check_feats(in_feat, manager, in_key)
+    _assert(pooling_mode in _POOL_CODE, "Invalid pooling mode", pooling_mode)
+    if not out_key.is_key_set():
+        ok, _ = manager._stride(in_key, kernel_stride)
+        out_key.set_key(list(ok[0]), ok[1])
+    km = manager._kernel_map(in_key, out_key, kernel_size, kernel_stride, kernel_dilation,
+                             region_type, offset, False, True)
+    lib = _lib.load()
+    C = in_feat.size(1)
+    n_out = km.n_out
+    out = torch.empty((n_out, C), dtype=in_feat.dtype, device=in_feat.device)
+    mode = _POOL_CODE[pooling_mode]
+    if mode == _lib.POOL_MAX:
+        aux = torch.empty((n_out, C), dtype=torch.int32, device=in_feat.device)
+    elif mode == _lib.POOL_AVG:
+        aux = torch.empty(n_out, dtype=in_feat.dtype, device=in_feat.device)
+    else:
+        aux = torch.empty(0, dtype=in_feat.dtype, device=in_feat.device)
+    _lib.check(lib.meb200_pool_forward(
+        _lib.ptr(in_feat), _lib.dtype_code(in_feat.dtype), km.n_in, C, _lib.ptr(km.out_nbr),
+        km.K, n_out, mode, _lib.ptr(out), _lib.ptr(aux) if aux.numel() else None,
+        _lib.current_stream()))
+    return out, aux
+
+
+def LocalPoolingBackwardGPU(in_feat, grad_out_feat, num_nonzero, kernel_size, kernel_stride,
+                            kernel_dilation, region_type, offset, pooling_mode, in_key, out_key,
+                            manager):
+    """reference: LocalPoolingBackwardGPU src/local_pooling_gpu.cu:139-220"""
+    _check_feats(in_feat, manager, in_key)
+    _assert(manager.exists(out_key), ERROR_MAP_NOT_FOUND)
+    grad_out_feat = grad_out_feat.contiguous()
+    _assert(in_feat.dtype == grad_out_feat.dtype, "type mismatch")
+    km = manager._kernel_map(in_key, out_key, kernel_size, kernel_stride, kernel_dilation,
+                             region_type, offset, False, True)
+    lib = _lib.load()
+    C = in_feat.size(1)
+    mode = _POOL_CODE[pooling_mode]
+    if mode == _lib.POOL_MAX:
+        grad_in = torch.zeros_like(in_feat)
+    else:
+        grad_in = torch.empty_like(in_feat)
+    _lib.check(lib.meb200_pool_backward(
+        _lib.ptr(grad_out_feat), _lib.dtype_code(in_feat.dtype), km.n_in, C, _lib.ptr(km.in_nbr),
+        km.K, km.n_out, mode, _lib.ptr(num_nonzero) if num_nonzero.numel() else None,
+        _lib.ptr(grad_in), _lib.current_stream()))
+    return grad_in

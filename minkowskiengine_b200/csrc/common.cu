@@ -1,0 +1,47 @@
+// Library-level state: last error (per thread), launch counter, build facts.
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace meb200 {
+
+static thread_local char g_err[1024] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int num_sms() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      cached = 148;
+  }
+  return cached;
+}
+
+}  // namespace meb200
+
+extern "C" {
+
+const char *meb200_last_error(void) { return meb200::g_err; }
+
+const char *meb200_build_arch(void) { return "sm_100a"; }
+
+int meb200_cudart_version(void) { return CUDART_VERSION; }
+
+uint64_t meb200_launch_count(void) { return meb200::g_launches.load(std::memory_order_relaxed); }
+
+}

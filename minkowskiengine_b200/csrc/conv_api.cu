@@ -1,0 +1,85 @@
+// C-ABI entry points of the sparse convolution; picks the tcgen05 path when the shape
+// qualifies (conv_tc.cuh) and the SIMT path otherwise.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "conv_simt.cuh"
+#include "conv_tc.cuh"
+
+using namespace meb200;
+
+static bool tc_disabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("MEB200_DISABLE_TC");
+    v = (e && e[0] && e[0] != '0') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+extern "C" {
+
+uint64_t meb200_conv_workspace_bytes(uint32_t n_in, uint32_t n_out, uint32_t c_in,
+                                     uint32_t c_out, uint32_t K, int dtype) {
+  (void)n_in; (void)n_out;
+  if (dtype == MEB200_F32) return 0;
+  // bf16/fp16 weights re-laid out for the tensor-core kernels: W^T per offset
+  return (uint64_t)K * c_in * c_out * 2 + 256;
+}
+
+int meb200_conv_forward(const void *in, int in_dtype, uint32_t n_in, uint32_t c_in,
+                        const void *weight, uint32_t K, uint32_t c_out, const int32_t *out_nbr,
+                        uint32_t n_out, void *out, int out_dtype, void *workspace,
+                        uint64_t workspace_bytes, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n_out == 0) return MEB200_OK;
+  MEB_CHECK_ARG(in_dtype >= 0 && in_dtype <= 2 && out_dtype >= 0 && out_dtype <= 2, "dtype");
+  MEB_CHECK_ARG(out_dtype == MEB200_F32 || out_dtype == in_dtype,
+                "output dtype must be fp32 or the input dtype");
+  MEB_CHECK_ARG(out && weight && out_nbr && (in || n_in == 0), "null buffer");
+  MEB_CHECK_ARG(c_in > 0 && c_out > 0 && K > 0, "empty channel/kernel dims");
+  if (!tc_disabled() && conv_tc_supported(in_dtype, c_in, c_out) &&
+      workspace_bytes >= (uint64_t)K * c_in * c_out * 2) {
+    return conv_forward_tc(in, in_dtype, n_in, c_in, weight, K, c_out, /*dgrad=*/false, out_nbr,
+                           n_out, out, out_dtype, workspace, stream);
+  }
+  return conv_forward_simt(in, in_dtype, n_in, c_in, weight, K, c_out, /*trans_w=*/false,
+                           out_nbr, n_out, out, out_dtype, stream);
+}
+
+int meb200_conv_backward(const void *in, const void *grad_out, int dtype, uint32_t n_in,
+                         uint32_t c_in, const void *weight, uint32_t K, uint32_t c_out,
+                         const int32_t *out_nbr, const int32_t *in_nbr, uint32_t n_out,
+                         void *grad_in, int grad_in_dtype, float *grad_weight, void *workspace,
+                         uint64_t workspace_bytes, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MEB_CHECK_ARG(dtype >= 0 && dtype <= 2, "dtype");
+  MEB_CHECK_ARG(grad_in_dtype == MEB200_F32 || grad_in_dtype == dtype,
+                "grad_in dtype must be fp32 or the feature dtype");
+  MEB_CHECK_ARG(c_in > 0 && c_out > 0 && K > 0, "empty channel/kernel dims");
+  bool tc = !tc_disabled() && workspace_bytes >= (uint64_t)K * c_in * c_out * 2;
+  if (grad_in != nullptr && n_in > 0) {
+    MEB_CHECK_ARG(in_nbr && weight && (grad_out || n_out == 0), "null buffer");
+    // dgrad = the forward kernel on the transposed table with W_k^T:
+    // rows = input rows, reduction over c_out, produces c_in columns.
+    int rc;
+    if (tc && conv_tc_supported(dtype, c_out, c_in))
+      rc = conv_forward_tc(grad_out, dtype, n_out, c_out, weight, K, c_in, /*dgrad=*/true,
+                           in_nbr, n_in, grad_in, grad_in_dtype, workspace, stream);
+    else
+      rc = conv_forward_simt(grad_out, dtype, n_out, c_out, weight, K, c_in, /*trans_w=*/true,
+                             in_nbr, n_in, grad_in, grad_in_dtype, stream);
+    if (rc != MEB200_OK) return rc;
+  }
+  if (grad_weight != nullptr) {
+    MEB_CHECK_ARG(out_nbr && (in || n_in == 0) && (grad_out || n_out == 0), "null buffer");
+    if (tc && conv_wgrad_tc_supported(dtype, c_in, c_out))
+      return conv_wgrad_tc(in, grad_out, dtype, c_in, K, c_out, out_nbr, n_out, grad_weight,
+                           stream);
+    return conv_wgrad_simt(in, grad_out, dtype, c_in, K, c_out, out_nbr, n_out, grad_weight,
+                           stream);
+  }
+  return MEB200_OK;
+}
+
+}

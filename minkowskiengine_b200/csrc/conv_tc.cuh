@@ -1,0 +1,22 @@
+// tcgen05 (5th-gen tensor core, TMEM accumulator) sparse convolution kernels.
+#pragma once
+#include "common.cuh"
+
+namespace meb200 {
+
+// bf16/fp16 features with channel counts the UMMA tiles cover.
+bool conv_tc_supported(int dtype, uint32_t c_reduce, uint32_t c_cols);
+bool conv_wgrad_tc_supported(int dtype, uint32_t c_in, uint32_t c_out);
+
+// out[r,:] = sum_k A[nbr[k][r],:] @ Wk  with Wk = W[k] (forward) or W[k]^T (dgrad).
+// W is always the layer's [K, c_in, c_out] tensor; for dgrad c_reduce = c_out and
+// c_cols = c_in.  `workspace` receives the re-laid-out operand-B copy of W.
+int conv_forward_tc(const void *A, int dtype, uint32_t n_a, uint32_t c_reduce, const void *W,
+                    uint32_t K, uint32_t c_cols, bool dgrad, const int32_t *nbr, uint32_t n_rows,
+                    void *out, int out_dtype, void *workspace, cudaStream_t stream);
+
+int conv_wgrad_tc(const void *in, const void *grad_out, int dtype, uint32_t c_in, uint32_t K,
+                  uint32_t c_out, const int32_t *out_nbr, uint32_t n_out, float *grad_weight,
+                  cudaStream_t stream);
+
+}  // namespace meb200
