@@ -1,0 +1,90 @@
+"""tcgen05 (tensor-core) convolution path: bf16 / fp16 operands, fp32 accumulation.
+
+Parity definition for reduced-precision inputs (SURVEY.md §8a notes): the oracle is fed the
+SAME bf16/fp16-rounded features and weights; with fp32 accumulation the CUDA result then
+differs only by summation order (asserted 2e-5 relative with fp32 output) plus one final
+rounding when the output is stored in bf16/fp16 (2^-8 relative, asserted 6e-3 of max)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import kmap_lists, rel_err, unique_cloud
+from oracle import oracle_np as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch_ref_forward(feats, w, nbr):
+    """fp32 torch restatement on the device: sum_k feats[nbr[k]] @ w[k] (missing rows = 0)."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    K, n_out = nbr.shape
+    out = torch.zeros((n_out, w.shape[2]), dtype=torch.float32, device=feats.device)
+    f32, w32 = feats.float(), w.float()
+    for k in range(K):
+        idx = nbr[k].long()
+        valid = idx >= 0
+        g = f32[idx.clamp(min=0)] * valid.unsqueeze(1)
+        out += g @ w32[k]
+    return out
+
+
+def _random_table(K, n_out, n_in, density, seed, device):
+    g = torch.Generator().manual_seed(seed)
+    idx = torch.randint(0, n_in, (K, n_out), generator=g, dtype=torch.int32)
+    drop = torch.rand((K, n_out), generator=g) > density
+    idx[drop] = -1
+    return idx.to(device)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("cin,cout,n_in,n_out,K", [
+    (16, 16, 500, 100, 27),          # single partial tile, BK=16
+    (32, 32, 3000, 3001, 27),        # BK=32, R=4 super tiles with a ragged tail
+    (64, 128, 5000, 2000, 27),       # BASELINE cfg1 channel shape, BK=64
+    (96, 96, 4000, 4000, 27),        # MinkUNet34C stride-1 blocks (BK=32, N=96)
+    (128, 96, 4000, 1000, 8),
+    (192, 128, 1000, 1000, 27),
+    (384, 256, 700, 300, 27),        # widest concat layer, N=256 (R=1)
+    (256, 256, 300, 129, 27),
+    (32, 64, 90000, 90000, 8),       # more super tiles than SMs: persistent loop + phases
+])
+def test_tc_forward_matches_fp32_reference(ME, cuda, dtype, cin, cout, n_in, n_out, K):
+    from minkowskiengine_b200 import backend
+    g = torch.Generator().manual_seed(cin * 1000 + cout)
+    feats = (torch.rand(n_in, cin, generator=g) - 0.5).to(dtype).to(cuda)
+    w = ((torch.rand(K, cin, cout, generator=g) - 0.5) / (cin ** 0.5)).to(dtype).to(cuda)
+    nbr = _random_table(K, n_out, n_in, 0.35, seed=K + n_out, device=cuda)
+    km = backend._KernelMap(nbr, torch.empty((K, n_in), dtype=torch.int32, device=cuda))
+    ref = _torch_ref_forward(feats, w, nbr)
+    out32 = backend._conv_forward(feats, w, km, out_dtype=torch.float32)
+    scale = ref.abs().max().item()
+    assert (out32 - ref).abs().max().item() / scale < 2e-5
+    out_lp = backend._conv_forward(feats, w, km)
+    assert out_lp.dtype == dtype
+    assert (out_lp.float() - ref).abs().max().item() / scale < 6e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16])
+@pytest.mark.parametrize("cin,cout,ks,stride", [(32, 64, 3, 1), (64, 96, 3, 2), (96, 32, 2, 2)])
+def test_tc_layer_vs_oracle(ME, cuda, dtype, cin, cout, ks, stride):
+    """Through the public API (SparseTensor + MinkowskiConvolution, bf16 features), forward
+    and backward, against the numpy oracle fed the same rounded values."""
+    D = 3
+    coords = unique_cloud(6000, 24, seed=5, allow_negative=True)
+    g = torch.Generator().manual_seed(9)
+    feats = torch.rand(len(coords), cin, generator=g).to(dtype)
+    conv = ME.MinkowskiConvolution(cin, cout, kernel_size=ks, stride=stride, dimension=D).to(cuda)
+    x = ME.SparseTensor(feats, coords, device=cuda, requires_grad=True)
+    y = conv(x)
+    assert y.F.dtype == dtype
+    in_c, out_c = x.C.cpu().numpy(), y.C.cpu().numpy()
+    im, om = O.kernel_map(in_c, out_c, O.region_offsets(O.HYPER_CUBE, [ks] * D, [1] * D, [1] * D))
+    w = conv.kernel.detach().to(dtype).float().cpu().numpy()
+    f = feats.float().numpy()
+    ref = O.conv_forward(f, w, im, om, len(out_c))
+    assert rel_err(y.F.detach().float().cpu().numpy(), ref) < 6e-3
+    gout = (torch.rand(y.F.shape, generator=g) - 0.5).to(dtype)
+    y.F.backward(gout.to(cuda))
+    gi, gw = O.conv_backward(f, gout.float().numpy(), w, im, om)
+    assert rel_err(x.F.grad.float().cpu().numpy(), gi) < 6e-3       # bf16-stored dgrad
+    assert rel_err(conv.kernel.grad.float().cpu().numpy(), gw) < 1e-4   # fp32 wgrad
