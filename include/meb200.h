@@ -54,6 +54,8 @@ const char *meb200_build_arch(void);
 int meb200_cudart_version(void); /* reference: cudart_version(), pybind/extern.hpp:808-838 */
 /* Number of kernels this library has launched since load (bench.py's gpu_launches).   */
 uint64_t meb200_launch_count(void);
+/* ... of which launches of the tcgen05 (tensor-core) convolution kernels. */
+uint64_t meb200_tc_launch_count(void);
 
 /* ---- coordinate hashing (reference a1/a2: src/coordinate.hpp:223-349,
  *      CoordinateMapCPU::insert_and_map coordinate_map_cpu.hpp:353-380,

@@ -22,6 +22,7 @@ PROTOTYPES = {
     "meb200_build_arch": (C.c_char_p, []),
     "meb200_cudart_version": (_i32, []),
     "meb200_launch_count": (_u64, []),
+    "meb200_tc_launch_count": (_u64, []),
     "meb200_hash_capacity": (_u32, [_u32]),
     "meb200_insert_scratch_bytes": (_u64, [_u32]),
     "meb200_insert_and_map": (_i32, [_vp, _vp, _u32, _u32, _vp, _u32, _vp, _vp, _vp, _vp,
@@ -96,3 +97,7 @@ def current_stream():
 
 def launch_count():
     return int(load().meb200_launch_count())
+
+
+def tc_launch_count():
+    return int(load().meb200_tc_launch_count())

@@ -493,7 +493,7 @@ def _conv_forward(in_feat, kernel, km, out_dtype=None):
     return out
 
 
-def _conv_backward(in_feat, grad_out, kernel, km):
+def _conv_backward(in_feat, grad_out, kernel, km, need_in=True, need_w=True):
     lib = _lib.load()
     code = _lib.dtype_code(in_feat.dtype)
     if grad_out.dtype != in_feat.dtype:
@@ -503,14 +503,16 @@ def _conv_backward(in_feat, grad_out, kernel, km):
     w = w.contiguous()
     K, c_in, c_out = w.shape
     n_out, n_in = km.n_out, km.n_in
-    grad_in = torch.empty((n_in, c_in), dtype=in_feat.dtype, device=in_feat.device)
-    grad_w = torch.empty((K, c_in, c_out), dtype=torch.float32, device=in_feat.device)
+    grad_in = torch.empty((n_in, c_in), dtype=in_feat.dtype, device=in_feat.device) \
+        if need_in else None
+    grad_w = torch.empty((K, c_in, c_out), dtype=torch.float32, device=in_feat.device) \
+        if need_w else None
     ws, ws_bytes = _workspace(n_in, n_out, c_in, c_out, K, code, in_feat.device)
     _lib.check(lib.meb200_conv_backward(
         _lib.ptr(in_feat), _lib.ptr(grad_out), code, n_in, c_in, _lib.ptr(w), K, c_out,
         _lib.ptr(km.out_nbr), _lib.ptr(km.in_nbr), n_out, _lib.ptr(grad_in), code,
         _lib.ptr(grad_w), _lib.ptr(ws), ws_bytes, _lib.current_stream()))
-    if grad_w.dtype != kernel.dtype:
+    if grad_w is not None and grad_w.dtype != kernel.dtype:
         grad_w = grad_w.to(kernel.dtype)
     return grad_in, grad_w
 
@@ -540,14 +542,14 @@ def ConvolutionForwardGPU(in_feat, kernel, kernel_size, kernel_stride, kernel_di
 
 def ConvolutionBackwardGPU(in_feat, grad_out_feat, kernel, kernel_size, kernel_stride,
                            kernel_dilation, region_type, offset, convolution_mode, in_key,
-                           out_key, manager):
+                           out_key, manager, need_in=True, need_w=True):
     """reference: ConvolutionBackwardGPU src/convolution_gpu.cu:161-244"""
     _check_feats(in_feat, manager, in_key)
     _assert(manager.exists(out_key), ERROR_MAP_NOT_FOUND)
     _assert(grad_out_feat.size(0) == manager.size(out_key), "Invalid grad_out size")
     km = manager._kernel_map(in_key, out_key, kernel_size, kernel_stride, kernel_dilation,
                              region_type, offset, False, False)
-    return _conv_backward(in_feat, grad_out_feat, kernel, km)
+    return _conv_backward(in_feat, grad_out_feat, kernel, km, need_in, need_w)
 
 
 def ConvolutionTransposeForwardGPU(in_feat, kernel, kernel_size, kernel_stride,
@@ -574,12 +576,12 @@ def ConvolutionTransposeForwardGPU(in_feat, kernel, kernel_size, kernel_stride,
 
 def ConvolutionTransposeBackwardGPU(in_feat, grad_out_feat, kernel, kernel_size, kernel_stride,
                                     kernel_dilation, region_type, offset, convolution_mode,
-                                    in_key, out_key, manager):
+                                    in_key, out_key, manager, need_in=True, need_w=True):
     _check_feats(in_feat, manager, in_key)
     _assert(manager.exists(out_key), ERROR_MAP_NOT_FOUND)
     km = manager._kernel_map(in_key, out_key, kernel_size, kernel_stride, kernel_dilation,
                              region_type, offset, True, False)
-    return _conv_backward(in_feat, grad_out_feat, kernel, km)
+    return _conv_backward(in_feat, grad_out_feat, kernel, km, need_in, need_w)
 
 
 _POOL_CODE = {PoolingMode.LOCAL_SUM_POOLING: _lib.POOL_SUM,

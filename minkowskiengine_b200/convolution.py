@@ -45,7 +45,8 @@ class MinkowskiConvolutionFunction(Function):
         grad_in_feat, grad_kernel = _C.ConvolutionBackwardGPU(
             ctx.input_features, grad_out_feat, ctx.kernel_weights, kgen.kernel_size,
             kgen.kernel_stride, kgen.kernel_dilation, kgen.region_type, kgen.region_offsets,
-            mode, in_key, out_key, manager._manager)
+            mode, in_key, out_key, manager._manager,
+            need_in=ctx.needs_input_grad[0], need_w=ctx.needs_input_grad[1])
         return grad_in_feat, grad_kernel, None, None, None, None, None
 
 
@@ -78,7 +79,8 @@ class MinkowskiConvolutionTransposeFunction(Function):
         grad_in_feat, grad_kernel = _C.ConvolutionTransposeBackwardGPU(
             ctx.input_features, grad_out_feat, ctx.kernel_weights, kgen.kernel_size,
             kgen.kernel_stride, kgen.kernel_dilation, kgen.region_type, kgen.region_offsets,
-            mode, in_key, out_key, manager._manager)
+            mode, in_key, out_key, manager._manager,
+            need_in=ctx.needs_input_grad[0], need_w=ctx.needs_input_grad[1])
         return grad_in_feat, grad_kernel, None, None, None, None, None
 
 

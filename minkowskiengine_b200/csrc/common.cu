@@ -9,6 +9,7 @@ namespace meb200 {
 
 static thread_local char g_err[1024] = "";
 static std::atomic<uint64_t> g_launches{0};
+static std::atomic<uint64_t> g_tc_launches{0};
 
 void set_error(const char *fmt, ...) {
   va_list ap;
@@ -18,6 +19,8 @@ void set_error(const char *fmt, ...) {
 }
 
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+void count_tc_launch() { g_tc_launches.fetch_add(1, std::memory_order_relaxed); }
+uint64_t tc_launches() { return g_tc_launches.load(std::memory_order_relaxed); }
 
 int num_sms() {
   static int cached = 0;
@@ -43,5 +46,7 @@ const char *meb200_build_arch(void) { return "sm_100a"; }
 int meb200_cudart_version(void) { return CUDART_VERSION; }
 
 uint64_t meb200_launch_count(void) { return meb200::g_launches.load(std::memory_order_relaxed); }
+
+uint64_t meb200_tc_launch_count(void) { return meb200::tc_launches(); }
 
 }

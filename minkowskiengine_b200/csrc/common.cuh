@@ -15,6 +15,8 @@ constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 // ---- error plumbing ---------------------------------------------------------------
 void set_error(const char *fmt, ...);
 void count_launch(unsigned n = 1);
+void count_tc_launch();
+uint64_t tc_launches();
 
 #define MEB_CHECK_ARG(cond, ...)                                                         \
   do {                                                                                   \

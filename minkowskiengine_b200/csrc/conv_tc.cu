@@ -313,6 +313,7 @@ static int launch_tc(const TcParams &p, size_t smem_bytes, unsigned grid, cudaSt
     configured = true;
   }
   kern<<<grid, kThreads, smem_bytes, stream>>>(p);
+  count_tc_launch();
   MEB_LAUNCH_OK();
   return MEB200_OK;
 }
@@ -372,12 +373,258 @@ int conv_forward_tc(const void *A, int dtype, uint32_t n_a, uint32_t c_reduce, c
 #undef MEB_TC_LAUNCH
 }
 
-bool conv_wgrad_tc_supported(int, uint32_t, uint32_t) { return false; }
+// =====================================================================================
+// wgrad:  dW[k][ci][co] = sum_o In[nbr[k][o]][ci] * dOut[o][co]
+//
+// GEMM view: D[M = ci][N = co] += A[M][Kd] * B[Kd][N] with the reduction dim Kd = output rows.
+// Both operands are gathered/loaded as ROWS (one row = the channels of one voxel), i.e. they sit
+// in shared memory with the M / N dim contiguous: "MN-major" UMMA operands.  Physical layout per
+// 64-channel block: [rows][128 B] with the same 8-row / 128B-swizzle atoms as the forward tiles
+// (so the gather code is shared); LBO = distance between 64-channel blocks, SBO = 1024 B between
+// 8-row groups.  One CTA owns (a group of G offsets, a slice of the output rows, <= 2 m-tiles of
+// 128 input channels); the dOut chunk (operand B) is loaded once and reused for the G offsets,
+// each offset accumulating into its own TMEM accumulator; the epilogue adds the fp32 partials
+// into dW with red.global (dW is zero-filled first).
+// =====================================================================================
+constexpr int kWgRows = 64;                 // reduction rows per pipeline stage
+constexpr uint32_t kBlkBytes = kWgRows * 128;  // one 64-channel block of one stage
 
-int conv_wgrad_tc(const void *, const void *, int, uint32_t, uint32_t, uint32_t, const int32_t *,
-                  uint32_t, float *, cudaStream_t) {
-  set_error("tcgen05 wgrad path not built");
-  return MEB200_ERR_UNSUPPORTED;
+struct WgParams {
+  const void *in;        // [n_in, c_in]
+  const void *gout;      // [n_out, c_out]
+  const int32_t *nbr;    // [K, n_out]
+  float *dW;             // [K, c_in, c_out]
+  uint32_t c_in, c_out, K, n_out;
+  uint32_t G, n_kgroups, mt_cta, n_mtgroups, rows_per_split, n_splits;
+  uint32_t blkA, blkB;   // 64-channel blocks per A / B stage
+  uint32_t nA, nB, a_stage_bytes, b_stage_bytes;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(const WgParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sA = smem_u32(smem);
+  const uint32_t sB = sA + p.nA * p.a_stage_bytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + p.nA * p.a_stage_bytes +
+                                                p.nB * p.b_stage_bytes);
+  const uint32_t bar0 = smem_u32(bars);
+  auto fullA = [&](uint32_t i) { return bar0 + 8u * i; };
+  auto emptyA = [&](uint32_t i) { return bar0 + 8u * (kMaxStages + i); };
+  auto fullB = [&](uint32_t i) { return bar0 + 8u * (2 * kMaxStages + i); };
+  auto emptyB = [&](uint32_t i) { return bar0 + 8u * (3 * kMaxStages + i); };
+  const uint32_t tfull = bar0 + 8u * (4 * kMaxStages);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * kMaxStages + 4);
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // work item
+  uint32_t wi = blockIdx.x;
+  const uint32_t kg = wi % p.n_kgroups; wi /= p.n_kgroups;
+  const uint32_t mtg = wi % p.n_mtgroups; wi /= p.n_mtgroups;
+  const uint32_t split = wi;
+  const uint32_t k0 = kg * p.G;
+  const uint32_t G = min(p.G, p.K - k0);
+  const uint32_t r_begin = split * p.rows_per_split;
+  const uint32_t r_end = min(r_begin + p.rows_per_split, p.n_out);
+  const uint32_t n_chunks = (r_end - r_begin + kWgRows - 1) / kWgRows;
+  const uint32_t ch0 = mtg * p.mt_cta * 128;                 // first input channel of this CTA
+  const uint32_t mt = min(p.mt_cta, (p.c_in - ch0 + 127) / 128);  // m-tiles actually present
+
+  if (threadIdx.x == 0) {
+    for (uint32_t i = 0; i < p.nA; ++i) { mbar_init(fullA(i), kProducerWarps * 32); mbar_init(emptyA(i), 1); }
+    for (uint32_t i = 0; i < p.nB; ++i) { mbar_init(fullB(i), kProducerWarps * 32); mbar_init(emptyB(i), 1); }
+    mbar_init(tfull, 1);
+    mbar_fence_init();
+  }
+  if (warp == kProducerWarps + kEpilogueWarps) {
+    tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kProducerWarps) {
+    const uint32_t sub_row = lane >> 3, j8 = lane & 7;
+    const T *in = reinterpret_cast<const T *>(p.in);
+    const T *gout = reinterpret_cast<const T *>(p.gout);
+    uint32_t g = 0, signaled = 0;
+    auto signal = [&](uint32_t gd) {
+      fence_proxy_async();
+      mbar_arrive(fullA(gd % p.nA));
+      if (gd % G == 0) mbar_arrive(fullB((gd / G) % p.nB));
+    };
+    auto wait_empty = [&](uint32_t bar, uint32_t parity) {
+      if (mbar_try_wait(bar, parity)) return;
+      cp_async_wait<0>();
+      while (signaled < g) signal(signaled++);
+      mbar_wait(bar, parity);
+    };
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+      const uint32_t row0 = r_begin + c * kWgRows;
+      for (uint32_t kk = 0; kk < G; ++kk) {
+        const uint32_t sa = g % p.nA;
+        wait_empty(emptyA(sa), ((g / p.nA) & 1u) ^ 1u);
+        if (kk == 0) {
+          const uint32_t gb = g / G, sb = gb % p.nB;
+          wait_empty(emptyB(sb), ((gb / p.nB) & 1u) ^ 1u);
+          const uint32_t dstB = sB + sb * p.b_stage_bytes;
+          for (uint32_t blk = 0; blk < p.blkB; ++blk) {
+            const uint32_t chn = blk * 64 + j8 * 8;
+#pragma unroll
+            for (int it = 0; it < kWgRows / 16; ++it) {
+              const uint32_t row = it * 16 + warp * 4 + sub_row;
+              const uint32_t o = row0 + row;
+              const bool ok = (o < r_end) && (chn < p.c_out);
+              const T *src = gout + (ok ? ((size_t)o * p.c_out + chn) : 0);
+              cp_async16(dstB + blk * kBlkBytes + row * 128 + ((j8 ^ (row & 7u)) << 4), src,
+                         ok ? 16u : 0u);
+            }
+          }
+        }
+        const int32_t *nbr_k = p.nbr + (size_t)(k0 + kk) * p.n_out;
+        const uint32_t dstA = sA + sa * p.a_stage_bytes;
+        int32_t src_rows[kWgRows / 16];
+#pragma unroll
+        for (int it = 0; it < kWgRows / 16; ++it) {
+          const uint32_t o = row0 + it * 16 + warp * 4 + sub_row;
+          src_rows[it] = (o < r_end) ? __ldg(nbr_k + o) : -1;
+        }
+        for (uint32_t blk = 0; blk < p.blkA; ++blk) {
+          const uint32_t chn = ch0 + blk * 64 + j8 * 8;
+#pragma unroll
+          for (int it = 0; it < kWgRows / 16; ++it) {
+            const uint32_t row = it * 16 + warp * 4 + sub_row;
+            const bool ok = (src_rows[it] >= 0) && (chn < p.c_in);
+            const T *src = in + (ok ? ((size_t)src_rows[it] * p.c_in + chn) : 0);
+            cp_async16(dstA + blk * kBlkBytes + row * 128 + ((j8 ^ (row & 7u)) << 4), src,
+                       ok ? 16u : 0u);
+          }
+        }
+        cp_async_commit();
+        ++g;
+        if (g - signaled > (uint32_t)kLag) {
+          cp_async_wait<kLag>();
+          while (g - signaled > (uint32_t)kLag) signal(signaled++);
+        }
+      }
+    }
+    cp_async_wait<0>();
+    while (signaled < g) signal(signaled++);
+  } else if (warp < kProducerWarps + kEpilogueWarps) {
+    const uint32_t q = warp & 3u;
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    for (uint32_t kk = 0; kk < G; ++kk) {
+      for (uint32_t t = 0; t < mt; ++t) {
+        const uint32_t ci = ch0 + t * 128 + q * 32 + lane;
+        const uint32_t col0 = (kk * p.mt_cta + t) * p.c_out;
+        float *dst_row = p.dW + ((size_t)(k0 + kk) * p.c_in + ci) * p.c_out;
+        for (uint32_t c = 0; c < p.c_out; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((q * 32u) << 16) + col0 + c, v);
+          tmem_ld_wait();
+          if (ci < p.c_in && n_chunks > 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float f = __uint_as_float(v[i]);
+              if (f != 0.f) atomicAdd(dst_row + c + i, f);
+            }
+          }
+        }
+      }
+    }
+  } else if (lane == 0) {
+    const uint32_t idesc = umma_idesc_f16(Fmt<T>::v, kTileM, p.c_out, 1, 1);
+    const uint32_t lboA = kBlkBytes, lboB = kBlkBytes;
+    uint32_t g = 0;
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+      const uint32_t gb = g / G, sb = gb % p.nB;
+      mbar_wait(fullB(sb), (gb / p.nB) & 1u);
+      const uint32_t bbase = sB + sb * p.b_stage_bytes;
+      for (uint32_t kk = 0; kk < G; ++kk, ++g) {
+        const uint32_t sa = g % p.nA;
+        mbar_wait(fullA(sa), (g / p.nA) & 1u);
+        tc_fence_after();
+        const uint32_t abase = sA + sa * p.a_stage_bytes;
+        for (uint32_t t = 0; t < mt; ++t) {
+          const uint32_t d = tmem_base + (kk * p.mt_cta + t) * p.c_out;
+#pragma unroll
+          for (int j = 0; j < kWgRows / 16; ++j) {
+            uint64_t da = umma_desc(abase + t * 2 * kBlkBytes + j * 2048, lboA, 1024, 2);
+            uint64_t db = umma_desc(bbase + j * 2048, lboB, 1024, 2);
+            umma_f16(d, da, db, idesc, (c | (uint32_t)j) != 0u);
+          }
+        }
+        umma_commit(emptyA(sa));
+      }
+      umma_commit(emptyB(sb));
+    }
+    umma_commit(tfull);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kProducerWarps + kEpilogueWarps) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+bool conv_wgrad_tc_supported(int dtype, uint32_t c_in, uint32_t c_out) {
+  if (dtype != MEB200_BF16 && dtype != MEB200_F16) return false;
+  return c_in % 8 == 0 && c_in >= 16 && c_out % 16 == 0 && c_out >= 16 && c_out <= 256;
+}
+
+int conv_wgrad_tc(const void *in, const void *grad_out, int dtype, uint32_t c_in, uint32_t K,
+                  uint32_t c_out, const int32_t *out_nbr, uint32_t n_out, float *grad_weight,
+                  cudaStream_t stream) {
+  MEB_CUDA(cudaMemsetAsync(grad_weight, 0, (size_t)K * c_in * c_out * sizeof(float), stream));
+  if (n_out == 0 || K == 0) return MEB200_OK;
+  WgParams p{};
+  p.in = in; p.gout = grad_out; p.nbr = out_nbr; p.dW = grad_weight;
+  p.c_in = c_in; p.c_out = c_out; p.K = K; p.n_out = n_out;
+  const uint32_t mt_total = cdiv(c_in, 128);
+  p.mt_cta = mt_total < kTmemCols / c_out ? mt_total : kTmemCols / c_out;
+  if (p.mt_cta > 2) p.mt_cta = 2;
+  p.n_mtgroups = cdiv(mt_total, p.mt_cta);
+  p.G = kTmemCols / (p.mt_cta * c_out);
+  if (p.G > K) p.G = K;
+  if (p.G > 8) p.G = 8;
+  p.n_kgroups = cdiv(K, p.G);
+  p.blkA = p.mt_cta * 2;
+  p.blkB = cdiv(c_out, 64);
+  p.a_stage_bytes = p.blkA * kBlkBytes;
+  p.b_stage_bytes = p.blkB * kBlkBytes;
+  const uint32_t bar_bytes = (4 * kMaxStages + 4) * 8 + 16;
+  p.nB = 2;
+  uint32_t avail = kSmemBudget - p.nB * p.b_stage_bytes - bar_bytes - 1024;
+  p.nA = avail / p.a_stage_bytes;
+  if (p.nA > (uint32_t)kMaxStages) p.nA = kMaxStages;
+  MEB_CHECK_ARG(p.nA >= 4, "not enough shared memory for the wgrad A pipeline");
+  // row slices: ~2 waves of CTAs, each slice a multiple of the stage height
+  uint32_t base = p.n_kgroups * p.n_mtgroups;
+  uint32_t want = cdiv(2ull * num_sms(), base);
+  uint32_t max_splits = cdiv(n_out, 4 * kWgRows);
+  uint32_t splits = want < 1 ? 1 : (want > max_splits ? max_splits : want);
+  p.rows_per_split = cdiv(cdiv(n_out, splits), kWgRows) * kWgRows;
+  p.n_splits = cdiv(n_out, p.rows_per_split);
+  size_t smem_bytes = 1024 + (size_t)p.nA * p.a_stage_bytes + (size_t)p.nB * p.b_stage_bytes + bar_bytes;
+  unsigned grid = base * p.n_splits;
+  if (dtype == MEB200_BF16) {
+    static bool cfg = false;
+    if (!cfg) { MEB_CUDA(cudaFuncSetAttribute(k_wgrad_tc<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg = true; }
+    k_wgrad_tc<__nv_bfloat16><<<grid, kThreads, smem_bytes, stream>>>(p);
+  } else {
+    static bool cfg = false;
+    if (!cfg) { MEB_CUDA(cudaFuncSetAttribute(k_wgrad_tc<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg = true; }
+    k_wgrad_tc<__half><<<grid, kThreads, smem_bytes, stream>>>(p);
+  }
+  count_tc_launch();
+  MEB_LAUNCH_OK();
+  return MEB200_OK;
 }
 
 }  // namespace meb200

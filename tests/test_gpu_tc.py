@@ -88,3 +88,37 @@ def test_tc_layer_vs_oracle(ME, cuda, dtype, cin, cout, ks, stride):
     gi, gw = O.conv_backward(f, gout.float().numpy(), w, im, om)
     assert rel_err(x.F.grad.float().cpu().numpy(), gi) < 6e-3       # bf16-stored dgrad
     assert rel_err(conv.kernel.grad.float().cpu().numpy(), gw) < 1e-4   # fp32 wgrad
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("cin,cout,n_in,n_out,K", [
+    (16, 16, 500, 100, 27),
+    (32, 32, 3000, 3001, 27),
+    (64, 128, 5000, 2000, 27),
+    (96, 96, 4000, 4000, 27),       # N = 96: one and a half 64-channel blocks
+    (128, 96, 4000, 1000, 8),
+    (192, 128, 1000, 1000, 27),     # two m-tiles (128 + 64 padded)
+    (384, 256, 700, 300, 27),       # three m-tiles -> two m-tile groups
+    (256, 256, 300, 129, 27),
+    (24, 48, 777, 333, 5),          # channel counts that are not multiples of 16 / 64
+    (32, 64, 60000, 60000, 8),
+])
+def test_tc_wgrad_matches_fp32_reference(ME, cuda, dtype, cin, cout, n_in, n_out, K):
+    from minkowskiengine_b200 import _lib, backend
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator().manual_seed(cin * 77 + cout)
+    feats = (torch.rand(n_in, cin, generator=g) - 0.5).to(dtype).to(cuda)
+    gout = (torch.rand(n_out, cout, generator=g) - 0.5).to(dtype).to(cuda)
+    w = torch.zeros(K, cin, cout, dtype=torch.float32, device=cuda)   # fp32 master weights
+    nbr = _random_table(K, n_out, n_in, 0.35, seed=K + n_out + 1, device=cuda)
+    km = backend._KernelMap(nbr, torch.full((K, n_in), -1, dtype=torch.int32, device=cuda))
+    before = _lib.tc_launch_count()
+    _, gw = backend._conv_backward(feats, gout, w, km, need_in=False, need_w=True)
+    assert _lib.tc_launch_count() > before, "wgrad did not take the tcgen05 path"
+    ref = torch.zeros(K, cin, cout, dtype=torch.float32, device=cuda)
+    f32, g32 = feats.float(), gout.float()
+    for k in range(K):
+        idx = nbr[k].long()
+        valid = (idx >= 0).unsqueeze(1)
+        ref[k] = (f32[idx.clamp(min=0)] * valid).t() @ g32
+    assert (gw.float() - ref).abs().max().item() / ref.abs().max().item() < 2e-5
