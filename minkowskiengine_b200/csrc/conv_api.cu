@@ -40,8 +40,14 @@ int meb200_conv_forward(const void *in, int in_dtype, uint32_t n_in, uint32_t c_
   MEB_CHECK_ARG(c_in > 0 && c_out > 0 && K > 0, "empty channel/kernel dims");
   if (!tc_disabled() && conv_tc_supported(in_dtype, c_in, c_out) &&
       workspace_bytes >= (uint64_t)K * c_in * c_out * 2) {
-    return conv_forward_tc(in, in_dtype, n_in, c_in, weight, K, c_out, /*dgrad=*/false, out_nbr,
-                           n_out, out, out_dtype, workspace, stream);
+    int rc = conv_forward_tc(in, in_dtype, n_in, c_in, weight, K, c_out, /*dgrad=*/false,
+                             out_nbr, n_out, out, out_dtype, workspace, stream);
+    if (rc != MEB200_ERR_UNSUPPORTED) return rc;
+  }
+  if (conv_small_cin_supported(c_in, c_out)) {
+    int rc = conv_small_cin_forward(in, in_dtype, c_in, weight, K, c_out, out_nbr, n_out, out,
+                                    out_dtype, stream);
+    if (rc != MEB200_ERR_UNSUPPORTED) return rc;
   }
   return conv_forward_simt(in, in_dtype, n_in, c_in, weight, K, c_out, /*trans_w=*/false,
                            out_nbr, n_out, out, out_dtype, stream);
@@ -62,20 +68,25 @@ int meb200_conv_backward(const void *in, const void *grad_out, int dtype, uint32
     MEB_CHECK_ARG(in_nbr && weight && (grad_out || n_out == 0), "null buffer");
     // dgrad = the forward kernel on the transposed table with W_k^T:
     // rows = input rows, reduction over c_out, produces c_in columns.
-    int rc;
+    int rc = MEB200_ERR_UNSUPPORTED;
     if (tc && conv_tc_supported(dtype, c_out, c_in))
       rc = conv_forward_tc(grad_out, dtype, n_out, c_out, weight, K, c_in, /*dgrad=*/true,
                            in_nbr, n_in, grad_in, grad_in_dtype, workspace, stream);
-    else
+    if (rc == MEB200_ERR_UNSUPPORTED)
       rc = conv_forward_simt(grad_out, dtype, n_out, c_out, weight, K, c_in, /*trans_w=*/true,
                              in_nbr, n_in, grad_in, grad_in_dtype, stream);
     if (rc != MEB200_OK) return rc;
   }
   if (grad_weight != nullptr) {
     MEB_CHECK_ARG(out_nbr && (in || n_in == 0) && (grad_out || n_out == 0), "null buffer");
-    if (tc && conv_wgrad_tc_supported(dtype, c_in, c_out))
-      return conv_wgrad_tc(in, grad_out, dtype, c_in, K, c_out, out_nbr, n_out, grad_weight,
-                           stream);
+    if (tc && conv_wgrad_tc_supported(dtype, c_in, c_out)) {
+      int rc = conv_wgrad_tc(in, grad_out, dtype, c_in, K, c_out, out_nbr, n_out, grad_weight,
+                             stream);
+      if (rc != MEB200_ERR_UNSUPPORTED) return rc;
+    }
+    if (conv_small_cin_supported(c_in, c_out))
+      return conv_small_cin_wgrad(in, grad_out, dtype, c_in, K, c_out, out_nbr, n_out,
+                                  grad_weight, stream);
     return conv_wgrad_simt(in, grad_out, dtype, c_in, K, c_out, out_nbr, n_out, grad_weight,
                            stream);
   }

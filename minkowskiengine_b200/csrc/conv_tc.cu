@@ -19,19 +19,20 @@
 // ring in TMEM (acc_stages x R accumulators of c_cols columns).
 #include "conv_tc.cuh"
 #include "ptx.cuh"
+#include "tc_config.h"
 
 namespace meb200 {
 
 using namespace ptx;
 
-constexpr int kTileM = 128;
+using tc::kTileM;
+using tc::kMaxStages;
+using tc::kTmemCols;
+using tc::kWgRows;
+using tc::kBlkBytes;
 constexpr int kProducerWarps = 4;
 constexpr int kEpilogueWarps = 4;
 constexpr int kThreads = (kProducerWarps + kEpilogueWarps + 1) * 32;
-constexpr int kMaxStages = 12;
-constexpr int kLag = 3;  // cp.async groups kept in flight per producer thread
-constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kSmemBudget = 200 * 1024;
 
 struct TcParams {
   const void *A;        // [n_a, c_red] gathered operand
@@ -42,7 +43,33 @@ struct TcParams {
   uint32_t n_super, R, acc_stages, nA, nB;
   uint32_t a_stage_bytes, b_stage_bytes;
   uint32_t out_f32;
+  uint32_t lag;          // cp.async groups each producer thread keeps in flight
+  uint32_t wb_k_stride;  // elements between consecutive offsets in Wb
+  uint32_t out_ld;       // leading dimension (elements) of `out`
 };
+
+// cp.async.wait_group takes an immediate: dispatch the few depths we use.
+__device__ __forceinline__ void cp_async_wait_dyn(uint32_t n) {
+  switch (n) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    case 4: cp_async_wait<4>(); break;
+    case 5: cp_async_wait<5>(); break;
+    case 6: cp_async_wait<6>(); break;
+    case 7: cp_async_wait<7>(); break;
+    case 8: cp_async_wait<8>(); break;
+    case 9: cp_async_wait<9>(); break;
+    case 10: cp_async_wait<10>(); break;
+    case 11: cp_async_wait<11>(); break;
+    case 12: cp_async_wait<12>(); break;
+    case 13: cp_async_wait<13>(); break;
+    case 14: cp_async_wait<14>(); break;
+    case 15: cp_async_wait<15>(); break;
+    default: cp_async_wait<16>(); break;
+  }
+}
 
 template <int BK>
 struct Swz {
@@ -76,7 +103,7 @@ __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
   return *reinterpret_cast<uint32_t *>(&h);
 }
 
-template <typename T, int BK>
+template <typename T, int BK, int RT>
 __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const TcParams p) {
   using S = Swz<BK>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -99,7 +126,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const TcParams p) {
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t chunks_red = p.c_red / BK;
-  const uint32_t R = p.R;
+  constexpr uint32_t R = RT;
 
   if (threadIdx.x == 0) {
     for (uint32_t i = 0; i < p.nA; ++i) {
@@ -131,72 +158,76 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const TcParams p) {
     const T *A = reinterpret_cast<const T *>(p.A);
     const T *Wb = reinterpret_cast<const T *>(p.Wb);
     const uint32_t iters_b = (p.c_cols + S::kRowsPerIter - 1) / S::kRowsPerIter;
-    uint32_t g = 0;         // A-stage groups committed so far (one cp.async group each)
-    uint32_t signaled = 0;  // groups already published to the MMA warp
-
-    auto signal = [&](uint32_t gd) {  // group gd has landed in smem
-      fence_proxy_async();
-      mbar_arrive(fullA(gd % p.nA));
-      if (gd % R == 0) mbar_arrive(fullB((gd / R) % p.nB));
+    // ring positions and use-parities, advanced incrementally (no div/mod on the hot path)
+    uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
+    // Neighbour rows this thread gathers for (super tile st, offset k): fetched one offset
+    // AHEAD of use so the table latency never sits between two pipeline stages.
+    int32_t idx_cur[RT][S::kItersA], idx_nxt[RT][S::kItersA];
+    auto load_idx = [&](uint32_t st, uint32_t k, int32_t (&dst)[RT][S::kItersA]) {
+      const int32_t *nbr_k = p.nbr + (size_t)k * p.n_rows;
+#pragma unroll
+      for (int r = 0; r < RT; ++r)
+#pragma unroll
+        for (int j = 0; j < S::kItersA; ++j) {
+          uint32_t grow = (st * R + r) * kTileM + j * S::kRowsPerIter + warp * S::kRowsPerInstr + sub_row;
+          dst[r][j] = (grow < p.n_rows) ? __ldg(nbr_k + grow) : -1;
+        }
     };
-    // Wait for a stage to be recycled.  If the consumer is behind, first publish everything
-    // this thread still holds back (the consumer may need exactly those groups to progress).
-    auto wait_empty = [&](uint32_t bar, uint32_t parity) {
-      if (mbar_try_wait(bar, parity)) return;
-      cp_async_wait<0>();
-      while (signaled < g) signal(signaled++);
-      mbar_wait(bar, parity);
-    };
+    if (blockIdx.x < p.n_super) load_idx(blockIdx.x, 0, idx_cur);
 
     for (uint32_t st = blockIdx.x; st < p.n_super; st += gridDim.x) {
-      const uint32_t row_base = st * R * kTileM;
       for (uint32_t k = 0; k < p.K; ++k) {
-        const int32_t *nbr_k = p.nbr + (size_t)k * p.n_rows;
+        {  // prefetch the indices of the next (super tile, offset)
+          uint32_t nst = st, nk = k + 1;
+          if (nk == p.K) { nk = 0; nst = st + gridDim.x; }
+          if (nst < p.n_super) load_idx(nst, nk, idx_nxt);
+        }
         for (uint32_t cc = 0; cc < chunks_red; ++cc) {
           const uint32_t c0 = cc * BK;
-          for (uint32_t r = 0; r < R; ++r) {
-            const uint32_t sa = g % p.nA;
-            wait_empty(emptyA(sa), ((g / p.nA) & 1u) ^ 1u);
+#pragma unroll
+          for (int r = 0; r < RT; ++r) {
+            mbar_wait(emptyA(sa), pha ^ 1u);
             if (r == 0) {
-              const uint32_t gb = g / R, sb = gb % p.nB;
-              wait_empty(emptyB(sb), ((gb / p.nB) & 1u) ^ 1u);
+              mbar_wait(emptyB(sb), phb ^ 1u);
               const uint32_t dstB = sB + sb * p.b_stage_bytes;
               for (uint32_t j = 0; j < iters_b; ++j) {
                 uint32_t n = j * S::kRowsPerIter + warp * S::kRowsPerInstr + sub_row;
                 if (n < p.c_cols) {
-                  const T *src = Wb + ((size_t)k * p.c_cols + n) * p.c_red + c0 + chunk * 8;
+                  const T *src = Wb + (size_t)k * p.wb_k_stride + (size_t)n * p.c_red + c0 + chunk * 8;
                   cp_async16(dstB + S::offset(n, chunk), src, 16);
                 }
               }
             }
             const uint32_t dstA = sA + sa * p.a_stage_bytes;
-            const uint32_t tile_row0 = row_base + r * kTileM;
 #pragma unroll
             for (int j = 0; j < S::kItersA; ++j) {
-              uint32_t row = j * S::kRowsPerIter + warp * S::kRowsPerInstr + sub_row;
-              uint32_t grow = tile_row0 + row;
-              int32_t src_row = (grow < p.n_rows) ? __ldg(nbr_k + grow) : -1;
+              const uint32_t row = j * S::kRowsPerIter + warp * S::kRowsPerInstr + sub_row;
+              const int32_t src_row = idx_cur[r][j];
               const T *src = A + (size_t)(src_row < 0 ? 0 : src_row) * p.c_red + c0 + chunk * 8;
               cp_async16(dstA + S::offset(row, chunk), src, src_row < 0 ? 0u : 16u);
             }
-            cp_async_commit();
-            ++g;
-            if (g - signaled > (uint32_t)kLag) {
-              cp_async_wait<kLag>();          // all but the newest kLag groups have landed
-              while (g - signaled > (uint32_t)kLag) signal(signaled++);
+            // publish: the barriers fire once this thread's copies for the stage have landed
+            if (r == 0) {
+              cp_async_mbar_arrive(fullB(sb));
+              if (++sb == p.nB) { sb = 0; phb ^= 1u; }
             }
+            cp_async_mbar_arrive(fullA(sa));
+            if (++sa == p.nA) { sa = 0; pha ^= 1u; }
           }
         }
+#pragma unroll
+        for (int r = 0; r < RT; ++r)
+#pragma unroll
+          for (int j = 0; j < S::kItersA; ++j) idx_cur[r][j] = idx_nxt[r][j];
       }
     }
-    cp_async_wait<0>();
-    while (signaled < g) signal(signaled++);
+    cp_async_wait<0>();  // nothing of this thread may still be in flight at teardown
   } else if (warp < kProducerWarps + kEpilogueWarps) {
     // =============================== EPILOGUE =======================================
     const uint32_t q = warp & 3u;  // TMEM lane quadrant this warp may access
     uint32_t t = 0;
     for (uint32_t st = blockIdx.x; st < p.n_super; st += gridDim.x, ++t) {
-      const uint32_t acc = t % p.acc_stages, par = (t / p.acc_stages) & 1u;
+      const uint32_t acc = t & 1u, par = (t >> 1) & 1u;   // two accumulator sets
       mbar_wait(tfull(acc), par);
       tc_fence_after();
       for (uint32_t r = 0; r < R; ++r) {
@@ -209,14 +240,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const TcParams p) {
           if (row < p.n_rows) {
             if (p.out_f32) {
               float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) +
-                                                       (size_t)row * p.c_cols + c);
+                                                       (size_t)row * p.out_ld + c);
 #pragma unroll
               for (int i = 0; i < 4; ++i)
                 dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
                                      __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
             } else {
               uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<T *>(p.out) +
-                                                     (size_t)row * p.c_cols + c);
+                                                     (size_t)row * p.out_ld + c);
 #pragma unroll
               for (int i = 0; i < 2; ++i) {
                 uint4 w;
@@ -236,19 +267,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const TcParams p) {
   } else if (lane == 0) {
     // =============================== MMA ISSUER =====================================
     const uint32_t idesc = umma_idesc_f16(Fmt<T>::v, kTileM, p.c_cols, 0, 0);
-    uint32_t g = 0, t = 0;
+    uint32_t t = 0, sa = 0, pha = 0, sb = 0, phb = 0;
     for (uint32_t st = blockIdx.x; st < p.n_super; st += gridDim.x, ++t) {
-      const uint32_t acc = t % p.acc_stages, par = (t / p.acc_stages) & 1u;
+      const uint32_t acc = t & 1u, par = (t >> 1) & 1u;
       mbar_wait(tempty(acc), par ^ 1u);
       tc_fence_after();
       for (uint32_t k = 0; k < p.K; ++k) {
         for (uint32_t cc = 0; cc < chunks_red; ++cc) {
-          const uint32_t gb = g / R, sb = gb % p.nB;
-          mbar_wait(fullB(sb), (gb / p.nB) & 1u);
+          mbar_wait(fullB(sb), phb);
           const uint32_t bbase = sB + sb * p.b_stage_bytes;
-          for (uint32_t r = 0; r < R; ++r, ++g) {
-            const uint32_t sa = g % p.nA;
-            mbar_wait(fullA(sa), (g / p.nA) & 1u);
+#pragma unroll
+          for (int r = 0; r < RT; ++r) {
+            mbar_wait(fullA(sa), pha);
             tc_fence_after();
             const uint32_t abase = sA + sa * p.a_stage_bytes;
             const uint32_t d = tmem_base + (acc * R + r) * p.c_cols;
@@ -259,8 +289,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const TcParams p) {
               umma_f16(d, da, db, idesc, (k | cc | (uint32_t)j) != 0u);
             }
             umma_commit(emptyA(sa));
+            if (++sa == p.nA) { sa = 0; pha ^= 1u; }
           }
           umma_commit(emptyB(sb));
+          if (++sb == p.nB) { sb = 0; phb ^= 1u; }
         }
       }
       umma_commit(tfull(acc));
@@ -298,15 +330,9 @@ static int pick_bk(uint32_t c_red) {
   return 0;
 }
 
-bool conv_tc_supported(int dtype, uint32_t c_reduce, uint32_t c_cols) {
-  if (dtype != MEB200_BF16 && dtype != MEB200_F16) return false;
-  if (pick_bk(c_reduce) == 0) return false;
-  return c_cols % 16 == 0 && c_cols >= 16 && c_cols <= 256;
-}
-
-template <typename T, int BK>
+template <typename T, int BK, int RT>
 static int launch_tc(const TcParams &p, size_t smem_bytes, unsigned grid, cudaStream_t stream) {
-  auto kern = k_conv_tc<T, BK>;
+  auto kern = k_conv_tc<T, BK, RT>;
   static bool configured = false;
   if (!configured) {
     MEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -318,14 +344,64 @@ static int launch_tc(const TcParams &p, size_t smem_bytes, unsigned grid, cudaSt
   return MEB200_OK;
 }
 
+template <typename T>
+static int launch_tc_bk_r(int bk, uint32_t R, const TcParams &p, size_t smem, unsigned grid,
+                          cudaStream_t s) {
+#define MEB_TC_R(BKV)                                                   \
+  switch (R) {                                                          \
+    case 4: return launch_tc<T, BKV, 4>(p, smem, grid, s);              \
+    case 2: return launch_tc<T, BKV, 2>(p, smem, grid, s);              \
+    default: return launch_tc<T, BKV, 1>(p, smem, grid, s);             \
+  }
+  switch (bk) {
+    case 64: MEB_TC_R(64)
+    case 32: MEB_TC_R(32)
+    default: MEB_TC_R(16)
+  }
+#undef MEB_TC_R
+}
+
+// One launch over output columns [0, c_cols) of a problem whose B operand / output may be
+// slices of wider tensors (N-splitting for c_cols > 256).
+static int launch_tc_slice(const void *A, int dtype, uint32_t c_reduce, const void *Wb,
+                           uint32_t wb_k_stride, uint32_t K, uint32_t c_cols, const int32_t *nbr,
+                           uint32_t n_rows, void *out, uint32_t out_ld, int out_dtype,
+                           cudaStream_t stream) {
+  TcParams p{};
+  p.A = A; p.Wb = Wb; p.nbr = nbr; p.out = out;
+  p.c_red = c_reduce; p.c_cols = c_cols; p.K = K; p.n_rows = n_rows;
+  p.out_f32 = out_dtype == MEB200_F32;
+  p.wb_k_stride = wb_k_stride; p.out_ld = out_ld;
+  const tc::FwdCfg cfg = tc::fwd_config(c_reduce, c_cols, n_rows);
+  if (cfg.bk == 0 || cfg.pipe.lag < 1) {
+    set_error("conv tc: no pipeline configuration fits (c_red=%u c_cols=%u)", c_reduce, c_cols);
+    return MEB200_ERR_UNSUPPORTED;
+  }
+  const int bk = cfg.bk;
+  const uint32_t R = cfg.R;
+  p.R = R; p.acc_stages = 2; p.n_super = cfg.n_super;
+  p.a_stage_bytes = cfg.a_stage_bytes; p.b_stage_bytes = cfg.b_stage_bytes;
+  p.lag = cfg.pipe.lag; p.nA = cfg.pipe.nA; p.nB = cfg.pipe.nB;
+  size_t smem_bytes = cfg.smem_bytes;
+  unsigned grid = p.n_super < (uint32_t)num_sms() ? p.n_super : (unsigned)num_sms();
+  if (dtype == MEB200_BF16)
+    return launch_tc_bk_r<__nv_bfloat16>(bk, R, p, smem_bytes, grid, stream);
+  return launch_tc_bk_r<__half>(bk, R, p, smem_bytes, grid, stream);
+}
+
+bool conv_tc_supported(int dtype, uint32_t c_reduce, uint32_t c_cols) {
+  if (dtype != MEB200_BF16 && dtype != MEB200_F16) return false;
+  if (pick_bk(c_reduce) == 0) return false;
+  return c_cols % 16 == 0 && c_cols >= 16 && c_cols <= 1024;
+}
+
 int conv_forward_tc(const void *A, int dtype, uint32_t n_a, uint32_t c_reduce, const void *W,
                     uint32_t K, uint32_t c_cols, bool dgrad, const int32_t *nbr, uint32_t n_rows,
                     void *out, int out_dtype, void *workspace, cudaStream_t stream) {
   (void)n_a;
   if (n_rows == 0) return MEB200_OK;
-  const int bk = pick_bk(c_reduce);
-  MEB_CHECK_ARG(bk != 0 && c_cols % 16 == 0 && c_cols <= 256, "shape not supported by tc path");
-  const void *Wb = W;
+  MEB_CHECK_ARG(conv_tc_supported(dtype, c_reduce, c_cols), "shape not supported by tc path");
+  const uint8_t *Wb = reinterpret_cast<const uint8_t *>(W);
   if (!dgrad) {
     // forward: B_k = W[k]^T so that the reduction dim (c_in) is contiguous
     MEB_CHECK_ARG(workspace != nullptr, "workspace required");
@@ -337,40 +413,19 @@ int conv_forward_tc(const void *A, int dtype, uint32_t n_a, uint32_t c_reduce, c
       k_transpose_w<__half><<<grid, 256, 0, stream>>>((const __half *)W, (__half *)workspace,
                                                      c_reduce, c_cols);
     MEB_LAUNCH_OK();
-    Wb = workspace;
+    Wb = reinterpret_cast<const uint8_t *>(workspace);
   }
-  TcParams p{};
-  p.A = A; p.Wb = Wb; p.nbr = nbr; p.out = out;
-  p.c_red = c_reduce; p.c_cols = c_cols; p.K = K; p.n_rows = n_rows;
-  p.out_f32 = out_dtype == MEB200_F32;
-  // accumulators: R row tiles share one B slice; double-buffer the set when it fits in TMEM
-  uint32_t R = kTmemCols / (2 * c_cols);
-  if (R > 4) R = 4;
-  uint32_t acc_stages = 2;
-  if (R == 0) { R = 1; acc_stages = kTmemCols / c_cols >= 2 ? 2 : 1; }
-  uint32_t tiles = cdiv(n_rows, kTileM);
-  if (R > tiles) R = tiles;
-  p.R = R; p.acc_stages = acc_stages;
-  p.n_super = cdiv(tiles, R);
-  p.a_stage_bytes = kTileM * bk * 2;
-  p.b_stage_bytes = ((c_cols * bk * 2 + 1023) / 1024) * 1024;
-  p.nB = 3;
-  const uint32_t bar_bytes = (4 * kMaxStages + 4) * 8 + 16;
-  uint32_t avail = kSmemBudget - p.nB * p.b_stage_bytes - bar_bytes - 1024;
-  p.nA = avail / p.a_stage_bytes;
-  if (p.nA > (uint32_t)kMaxStages) p.nA = kMaxStages;
-  MEB_CHECK_ARG(p.nA >= 4, "not enough shared memory for the A pipeline");
-  size_t smem_bytes = 1024 + (size_t)p.nA * p.a_stage_bytes + (size_t)p.nB * p.b_stage_bytes + bar_bytes;
-  unsigned grid = p.n_super < (uint32_t)num_sms() ? p.n_super : (unsigned)num_sms();
-#define MEB_TC_LAUNCH(TT)                                                          \
-  switch (bk) {                                                                    \
-    case 64: return launch_tc<TT, 64>(p, smem_bytes, grid, stream);                \
-    case 32: return launch_tc<TT, 32>(p, smem_bytes, grid, stream);                \
-    default: return launch_tc<TT, 16>(p, smem_bytes, grid, stream);                \
+  // operand B is [K, c_cols, c_reduce]; split the column range in slices of <= 256
+  const size_t out_esz = out_dtype == MEB200_F32 ? 4 : 2;
+  for (uint32_t n0 = 0; n0 < c_cols; n0 += 256) {
+    uint32_t nc = c_cols - n0 < 256 ? c_cols - n0 : 256;
+    int rc = launch_tc_slice(A, dtype, c_reduce, Wb + (size_t)n0 * c_reduce * 2,
+                             c_cols * c_reduce, K, nc, nbr, n_rows,
+                             reinterpret_cast<uint8_t *>(out) + (size_t)n0 * out_esz, c_cols,
+                             out_dtype, stream);
+    if (rc != MEB200_OK) return rc;
   }
-  if (dtype == MEB200_BF16) { MEB_TC_LAUNCH(__nv_bfloat16) }
-  MEB_TC_LAUNCH(__half)
-#undef MEB_TC_LAUNCH
+  return MEB200_OK;
 }
 
 // =====================================================================================
@@ -386,8 +441,6 @@ int conv_forward_tc(const void *A, int dtype, uint32_t n_a, uint32_t c_reduce, c
 // each offset accumulating into its own TMEM accumulator; the epilogue adds the fp32 partials
 // into dW with red.global (dW is zero-filled first).
 // =====================================================================================
-constexpr int kWgRows = 64;                 // reduction rows per pipeline stage
-constexpr uint32_t kBlkBytes = kWgRows * 128;  // one 64-channel block of one stage
 
 struct WgParams {
   const void *in;        // [n_in, c_in]
@@ -398,6 +451,7 @@ struct WgParams {
   uint32_t G, n_kgroups, mt_cta, n_mtgroups, rows_per_split, n_splits;
   uint32_t blkA, blkB;   // 64-channel blocks per A / B stage
   uint32_t nA, nB, a_stage_bytes, b_stage_bytes;
+  uint32_t lag;
 };
 
 template <typename T>
@@ -450,26 +504,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(const WgParams p) {
     const uint32_t sub_row = lane >> 3, j8 = lane & 7;
     const T *in = reinterpret_cast<const T *>(p.in);
     const T *gout = reinterpret_cast<const T *>(p.gout);
-    uint32_t g = 0, signaled = 0;
-    auto signal = [&](uint32_t gd) {
-      fence_proxy_async();
-      mbar_arrive(fullA(gd % p.nA));
-      if (gd % G == 0) mbar_arrive(fullB((gd / G) % p.nB));
+    uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
+    // neighbour rows for (chunk c, offset kk), fetched one work item ahead of use
+    int32_t idx_cur[kWgRows / 16], idx_nxt[kWgRows / 16];
+    auto load_idx = [&](uint32_t c, uint32_t kk, int32_t (&dst)[kWgRows / 16]) {
+      const int32_t *nbr_k = p.nbr + (size_t)(k0 + kk) * p.n_out;
+#pragma unroll
+      for (int it = 0; it < kWgRows / 16; ++it) {
+        const uint32_t o = r_begin + c * kWgRows + it * 16 + warp * 4 + sub_row;
+        dst[it] = (o < r_end) ? __ldg(nbr_k + o) : -1;
+      }
     };
-    auto wait_empty = [&](uint32_t bar, uint32_t parity) {
-      if (mbar_try_wait(bar, parity)) return;
-      cp_async_wait<0>();
-      while (signaled < g) signal(signaled++);
-      mbar_wait(bar, parity);
-    };
+    if (n_chunks > 0) load_idx(0, 0, idx_cur);
     for (uint32_t c = 0; c < n_chunks; ++c) {
       const uint32_t row0 = r_begin + c * kWgRows;
       for (uint32_t kk = 0; kk < G; ++kk) {
-        const uint32_t sa = g % p.nA;
-        wait_empty(emptyA(sa), ((g / p.nA) & 1u) ^ 1u);
+        {
+          uint32_t nc = c, nkk = kk + 1;
+          if (nkk == G) { nkk = 0; nc = c + 1; }
+          if (nc < n_chunks) load_idx(nc, nkk, idx_nxt);
+        }
+        mbar_wait(emptyA(sa), pha ^ 1u);
         if (kk == 0) {
-          const uint32_t gb = g / G, sb = gb % p.nB;
-          wait_empty(emptyB(sb), ((gb / p.nB) & 1u) ^ 1u);
+          mbar_wait(emptyB(sb), phb ^ 1u);
           const uint32_t dstB = sB + sb * p.b_stage_bytes;
           for (uint32_t blk = 0; blk < p.blkB; ++blk) {
             const uint32_t chn = blk * 64 + j8 * 8;
@@ -484,35 +541,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(const WgParams p) {
             }
           }
         }
-        const int32_t *nbr_k = p.nbr + (size_t)(k0 + kk) * p.n_out;
         const uint32_t dstA = sA + sa * p.a_stage_bytes;
-        int32_t src_rows[kWgRows / 16];
-#pragma unroll
-        for (int it = 0; it < kWgRows / 16; ++it) {
-          const uint32_t o = row0 + it * 16 + warp * 4 + sub_row;
-          src_rows[it] = (o < r_end) ? __ldg(nbr_k + o) : -1;
-        }
         for (uint32_t blk = 0; blk < p.blkA; ++blk) {
           const uint32_t chn = ch0 + blk * 64 + j8 * 8;
 #pragma unroll
           for (int it = 0; it < kWgRows / 16; ++it) {
             const uint32_t row = it * 16 + warp * 4 + sub_row;
-            const bool ok = (src_rows[it] >= 0) && (chn < p.c_in);
-            const T *src = in + (ok ? ((size_t)src_rows[it] * p.c_in + chn) : 0);
+            const bool ok = (idx_cur[it] >= 0) && (chn < p.c_in);
+            const T *src = in + (ok ? ((size_t)idx_cur[it] * p.c_in + chn) : 0);
             cp_async16(dstA + blk * kBlkBytes + row * 128 + ((j8 ^ (row & 7u)) << 4), src,
                        ok ? 16u : 0u);
           }
         }
-        cp_async_commit();
-        ++g;
-        if (g - signaled > (uint32_t)kLag) {
-          cp_async_wait<kLag>();
-          while (g - signaled > (uint32_t)kLag) signal(signaled++);
+        if (kk == 0) {
+          cp_async_mbar_arrive(fullB(sb));
+          if (++sb == p.nB) { sb = 0; phb ^= 1u; }
         }
+        cp_async_mbar_arrive(fullA(sa));
+        if (++sa == p.nA) { sa = 0; pha ^= 1u; }
+#pragma unroll
+        for (int it = 0; it < kWgRows / 16; ++it) idx_cur[it] = idx_nxt[it];
       }
     }
     cp_async_wait<0>();
-    while (signaled < g) signal(signaled++);
   } else if (warp < kProducerWarps + kEpilogueWarps) {
     const uint32_t q = warp & 3u;
     mbar_wait(tfull, 0);
@@ -539,14 +590,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(const WgParams p) {
   } else if (lane == 0) {
     const uint32_t idesc = umma_idesc_f16(Fmt<T>::v, kTileM, p.c_out, 1, 1);
     const uint32_t lboA = kBlkBytes, lboB = kBlkBytes;
-    uint32_t g = 0;
+    uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
     for (uint32_t c = 0; c < n_chunks; ++c) {
-      const uint32_t gb = g / G, sb = gb % p.nB;
-      mbar_wait(fullB(sb), (gb / p.nB) & 1u);
+      mbar_wait(fullB(sb), phb);
       const uint32_t bbase = sB + sb * p.b_stage_bytes;
-      for (uint32_t kk = 0; kk < G; ++kk, ++g) {
-        const uint32_t sa = g % p.nA;
-        mbar_wait(fullA(sa), (g / p.nA) & 1u);
+      for (uint32_t kk = 0; kk < G; ++kk) {
+        mbar_wait(fullA(sa), pha);
         tc_fence_after();
         const uint32_t abase = sA + sa * p.a_stage_bytes;
         for (uint32_t t = 0; t < mt; ++t) {
@@ -559,8 +608,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(const WgParams p) {
           }
         }
         umma_commit(emptyA(sa));
+        if (++sa == p.nA) { sa = 0; pha ^= 1u; }
       }
       umma_commit(emptyB(sb));
+      if (++sb == p.nB) { sb = 0; phb ^= 1u; }
     }
     umma_commit(tfull);
   }
@@ -586,40 +637,25 @@ int conv_wgrad_tc(const void *in, const void *grad_out, int dtype, uint32_t c_in
   WgParams p{};
   p.in = in; p.gout = grad_out; p.nbr = out_nbr; p.dW = grad_weight;
   p.c_in = c_in; p.c_out = c_out; p.K = K; p.n_out = n_out;
-  const uint32_t mt_total = cdiv(c_in, 128);
-  p.mt_cta = mt_total < kTmemCols / c_out ? mt_total : kTmemCols / c_out;
-  if (p.mt_cta > 2) p.mt_cta = 2;
-  p.n_mtgroups = cdiv(mt_total, p.mt_cta);
-  p.G = kTmemCols / (p.mt_cta * c_out);
-  if (p.G > K) p.G = K;
-  if (p.G > 8) p.G = 8;
-  p.n_kgroups = cdiv(K, p.G);
-  p.blkA = p.mt_cta * 2;
-  p.blkB = cdiv(c_out, 64);
-  p.a_stage_bytes = p.blkA * kBlkBytes;
-  p.b_stage_bytes = p.blkB * kBlkBytes;
-  const uint32_t bar_bytes = (4 * kMaxStages + 4) * 8 + 16;
-  p.nB = 2;
-  uint32_t avail = kSmemBudget - p.nB * p.b_stage_bytes - bar_bytes - 1024;
-  p.nA = avail / p.a_stage_bytes;
-  if (p.nA > (uint32_t)kMaxStages) p.nA = kMaxStages;
-  MEB_CHECK_ARG(p.nA >= 4, "not enough shared memory for the wgrad A pipeline");
-  // row slices: ~2 waves of CTAs, each slice a multiple of the stage height
-  uint32_t base = p.n_kgroups * p.n_mtgroups;
-  uint32_t want = cdiv(2ull * num_sms(), base);
-  uint32_t max_splits = cdiv(n_out, 4 * kWgRows);
-  uint32_t splits = want < 1 ? 1 : (want > max_splits ? max_splits : want);
-  p.rows_per_split = cdiv(cdiv(n_out, splits), kWgRows) * kWgRows;
-  p.n_splits = cdiv(n_out, p.rows_per_split);
-  size_t smem_bytes = 1024 + (size_t)p.nA * p.a_stage_bytes + (size_t)p.nB * p.b_stage_bytes + bar_bytes;
-  unsigned grid = base * p.n_splits;
+  const tc::WgCfg cfg = tc::wgrad_config(c_in, c_out, K, n_out, (uint32_t)num_sms());
+  if (cfg.mt_cta == 0) {
+    set_error("wgrad tc: no pipeline configuration fits (c_in=%u c_out=%u K=%u)", c_in, c_out, K);
+    return MEB200_ERR_UNSUPPORTED;
+  }
+  p.mt_cta = cfg.mt_cta; p.n_mtgroups = cfg.n_mtgroups; p.G = cfg.G; p.n_kgroups = cfg.n_kgroups;
+  p.blkA = cfg.blkA; p.blkB = cfg.blkB;
+  p.a_stage_bytes = cfg.a_stage_bytes; p.b_stage_bytes = cfg.b_stage_bytes;
+  p.lag = cfg.pipe.lag; p.nA = cfg.pipe.nA; p.nB = cfg.pipe.nB;
+  p.rows_per_split = cfg.rows_per_split; p.n_splits = cfg.n_splits;
+  size_t smem_bytes = cfg.smem_bytes;
+  unsigned grid = cfg.n_kgroups * cfg.n_mtgroups * cfg.n_splits;
   if (dtype == MEB200_BF16) {
-    static bool cfg = false;
-    if (!cfg) { MEB_CUDA(cudaFuncSetAttribute(k_wgrad_tc<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg = true; }
+    static bool done = false;
+    if (!done) { MEB_CUDA(cudaFuncSetAttribute(k_wgrad_tc<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); done = true; }
     k_wgrad_tc<__nv_bfloat16><<<grid, kThreads, smem_bytes, stream>>>(p);
   } else {
-    static bool cfg = false;
-    if (!cfg) { MEB_CUDA(cudaFuncSetAttribute(k_wgrad_tc<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg = true; }
+    static bool done = false;
+    if (!done) { MEB_CUDA(cudaFuncSetAttribute(k_wgrad_tc<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); done = true; }
     k_wgrad_tc<__half><<<grid, kThreads, smem_bytes, stream>>>(p);
   }
   count_tc_launch();

@@ -1,0 +1,60 @@
+"""Host-side launch configuration of the tcgen05 kernels (csrc/tc_config.h), checked on CPU:
+every channel shape MinkUNet14/34C/... can produce must get a pipeline (lag >= 1) that fits in
+the 227 KB of shared memory a CTA may use and 512 TMEM columns."""
+import itertools
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SRC = r"""
+#include <stdio.h>
+#include <initializer_list>
+#include "tc_config.h"
+using namespace meb200::tc;
+int main() {
+  const unsigned chans[] = {16, 32, 48, 64, 96, 128, 160, 192, 256, 384, 512};
+  const unsigned ncs[] = {16, 32, 48, 64, 96, 128, 192, 256};
+  int bad = 0;
+  for (unsigned cr : chans) for (unsigned cc : ncs) for (unsigned rows : {1u, 129u, 5000u, 800000u}) {
+    FwdCfg f = fwd_config(cr, cc, rows);
+    bool ok = f.bk != 0 && f.pipe.lag >= 1 && f.smem_bytes <= 227 * 1024 && 2 * f.R * cc <= kTmemCols
+              && f.pipe.nA >= 3 && (f.pipe.nB - 1) * f.R >= f.pipe.nA;
+    if (!ok) { printf("FWD BAD cr=%u cc=%u rows=%u bk=%d lag=%u\n", cr, cc, rows, f.bk, f.pipe.lag); ++bad; }
+    printf("fwd %u %u %u : bk=%d R=%u lag=%u nA=%u nB=%u smem=%u\n", cr, cc, rows, f.bk, f.R, f.pipe.lag, f.pipe.nA, f.pipe.nB, f.smem_bytes);
+  }
+  const unsigned cins[] = {16, 24, 32, 64, 96, 128, 192, 256, 384, 512};
+  for (unsigned ci : cins) for (unsigned co : ncs) for (unsigned K : {1u, 8u, 27u, 125u}) for (unsigned rows : {1u, 300u, 800000u}) {
+    WgCfg w = wgrad_config(ci, co, K, rows, 148);
+    bool ok = w.mt_cta != 0 && w.pipe.lag >= 1 && w.smem_bytes <= 227 * 1024 &&
+              w.G * w.mt_cta * co <= kTmemCols && w.G >= 1 && w.n_splits * w.rows_per_split >= rows
+              && w.pipe.nA >= 3 && (w.pipe.nB - 1) * w.G >= w.pipe.nA;
+    if (w.mt_cta == 0 && co == 256 && K == 1) ok = true;  // declared unsupported -> SIMT fallback
+    if (!ok) { printf("WG BAD ci=%u co=%u K=%u rows=%u\n", ci, co, K, rows); ++bad; }
+    printf("wg %u %u %u %u : mt=%u G=%u lag=%u nA=%u nB=%u splits=%u smem=%u\n", ci, co, K, rows, w.mt_cta, w.G, w.pipe.lag, w.pipe.nA, w.pipe.nB, w.n_splits, w.smem_bytes);
+  }
+  printf("bad=%d\n", bad);
+  return bad != 0;
+}
+"""
+
+
+def test_tc_launch_configs(tmp_path):
+    src = tmp_path / "cfg.cpp"
+    src.write_text(SRC)
+    exe = tmp_path / "cfg"
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-I",
+                    os.path.join(ROOT, "minkowskiengine_b200", "csrc"), str(src), "-o", str(exe)],
+                   check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "bad=0" in r.stdout
+
+
+if __name__ == "__main__":
+    import pathlib
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        test_tc_launch_configs(pathlib.Path(d))
+        print("ok")
