@@ -17,6 +17,10 @@
 //                          tcgen05.commit that recycles smem stages / publishes accumulators
 // Pipelines (all mbarrier based): A ring (nA stages), B ring (nB stages), accumulator
 // ring in TMEM (acc_stages x R accumulators of c_cols columns).
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include "conv_tc.cuh"
 #include "ptx.cuh"
 #include "tc_config.h"
@@ -30,9 +34,11 @@ using tc::kMaxStages;
 using tc::kTmemCols;
 using tc::kWgRows;
 using tc::kBlkBytes;
-constexpr int kProducerWarps = 4;
+constexpr int kProducerWarps = 4;   // wgrad kernel
 constexpr int kEpilogueWarps = 4;
 constexpr int kThreads = (kProducerWarps + kEpilogueWarps + 1) * 32;
+constexpr int kFwdProducerWarps = 8;  // forward/dgrad kernel: one warp fills a whole stage
+constexpr int kFwdThreads = (kFwdProducerWarps + kEpilogueWarps + 1) * 32;
 
 struct TcParams {
   const void *A;        // [n_a, c_red] gathered operand
@@ -40,8 +46,12 @@ struct TcParams {
   const int32_t *nbr;   // [K, n_rows]
   void *out;            // [n_rows, c_cols]
   uint32_t c_red, c_cols, K, n_rows;
+  uint32_t n_a;          // rows of A (gather indices >= n_a are out of bounds -> zero rows)
+  uint32_t wb_row0;      // first row of this launch's column slice inside one offset of Wb
+  uint32_t wb_rows_per_k;  // rows of Wb per offset (= full c_cols of the layer)
   uint32_t n_super, R, acc_stages, nA, nB;
   uint32_t a_stage_bytes, b_stage_bytes;
+  uint32_t cps, n_macro, a_sub_bytes, b_sub_bytes;  // chunks per stage, stages per offset
   uint32_t out_f32;
   uint32_t lag;          // cp.async groups each producer thread keeps in flight
   uint32_t wb_k_stride;  // elements between consecutive offsets in Wb
@@ -76,8 +86,7 @@ struct Swz {
   static constexpr int kRowBytes = BK * 2;
   static constexpr int kChunks = kRowBytes / 16;          // 16-byte chunks per row
   static constexpr int kRowsPerInstr = 32 / kChunks;      // rows one warp-wide cp.async covers
-  static constexpr int kRowsPerIter = kRowsPerInstr * kProducerWarps;
-  static constexpr int kItersA = kTileM / kRowsPerIter;
+  static constexpr int kItersA = kTileM / kRowsPerInstr;  // warp-wide copies per 128-row tile
   static constexpr uint32_t kLayout = BK == 64 ? 2u : (BK == 32 ? 4u : 6u);
   static constexpr uint32_t kSbo = 8 * kRowBytes;         // 8-row core-matrix group stride
   __device__ static __forceinline__ uint32_t offset(uint32_t row, uint32_t chunk) {
@@ -103,9 +112,15 @@ __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
   return *reinterpret_cast<uint32_t *>(&h);
 }
 
-template <typename T, int BK, int RT>
-__global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const TcParams p) {
+// TMA = true : operands are fetched by the TMA unit (row gather4 for A, tile loads for B);
+// TMA = false: cp.async path (kept as a fallback; the LSU-driven copies top out near
+//              20 B/cycle/SM on B200).
+template <typename T, int BK, int RT, bool TMA>
+__global__ void __launch_bounds__(kFwdThreads, 1)
+k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+          const TcParams p) {
   using S = Swz<BK>;
+  constexpr int NP = kFwdProducerWarps;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem base is only guaranteed 16 B aligned: round up to the swizzle atom
   uint8_t *smem = reinterpret_cast<uint8_t *>(
@@ -125,16 +140,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const TcParams p) {
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * kMaxStages + 4);
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t chunks_red = p.c_red / BK;
   constexpr uint32_t R = RT;
 
   if (threadIdx.x == 0) {
     for (uint32_t i = 0; i < p.nA; ++i) {
-      mbar_init(fullA(i), kProducerWarps * 32);
+      // cp.async: the 32 lanes of the producer warp that fills the stage; TMA: one
+      // arrive.expect_tx, the copies complete the transaction count
+      mbar_init(fullA(i), TMA ? 1 : 32);
       mbar_init(emptyA(i), 1);
     }
     for (uint32_t i = 0; i < p.nB; ++i) {
-      mbar_init(fullB(i), kProducerWarps * 32);
+      mbar_init(fullB(i), TMA ? 1 : 32);
       mbar_init(emptyB(i), 1);
     }
     for (uint32_t i = 0; i < 2; ++i) {
@@ -143,7 +159,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const TcParams p) {
     }
     mbar_fence_init();
   }
-  if (warp == kProducerWarps + kEpilogueWarps) {
+  if (warp == NP + kEpilogueWarps) {
     tmem_alloc(smem_u32(tmem_slot), kTmemCols);
     tmem_relinquish();
   }
@@ -152,77 +168,150 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const TcParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < kProducerWarps) {
+  if (TMA && warp < NP) {
+    // =============================== TMA PRODUCERS ==================================
+    // Stages are dealt round-robin to (at most) two issuing warps.  Per stage a warp reads the
+    // 128 neighbour rows of the tile (lane l owns rows 4l..4l+3, fetched one stage ahead) and
+    // every lane issues ONE row-gather of its four rows per channel chunk; lane 0 arms the
+    // barrier with the byte count and loads the B slice when the stage opens a new group.
+    constexpr uint32_t NPT = 2;
+    const uint32_t SPK = p.n_macro * R;
+    const uint32_t SPS = p.K * SPK;
+    const uint32_t n_my = p.n_super > blockIdx.x
+                              ? (p.n_super - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t total = n_my * SPS;
+    struct Pos { uint32_t st, k, mc, r; };
+    auto decode = [&](uint32_t g) {
+      Pos q;
+      const uint32_t t = g / SPS, rem = g - t * SPS;
+      q.st = blockIdx.x + t * gridDim.x;
+      q.k = rem / SPK;
+      const uint32_t rem2 = rem - q.k * SPK;
+      q.mc = rem2 / R;
+      q.r = rem2 - q.mc * R;
+      return q;
+    };
+    int32_t idx_cur[4], idx_nxt[4];
+    auto load_idx = [&](uint32_t g, int32_t (&dst)[4]) {
+      const Pos q = decode(g);
+      const int32_t *nbr_k = p.nbr + (size_t)q.k * p.n_rows;
+      const uint32_t row0 = (q.st * R + q.r) * kTileM + lane * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t grow = row0 + i;
+        const int32_t v = (grow < p.n_rows) ? __ldg(nbr_k + grow) : -1;
+        dst[i] = v < 0 ? (int32_t)p.n_a : v;   // out of bounds -> TMA zero fill
+      }
+    };
+    const uint32_t step = p.nA < NPT ? p.nA : NPT;
+    uint32_t g = warp < step ? warp : total;
+    if (warp < step && lane == 0) { tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB); }
+    if (g < total) load_idx(g, idx_cur);
+    for (; g < total; g += step) {
+      if (g + step < total) load_idx(g + step, idx_nxt);
+      const Pos q = decode(g);
+      const uint32_t sa = g % p.nA, pha = (g / p.nA) & 1u;
+      const int32_t c0 = (int32_t)(q.mc * p.cps * BK);
+      mbar_wait(emptyA(sa), pha ^ 1u);
+      if (q.r == 0) {
+        const uint32_t gb = g / R, sb = gb % p.nB, phb = (gb / p.nB) & 1u;
+        mbar_wait(emptyB(sb), phb ^ 1u);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(fullB(sb), p.cps * p.c_cols * BK * 2);
+          const uint32_t dstB = sB + sb * p.b_stage_bytes;
+          const int32_t brow = (int32_t)(q.k * p.wb_rows_per_k + p.wb_row0);
+          for (uint32_t s = 0; s < p.cps; ++s)
+            tma_load_2d(dstB + s * p.b_sub_bytes, &mapB, c0 + (int32_t)(s * BK), brow, fullB(sb));
+        }
+      }
+      if (lane == 0) mbar_arrive_expect_tx(fullA(sa), p.cps * kTileM * BK * 2);
+      __syncwarp();
+      const uint32_t dstA = sA + sa * p.a_stage_bytes + lane * 4 * S::kRowBytes;
+      for (uint32_t s = 0; s < p.cps; ++s)
+        tma_gather4(dstA + s * p.a_sub_bytes, &mapA, c0 + (int32_t)(s * BK), idx_cur[0], idx_cur[1],
+                    idx_cur[2], idx_cur[3], fullA(sa));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) idx_cur[i] = idx_nxt[i];
+    }
+  } else if (!TMA && warp < NP) {
     // =============================== PRODUCERS ======================================
+    // Pipeline stages are dealt round-robin to the NP producer warps; a warp fills its whole
+    // stage (128 gathered rows x cps channel chunks, plus the B slice when it owns the first
+    // row tile of a (offset, chunk) group), so NP different stages are being filled at once.
     const uint32_t sub_row = lane / S::kChunks, chunk = lane % S::kChunks;
     const T *A = reinterpret_cast<const T *>(p.A);
     const T *Wb = reinterpret_cast<const T *>(p.Wb);
-    const uint32_t iters_b = (p.c_cols + S::kRowsPerIter - 1) / S::kRowsPerIter;
-    // ring positions and use-parities, advanced incrementally (no div/mod on the hot path)
-    uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
-    // Neighbour rows this thread gathers for (super tile st, offset k): fetched one offset
-    // AHEAD of use so the table latency never sits between two pipeline stages.
-    int32_t idx_cur[RT][S::kItersA], idx_nxt[RT][S::kItersA];
-    auto load_idx = [&](uint32_t st, uint32_t k, int32_t (&dst)[RT][S::kItersA]) {
-      const int32_t *nbr_k = p.nbr + (size_t)k * p.n_rows;
-#pragma unroll
-      for (int r = 0; r < RT; ++r)
-#pragma unroll
-        for (int j = 0; j < S::kItersA; ++j) {
-          uint32_t grow = (st * R + r) * kTileM + j * S::kRowsPerIter + warp * S::kRowsPerInstr + sub_row;
-          dst[r][j] = (grow < p.n_rows) ? __ldg(nbr_k + grow) : -1;
-        }
+    const uint32_t SPK = p.n_macro * R;   // A stages per (super tile, offset)
+    const uint32_t SPS = p.K * SPK;       // A stages per super tile
+    const uint32_t n_my = p.n_super > blockIdx.x
+                              ? (p.n_super - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t total = n_my * SPS;
+    struct Pos { uint32_t st, k, mc, r; };
+    auto decode = [&](uint32_t g) {
+      Pos q;
+      const uint32_t t = g / SPS, rem = g - t * SPS;
+      q.st = blockIdx.x + t * gridDim.x;
+      q.k = rem / SPK;
+      const uint32_t rem2 = rem - q.k * SPK;
+      q.mc = rem2 / R;
+      q.r = rem2 - q.mc * R;
+      return q;
     };
-    if (blockIdx.x < p.n_super) load_idx(blockIdx.x, 0, idx_cur);
-
-    for (uint32_t st = blockIdx.x; st < p.n_super; st += gridDim.x) {
-      for (uint32_t k = 0; k < p.K; ++k) {
-        {  // prefetch the indices of the next (super tile, offset)
-          uint32_t nst = st, nk = k + 1;
-          if (nk == p.K) { nk = 0; nst = st + gridDim.x; }
-          if (nst < p.n_super) load_idx(nst, nk, idx_nxt);
-        }
-        for (uint32_t cc = 0; cc < chunks_red; ++cc) {
-          const uint32_t c0 = cc * BK;
+    // lane l holds the neighbour rows of tile rows l, l+32, l+64, l+96 (coalesced table reads),
+    // fetched one stage ahead of use; the copy loop pulls them out with shuffles.
+    int32_t idx_cur[4], idx_nxt[4];
+    auto load_idx = [&](uint32_t g, int32_t (&dst)[4]) {
+      const Pos q = decode(g);
+      const int32_t *nbr_k = p.nbr + (size_t)q.k * p.n_rows;
+      const uint32_t row0 = (q.st * R + q.r) * kTileM + lane;
 #pragma unroll
-          for (int r = 0; r < RT; ++r) {
-            mbar_wait(emptyA(sa), pha ^ 1u);
-            if (r == 0) {
-              mbar_wait(emptyB(sb), phb ^ 1u);
-              const uint32_t dstB = sB + sb * p.b_stage_bytes;
-              for (uint32_t j = 0; j < iters_b; ++j) {
-                uint32_t n = j * S::kRowsPerIter + warp * S::kRowsPerInstr + sub_row;
-                if (n < p.c_cols) {
-                  const T *src = Wb + (size_t)k * p.wb_k_stride + (size_t)n * p.c_red + c0 + chunk * 8;
-                  cp_async16(dstB + S::offset(n, chunk), src, 16);
-                }
-              }
-            }
-            const uint32_t dstA = sA + sa * p.a_stage_bytes;
-#pragma unroll
-            for (int j = 0; j < S::kItersA; ++j) {
-              const uint32_t row = j * S::kRowsPerIter + warp * S::kRowsPerInstr + sub_row;
-              const int32_t src_row = idx_cur[r][j];
-              const T *src = A + (size_t)(src_row < 0 ? 0 : src_row) * p.c_red + c0 + chunk * 8;
-              cp_async16(dstA + S::offset(row, chunk), src, src_row < 0 ? 0u : 16u);
-            }
-            // publish: the barriers fire once this thread's copies for the stage have landed
-            if (r == 0) {
-              cp_async_mbar_arrive(fullB(sb));
-              if (++sb == p.nB) { sb = 0; phb ^= 1u; }
-            }
-            cp_async_mbar_arrive(fullA(sa));
-            if (++sa == p.nA) { sa = 0; pha ^= 1u; }
-          }
-        }
-#pragma unroll
-        for (int r = 0; r < RT; ++r)
-#pragma unroll
-          for (int j = 0; j < S::kItersA; ++j) idx_cur[r][j] = idx_nxt[r][j];
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t grow = row0 + i * 32;
+        dst[i] = (grow < p.n_rows) ? __ldg(nbr_k + grow) : -1;
       }
+    };
+    // Only min(NP, nA) warps take stages: a warp's consecutive stages (g, g + step) must be at
+    // most one ring revolution apart, otherwise the parity wait on the empty barrier could be
+    // satisfied by a phase two uses back (the mbarrier only remembers one parity bit).
+    const uint32_t step = p.nA < (uint32_t)NP ? p.nA : (uint32_t)NP;
+    uint32_t g = warp < step ? warp : total;
+    if (g < total) load_idx(g, idx_cur);
+    for (; g < total; g += step) {
+      if (g + step < total) load_idx(g + step, idx_nxt);
+      const Pos q = decode(g);
+      const uint32_t sa = g % p.nA, pha = (g / p.nA) & 1u;
+      const uint32_t c0 = q.mc * p.cps * BK + chunk * 8;   // first channel this lane copies
+      mbar_wait(emptyA(sa), pha ^ 1u);
+      if (q.r == 0) {
+        const uint32_t gb = g / R, sb = gb % p.nB, phb = (gb / p.nB) & 1u;
+        mbar_wait(emptyB(sb), phb ^ 1u);
+        const uint32_t dstB = sB + sb * p.b_stage_bytes;
+        const T *srcB = Wb + (size_t)q.k * p.wb_k_stride + c0;
+        for (uint32_t n = sub_row; n < p.c_cols; n += S::kRowsPerInstr) {
+          const T *src = srcB + (size_t)n * p.c_red;
+          const uint32_t dst = dstB + S::offset(n, chunk);
+          for (uint32_t s = 0; s < p.cps; ++s) cp_async16(dst + s * p.b_sub_bytes, src + s * BK, 16);
+        }
+        cp_async_mbar_arrive(fullB(sb));
+      }
+      const uint32_t dstA = sA + sa * p.a_stage_bytes;
+#pragma unroll
+      for (int it = 0; it < S::kItersA; ++it) {
+        constexpr int dummy = 0; (void)dummy;
+        const int slot = (it * S::kRowsPerInstr) / 32;
+        const uint32_t row = it * S::kRowsPerInstr + sub_row;
+        const int32_t src_row = __shfl_sync(0xffffffffu, idx_cur[slot], row & 31u);
+        const T *src = A + (size_t)(src_row < 0 ? 0 : src_row) * p.c_red + c0;
+        const uint32_t dst = dstA + S::offset(row, chunk);
+        const uint32_t nbytes = src_row < 0 ? 0u : 16u;
+        for (uint32_t s = 0; s < p.cps; ++s) cp_async16(dst + s * p.a_sub_bytes, src + s * BK, nbytes);
+      }
+      cp_async_mbar_arrive(fullA(sa));   // fires once this warp's copies for the stage landed
+#pragma unroll
+      for (int i = 0; i < 4; ++i) idx_cur[i] = idx_nxt[i];
     }
     cp_async_wait<0>();  // nothing of this thread may still be in flight at teardown
-  } else if (warp < kProducerWarps + kEpilogueWarps) {
+  } else if (warp < NP + kEpilogueWarps) {
     // =============================== EPILOGUE =======================================
     const uint32_t q = warp & 3u;  // TMEM lane quadrant this warp may access
     uint32_t t = 0;
@@ -273,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const TcParams p) {
       mbar_wait(tempty(acc), par ^ 1u);
       tc_fence_after();
       for (uint32_t k = 0; k < p.K; ++k) {
-        for (uint32_t cc = 0; cc < chunks_red; ++cc) {
+        for (uint32_t mc = 0; mc < p.n_macro; ++mc) {
           mbar_wait(fullB(sb), phb);
           const uint32_t bbase = sB + sb * p.b_stage_bytes;
 #pragma unroll
@@ -282,11 +371,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const TcParams p) {
             tc_fence_after();
             const uint32_t abase = sA + sa * p.a_stage_bytes;
             const uint32_t d = tmem_base + (acc * R + r) * p.c_cols;
+            for (uint32_t s = 0; s < p.cps; ++s) {
 #pragma unroll
-            for (int j = 0; j < BK / 16; ++j) {
-              uint64_t da = umma_desc(abase + j * 32, 16, S::kSbo, S::kLayout);
-              uint64_t db = umma_desc(bbase + j * 32, 16, S::kSbo, S::kLayout);
-              umma_f16(d, da, db, idesc, (k | cc | (uint32_t)j) != 0u);
+              for (int j = 0; j < BK / 16; ++j) {
+                uint64_t da = umma_desc(abase + s * p.a_sub_bytes + j * 32, 16, S::kSbo, S::kLayout);
+                uint64_t db = umma_desc(bbase + s * p.b_sub_bytes + j * 32, 16, S::kSbo, S::kLayout);
+                umma_f16(d, da, db, idesc, (k | mc | s | (uint32_t)j) != 0u);
+              }
             }
             umma_commit(emptyA(sa));
             if (++sa == p.nA) { sa = 0; pha ^= 1u; }
@@ -301,7 +392,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const TcParams p) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kProducerWarps + kEpilogueWarps) {
+  if (warp == NP + kEpilogueWarps) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -330,49 +421,124 @@ static int pick_bk(uint32_t c_red) {
   return 0;
 }
 
-template <typename T, int BK, int RT>
-static int launch_tc(const TcParams &p, size_t smem_bytes, unsigned grid, cudaStream_t stream) {
-  auto kern = k_conv_tc<T, BK, RT>;
+// ---- TMA tensor maps (driver entry point fetched through the runtime: no libcuda link) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) ==
+            cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2-D row-major [rows, cols] 16-bit tensor, box = box_rows x box_cols, swizzle by box width.
+static int make_map_2d(CUtensorMap *m, int dtype, const void *base, uint64_t rows, uint64_t cols,
+                       uint32_t box_cols, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return MEB200_ERR_UNSUPPORTED;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw = box_cols * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : (box_cols * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = fn(m, dtype == MEB200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                          : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                  2, const_cast<void *>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu box=%ux%u", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols, box_rows, box_cols);
+    return MEB200_ERR_CUDA;
+  }
+  return MEB200_OK;
+}
+
+static bool tma_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("MEB200_TC_GATHER");   // "tma" (default) | "cpasync"
+    v = (e && e[0] == 'c') ? 0 : 1;
+    if (v == 1 && encode_tiled_fn() == nullptr) v = 0;
+  }
+  return v == 1;
+}
+
+template <typename T, int BK, int RT, bool TMA>
+static int launch_tc(const CUtensorMap &mA, const CUtensorMap &mB, const TcParams &p,
+                     size_t smem_bytes, unsigned grid, cudaStream_t stream) {
+  auto kern = k_conv_tc<T, BK, RT, TMA>;
   static bool configured = false;
   if (!configured) {
     MEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  kern<<<grid, kThreads, smem_bytes, stream>>>(p);
+  kern<<<grid, kFwdThreads, smem_bytes, stream>>>(mA, mB, p);
   count_tc_launch();
   MEB_LAUNCH_OK();
   return MEB200_OK;
 }
 
 template <typename T>
-static int launch_tc_bk_r(int bk, uint32_t R, const TcParams &p, size_t smem, unsigned grid,
+static int launch_tc_bk_r(int bk, uint32_t R, bool tma, const CUtensorMap &mA,
+                          const CUtensorMap &mB, const TcParams &p, size_t smem, unsigned grid,
                           cudaStream_t s) {
-#define MEB_TC_R(BKV)                                                   \
-  switch (R) {                                                          \
-    case 4: return launch_tc<T, BKV, 4>(p, smem, grid, s);              \
-    case 2: return launch_tc<T, BKV, 2>(p, smem, grid, s);              \
-    default: return launch_tc<T, BKV, 1>(p, smem, grid, s);             \
+#define MEB_TC_R(BKV, TM)                                                     \
+  switch (R) {                                                                \
+    case 4: return launch_tc<T, BKV, 4, TM>(mA, mB, p, smem, grid, s);        \
+    case 2: return launch_tc<T, BKV, 2, TM>(mA, mB, p, smem, grid, s);        \
+    default: return launch_tc<T, BKV, 1, TM>(mA, mB, p, smem, grid, s);       \
+  }
+  if (tma) {
+    switch (bk) {
+      case 64: MEB_TC_R(64, true)
+      case 32: MEB_TC_R(32, true)
+      default: MEB_TC_R(16, true)
+    }
   }
   switch (bk) {
-    case 64: MEB_TC_R(64)
-    case 32: MEB_TC_R(32)
-    default: MEB_TC_R(16)
+    case 64: MEB_TC_R(64, false)
+    case 32: MEB_TC_R(32, false)
+    default: MEB_TC_R(16, false)
   }
 #undef MEB_TC_R
 }
 
 // One launch over output columns [0, c_cols) of a problem whose B operand / output may be
 // slices of wider tensors (N-splitting for c_cols > 256).
-static int launch_tc_slice(const void *A, int dtype, uint32_t c_reduce, const void *Wb,
-                           uint32_t wb_k_stride, uint32_t K, uint32_t c_cols, const int32_t *nbr,
-                           uint32_t n_rows, void *out, uint32_t out_ld, int out_dtype,
-                           cudaStream_t stream) {
+static int launch_tc_slice(const void *A, int dtype, uint32_t n_a, uint32_t c_reduce,
+                           const void *Wb_full, uint32_t c_cols_full, uint32_t n0, uint32_t K,
+                           uint32_t c_cols, const int32_t *nbr, uint32_t n_rows, void *out,
+                           uint32_t out_ld, int out_dtype, cudaStream_t stream) {
+  const void *Wb = reinterpret_cast<const uint8_t *>(Wb_full) + (size_t)n0 * c_reduce * 2;
+  const uint32_t wb_k_stride = c_cols_full * c_reduce;
   TcParams p{};
   p.A = A; p.Wb = Wb; p.nbr = nbr; p.out = out;
   p.c_red = c_reduce; p.c_cols = c_cols; p.K = K; p.n_rows = n_rows;
   p.out_f32 = out_dtype == MEB200_F32;
   p.wb_k_stride = wb_k_stride; p.out_ld = out_ld;
-  const tc::FwdCfg cfg = tc::fwd_config(c_reduce, c_cols, n_rows);
+  p.n_a = n_a; p.wb_row0 = n0; p.wb_rows_per_k = c_cols_full;
+  static int max_stage_kb = -1;   // tuning knob: MEB200_TC_STAGE_KB (default 32)
+  if (max_stage_kb < 0) {
+    const char *e = getenv("MEB200_TC_STAGE_KB");
+    max_stage_kb = e ? atoi(e) : 32;
+    if (max_stage_kb <= 0) max_stage_kb = 32;
+  }
+  const tc::FwdCfg cfg = tc::fwd_config(c_reduce, c_cols, n_rows, (uint32_t)max_stage_kb * 1024);
   if (cfg.bk == 0 || cfg.pipe.lag < 1) {
     set_error("conv tc: no pipeline configuration fits (c_red=%u c_cols=%u)", c_reduce, c_cols);
     return MEB200_ERR_UNSUPPORTED;
@@ -381,12 +547,26 @@ static int launch_tc_slice(const void *A, int dtype, uint32_t c_reduce, const vo
   const uint32_t R = cfg.R;
   p.R = R; p.acc_stages = 2; p.n_super = cfg.n_super;
   p.a_stage_bytes = cfg.a_stage_bytes; p.b_stage_bytes = cfg.b_stage_bytes;
+  p.cps = cfg.cps; p.n_macro = c_reduce / (uint32_t)bk / cfg.cps;
+  p.a_sub_bytes = cfg.a_sub_bytes; p.b_sub_bytes = cfg.b_sub_bytes;
   p.lag = cfg.pipe.lag; p.nA = cfg.pipe.nA; p.nB = cfg.pipe.nB;
   size_t smem_bytes = cfg.smem_bytes;
   unsigned grid = p.n_super < (uint32_t)num_sms() ? p.n_super : (unsigned)num_sms();
+  CUtensorMap mA, mB;
+  memset(&mA, 0, sizeof(mA));
+  memset(&mB, 0, sizeof(mB));
+  const bool tma = tma_enabled() && n_a > 0 &&
+                   (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(Wb_full) & 15) == 0;
+  if (tma) {
+    int rc = make_map_2d(&mA, dtype, A, n_a, c_reduce, (uint32_t)bk, 1);
+    if (rc != MEB200_OK) return rc;
+    rc = make_map_2d(&mB, dtype, Wb_full, (uint64_t)K * c_cols_full, c_reduce, (uint32_t)bk, c_cols);
+    if (rc != MEB200_OK) return rc;
+  }
   if (dtype == MEB200_BF16)
-    return launch_tc_bk_r<__nv_bfloat16>(bk, R, p, smem_bytes, grid, stream);
-  return launch_tc_bk_r<__half>(bk, R, p, smem_bytes, grid, stream);
+    return launch_tc_bk_r<__nv_bfloat16>(bk, R, tma, mA, mB, p, smem_bytes, grid, stream);
+  return launch_tc_bk_r<__half>(bk, R, tma, mA, mB, p, smem_bytes, grid, stream);
 }
 
 bool conv_tc_supported(int dtype, uint32_t c_reduce, uint32_t c_cols) {
@@ -398,7 +578,6 @@ bool conv_tc_supported(int dtype, uint32_t c_reduce, uint32_t c_cols) {
 int conv_forward_tc(const void *A, int dtype, uint32_t n_a, uint32_t c_reduce, const void *W,
                     uint32_t K, uint32_t c_cols, bool dgrad, const int32_t *nbr, uint32_t n_rows,
                     void *out, int out_dtype, void *workspace, cudaStream_t stream) {
-  (void)n_a;
   if (n_rows == 0) return MEB200_OK;
   MEB_CHECK_ARG(conv_tc_supported(dtype, c_reduce, c_cols), "shape not supported by tc path");
   const uint8_t *Wb = reinterpret_cast<const uint8_t *>(W);
@@ -419,8 +598,7 @@ int conv_forward_tc(const void *A, int dtype, uint32_t n_a, uint32_t c_reduce, c
   const size_t out_esz = out_dtype == MEB200_F32 ? 4 : 2;
   for (uint32_t n0 = 0; n0 < c_cols; n0 += 256) {
     uint32_t nc = c_cols - n0 < 256 ? c_cols - n0 : 256;
-    int rc = launch_tc_slice(A, dtype, c_reduce, Wb + (size_t)n0 * c_reduce * 2,
-                             c_cols * c_reduce, K, nc, nbr, n_rows,
+    int rc = launch_tc_slice(A, dtype, n_a, c_reduce, Wb, c_cols, n0, K, nc, nbr, n_rows,
                              reinterpret_cast<uint8_t *>(out) + (size_t)n0 * out_esz, c_cols,
                              out_dtype, stream);
     if (rc != MEB200_OK) return rc;

@@ -61,6 +61,33 @@ __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ---- TMA (bulk tensor copies, async proxy) ------------------------------------------
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+// 2-D tile load: box (c0.., c1..) of the tensor map -> swizzled shared memory.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *tmap, int32_t c0, int32_t c1,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3}], [%4];" ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+// Row gather: four rows (r0..r3) x one box of columns starting at c0; rows outside the tensor
+// are zero-filled.  Lands as four consecutive rows of the (swizzled) destination tile.
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const void *tmap, int32_t c0, int32_t r0,
+                                            int32_t r1, int32_t r2, int32_t r3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst), "l"(tmap), "r"(c0), "r"(r0), "r"(r1),
+      "r"(r2), "r"(r3), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void *tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
 // ---- TMEM / tcgen05 ---------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),

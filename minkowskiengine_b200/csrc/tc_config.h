@@ -19,16 +19,23 @@ constexpr uint32_t kBlkBytes = kWgRows * 128;           // wgrad: one 64-channel
 inline uint32_t cdiv_u(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
 
 // Producers publish a stage with cp.async.mbarrier.arrive (the barrier fires when the copies
-// land), so every stage of the ring may be in flight.  The B ring must hold the B slice of every
-// A stage that can be in flight (`share` A stages use one B slice) plus one being filled —
-// otherwise a producer would wait for a B stage whose consumers are still behind it in the ring.
-struct PipeCfg { uint32_t lag, nA, nB; };   // lag = nA - 1 (kept for reporting)
+// land), so every stage of a ring may be in flight.  `share` consecutive A stages use one B
+// stage; the number of A stages that can actually be in flight is limited by both rings:
+//   depth = min(nA, (nB - 1) * share + 1)
+// The search maximises the bytes of operand A in flight (depth * a_bytes).
+struct PipeCfg { uint32_t lag, nA, nB; };   // lag = effective depth (kept for reporting)
 inline PipeCfg pick_pipeline(uint32_t a_bytes, uint32_t b_bytes, uint32_t share, uint32_t budget) {
   PipeCfg best{0, 0, 0};
-  for (uint32_t nA = kMaxStages; nA >= 3; --nA) {
-    uint32_t nB = (nA + share - 1) / share + 1;
-    if (nB > (uint32_t)kMaxStages) continue;
-    if ((uint64_t)nA * a_bytes + (uint64_t)nB * b_bytes <= budget) { best = {nA - 1, nA, nB}; break; }
+  uint64_t best_score = 0;
+  for (uint32_t nB = 2; nB <= (uint32_t)kMaxStages; ++nB) {
+    if ((uint64_t)nB * b_bytes + 2ull * a_bytes > budget) break;
+    uint32_t nA = (uint32_t)((budget - (uint64_t)nB * b_bytes) / a_bytes);
+    if (nA > (uint32_t)kMaxStages) nA = kMaxStages;
+    if (nA < 2) continue;
+    uint32_t depth = (nB - 1) * share + 1;
+    if (depth > nA) depth = nA;
+    uint64_t score = (uint64_t)depth * a_bytes;
+    if (score > best_score) { best_score = score; best = {depth, nA, nB}; }
   }
   return best;
 }
@@ -36,13 +43,15 @@ inline PipeCfg pick_pipeline(uint32_t a_bytes, uint32_t b_bytes, uint32_t share,
 // ---- forward / dgrad: out[r, 0:c_cols] over n_rows rows, reduction over c_red channels ----
 struct FwdCfg {
   int bk;                 // channel-chunk width (64/32/16 -> 128B/64B/32B swizzle), 0 = unsupported
+  uint32_t cps;           // channel chunks per pipeline stage (one barrier round trip per stage)
   uint32_t R;             // row tiles sharing one B slice (1, 2 or 4)
   uint32_t n_super;       // super tiles of R*128 rows
-  uint32_t a_stage_bytes, b_stage_bytes;
+  uint32_t a_sub_bytes, b_sub_bytes;       // one chunk of A (128 rows) / of B (c_cols rows)
+  uint32_t a_stage_bytes, b_stage_bytes;   // cps chunks
   PipeCfg pipe;
   uint32_t smem_bytes;
 };
-inline FwdCfg fwd_config(uint32_t c_red, uint32_t c_cols, uint32_t n_rows) {
+inline FwdCfg fwd_config(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, uint32_t max_stage_bytes = 32 * 1024) {
   FwdCfg c{};
   uint32_t R = kTmemCols / (2 * c_cols);                // accumulator set is double buffered
   R = R >= 4 ? 4 : (R >= 2 ? 2 : 1);
@@ -51,13 +60,25 @@ inline FwdCfg fwd_config(uint32_t c_red, uint32_t c_cols, uint32_t n_rows) {
   c.R = R;
   c.n_super = cdiv_u(tiles, R);
   const int cands[3] = {64, 32, 16};
+  uint64_t best_score = 0;
   for (int cand : cands) {
     if (c_red % cand != 0) continue;
-    uint32_t a_bytes = kTileM * cand * 2;
-    uint32_t b_bytes = ((c_cols * cand * 2 + 1023) / 1024) * 1024;
-    PipeCfg p = pick_pipeline(a_bytes, b_bytes, R, kSmemBudget - kBarBytes - 1024);
-    if (p.lag > c.pipe.lag) { c.pipe = p; c.bk = cand; c.a_stage_bytes = a_bytes; c.b_stage_bytes = b_bytes; }
-    if (p.lag >= 4) break;
+    const uint32_t chunks = c_red / cand;
+    const uint32_t a_sub = kTileM * cand * 2;
+    const uint32_t b_sub = ((c_cols * cand * 2 + 1023) / 1024) * 1024;
+    for (uint32_t cps = chunks; cps >= 1; --cps) {
+      if (chunks % cps != 0 || (cps * a_sub > max_stage_bytes && cps > 1)) continue;
+      PipeCfg p = pick_pipeline(cps * a_sub, cps * b_sub, R, kSmemBudget - kBarBytes - 1024);
+      if (p.lag < 3) continue;
+      // bytes of A in flight, with a mild preference for fat stages (fewer barrier round trips)
+      uint64_t score = (uint64_t)p.lag * cps * a_sub * 8 + (uint64_t)cps * a_sub;
+      if (score > best_score + best_score / 8) {
+        best_score = score;
+        c.pipe = p; c.bk = cand; c.cps = cps; c.a_sub_bytes = a_sub; c.b_sub_bytes = b_sub;
+        c.a_stage_bytes = cps * a_sub; c.b_stage_bytes = cps * b_sub;
+      }
+      break;  // the fattest feasible stage for this chunk width
+    }
   }
   c.smem_bytes = 1024 + c.pipe.nA * c.a_stage_bytes + c.pipe.nB * c.b_stage_bytes + kBarBytes;
   return c;

@@ -20,16 +20,18 @@ int main() {
   for (unsigned cr : chans) for (unsigned cc : ncs) for (unsigned rows : {1u, 129u, 5000u, 800000u}) {
     FwdCfg f = fwd_config(cr, cc, rows);
     bool ok = f.bk != 0 && f.pipe.lag >= 1 && f.smem_bytes <= 227 * 1024 && 2 * f.R * cc <= kTmemCols
-              && f.pipe.nA >= 3 && (f.pipe.nB - 1) * f.R >= f.pipe.nA;
+              && f.pipe.nA >= 3 && f.pipe.nB >= 2 && f.cps >= 1 && (cr / f.bk) % f.cps == 0
+              && f.a_stage_bytes == f.cps * f.a_sub_bytes && f.a_stage_bytes <= 32 * 1024
+              && 2 * f.pipe.nB * f.R >= f.pipe.nA + f.R - 1;  /* B-ring parity safety */
     if (!ok) { printf("FWD BAD cr=%u cc=%u rows=%u bk=%d lag=%u\n", cr, cc, rows, f.bk, f.pipe.lag); ++bad; }
-    printf("fwd %u %u %u : bk=%d R=%u lag=%u nA=%u nB=%u smem=%u\n", cr, cc, rows, f.bk, f.R, f.pipe.lag, f.pipe.nA, f.pipe.nB, f.smem_bytes);
+    printf("fwd %u %u %u : bk=%d cps=%u R=%u depth=%u nA=%u nB=%u smem=%u\n", cr, cc, rows, f.bk, f.cps, f.R, f.pipe.lag, f.pipe.nA, f.pipe.nB, f.smem_bytes);
   }
   const unsigned cins[] = {16, 24, 32, 64, 96, 128, 192, 256, 384, 512};
   for (unsigned ci : cins) for (unsigned co : ncs) for (unsigned K : {1u, 8u, 27u, 125u}) for (unsigned rows : {1u, 300u, 800000u}) {
     WgCfg w = wgrad_config(ci, co, K, rows, 148);
     bool ok = w.mt_cta != 0 && w.pipe.lag >= 1 && w.smem_bytes <= 227 * 1024 &&
               w.G * w.mt_cta * co <= kTmemCols && w.G >= 1 && w.n_splits * w.rows_per_split >= rows
-              && w.pipe.nA >= 3 && (w.pipe.nB - 1) * w.G >= w.pipe.nA;
+              && w.pipe.nA >= 2 && w.pipe.nB >= 2;
     if (w.mt_cta == 0 && co == 256 && K == 1) ok = true;  // declared unsupported -> SIMT fallback
     if (!ok) { printf("WG BAD ci=%u co=%u K=%u rows=%u\n", ci, co, K, rows); ++bad; }
     printf("wg %u %u %u %u : mt=%u G=%u lag=%u nA=%u nB=%u splits=%u smem=%u\n", ci, co, K, rows, w.mt_cta, w.G, w.pipe.lag, w.pipe.nA, w.pipe.nB, w.n_splits, w.smem_bytes);
