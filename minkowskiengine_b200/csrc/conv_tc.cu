@@ -112,6 +112,285 @@ __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
   return *reinterpret_cast<uint32_t *>(&h);
 }
 
+// barrier slots: fullA[kMax] emptyA[kMax] fullB[kMax] emptyB[kMax] tfull[2] tempty[2]
+__device__ __forceinline__ uint32_t bar_fullA(uint32_t b0, uint32_t i) { return b0 + 8u * i; }
+__device__ __forceinline__ uint32_t bar_emptyA(uint32_t b0, uint32_t i) { return b0 + 8u * (kMaxStages + i); }
+__device__ __forceinline__ uint32_t bar_fullB(uint32_t b0, uint32_t i) { return b0 + 8u * (2 * kMaxStages + i); }
+__device__ __forceinline__ uint32_t bar_emptyB(uint32_t b0, uint32_t i) { return b0 + 8u * (3 * kMaxStages + i); }
+__device__ __forceinline__ uint32_t bar_tfull(uint32_t b0, uint32_t i) { return b0 + 8u * (4 * kMaxStages + i); }
+__device__ __forceinline__ uint32_t bar_tempty(uint32_t b0, uint32_t i) { return b0 + 8u * (4 * kMaxStages + 2 + i); }
+
+// Epilogue warps: accumulator (TMEM) -> registers -> converted 16-byte global stores.
+template <typename T, int RT>
+__device__ __forceinline__ void epilogue_role(const TcParams &p, uint32_t bar0, uint32_t tmem_base,
+                                              uint32_t q, uint32_t lane) {
+  constexpr uint32_t R = RT;
+  uint32_t t = 0;
+  for (uint32_t st = blockIdx.x; st < p.n_super; st += gridDim.x, ++t) {
+    const uint32_t acc = t & 1u, par = (t >> 1) & 1u;   // two accumulator sets
+    mbar_wait(bar_tfull(bar0, acc), par);
+    tc_fence_after();
+    for (uint32_t r = 0; r < R; ++r) {
+      const uint32_t row = (st * R + r) * kTileM + q * 32 + lane;
+      const uint32_t col0 = (acc * R + r) * p.c_cols;
+      for (uint32_t c = 0; c < p.c_cols; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((q * 32u) << 16) + col0 + c, v);
+        tmem_ld_wait();
+        if (row < p.n_rows) {
+          if (p.out_f32) {
+            float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) +
+                                                     (size_t)row * p.out_ld + c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                   __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+          } else {
+            uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<T *>(p.out) +
+                                                   (size_t)row * p.out_ld + c);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              uint4 w;
+              w.x = pack2<T>(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]));
+              w.y = pack2<T>(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
+              w.z = pack2<T>(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
+              w.w = pack2<T>(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
+              dst[i] = w;
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    mbar_arrive(bar_tempty(bar0, acc));
+  }
+}
+
+// MMA issuer (one thread): consumes the A/B rings in order, accumulates in TMEM.
+template <typename T, int BK, int RT>
+__device__ __forceinline__ void mma_role(const TcParams &p, uint32_t sA, uint32_t sB, uint32_t bar0,
+                                         uint32_t tmem_base) {
+  using S = Swz<BK>;
+  constexpr uint32_t R = RT;
+  const uint32_t idesc = umma_idesc_f16(Fmt<T>::v, kTileM, p.c_cols, 0, 0);
+  uint32_t t = 0, sa = 0, pha = 0, sb = 0, phb = 0;
+  for (uint32_t st = blockIdx.x; st < p.n_super; st += gridDim.x, ++t) {
+    const uint32_t acc = t & 1u, par = (t >> 1) & 1u;
+    mbar_wait(bar_tempty(bar0, acc), par ^ 1u);
+    tc_fence_after();
+    for (uint32_t k = 0; k < p.K; ++k) {
+      for (uint32_t mc = 0; mc < p.n_macro; ++mc) {
+        mbar_wait(bar_fullB(bar0, sb), phb);
+        const uint32_t bbase = sB + sb * p.b_stage_bytes;
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+          mbar_wait(bar_fullA(bar0, sa), pha);
+          tc_fence_after();
+          const uint32_t abase = sA + sa * p.a_stage_bytes;
+          const uint32_t d = tmem_base + (acc * R + r) * p.c_cols;
+          for (uint32_t s = 0; s < p.cps; ++s) {
+#pragma unroll
+            for (int j = 0; j < BK / 16; ++j) {
+              uint64_t da = umma_desc(abase + s * p.a_sub_bytes + j * 32, 16, S::kSbo, S::kLayout);
+              uint64_t db = umma_desc(bbase + s * p.b_sub_bytes + j * 32, 16, S::kSbo, S::kLayout);
+              umma_f16(d, da, db, idesc, (k | mc | s | (uint32_t)j) != 0u);
+            }
+          }
+          umma_commit(bar_emptyA(bar0, sa));
+          if (++sa == p.nA) { sa = 0; pha ^= 1u; }
+        }
+        umma_commit(bar_emptyB(bar0, sb));
+        if (++sb == p.nB) { sb = 0; phb ^= 1u; }
+      }
+    }
+    umma_commit(bar_tfull(bar0, acc));
+  }
+}
+
+// =====================================================================================
+// Register-staged gather kernel (default forward/dgrad path).
+//
+// Measured on B200 (profiles/r1_gather_bw_microbench.txt): random row gathers are bounded by
+// latency x bytes in flight (~1800 cycles from L2, ~4400 from HBM under load); the TMA
+// row-gather sustains only ~6-8 B/cycle/SM and cp.async keeps zero rows in the ring.  Here the
+// bytes in flight live in REGISTERS: 12 producer warps each own a pipeline stage, compact the
+// valid (tile row, source row) pairs of that stage with ballots, issue up to 16 x 16-byte
+// loads per lane for VALID rows only, then write the tile (zero-filled first) into the
+// swizzled stage with st.shared and publish it (fence.proxy.async + mbarrier arrive).  The B
+// slice comes through the TMA unit (one tile load per channel chunk).
+// =====================================================================================
+constexpr int kRsProducerWarps = 12;
+constexpr int kRsThreads = (kRsProducerWarps + kEpilogueWarps + 1) * 32;
+constexpr int kRsBatch = 16;   // 16-byte loads in flight per lane
+
+__device__ __forceinline__ uint4 ldg128(const void *p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <typename T, int BK, int RT>
+__global__ void __launch_bounds__(kRsThreads, 1)
+k_conv_rs(const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+  using S = Swz<BK>;
+  constexpr int NP = kRsProducerWarps;
+  constexpr uint32_t R = RT;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sA = smem_u32(smem);
+  const uint32_t sB = sA + p.nA * p.a_stage_bytes;
+  uint8_t *tail = smem + p.nA * p.a_stage_bytes + p.nB * p.b_stage_bytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(tail);
+  const uint32_t bar0 = smem_u32(bars);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * kMaxStages + 4);
+  // per-warp compaction scratch: 128 x (source row, tile row)
+  uint2 *scratch_all = reinterpret_cast<uint2 *>(tail + tc::kBarBytes);
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (uint32_t i = 0; i < p.nA; ++i) { mbar_init(bar_fullA(bar0, i), 1); mbar_init(bar_emptyA(bar0, i), 1); }
+    for (uint32_t i = 0; i < p.nB; ++i) { mbar_init(bar_fullB(bar0, i), 1); mbar_init(bar_emptyB(bar0, i), 1); }
+    for (uint32_t i = 0; i < 2; ++i) { mbar_init(bar_tfull(bar0, i), 1); mbar_init(bar_tempty(bar0, i), kEpilogueWarps * 32); }
+    mbar_fence_init();
+  }
+  if (warp == NP + kEpilogueWarps) {
+    tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < NP) {
+    const uint32_t sub_row = lane / S::kChunks, chunk = lane % S::kChunks;
+    const T *A = reinterpret_cast<const T *>(p.A);
+    uint2 *scratch = scratch_all + warp * kTileM;
+    const uint32_t scratch_s = smem_u32(scratch);
+    const uint32_t SPK = p.n_macro * R;
+    const uint32_t SPS = p.K * SPK;
+    const uint32_t n_my = p.n_super > blockIdx.x
+                              ? (p.n_super - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t total = n_my * SPS;
+    struct Pos { uint32_t st, k, mc, r; };
+    auto decode = [&](uint32_t g) {
+      Pos q;
+      const uint32_t t = g / SPS, rem = g - t * SPS;
+      q.st = blockIdx.x + t * gridDim.x;
+      q.k = rem / SPK;
+      const uint32_t rem2 = rem - q.k * SPK;
+      q.mc = rem2 / R;
+      q.r = rem2 - q.mc * R;
+      return q;
+    };
+    int32_t idx_cur[4], idx_nxt[4];
+    auto load_idx = [&](uint32_t g, int32_t (&dst)[4]) {
+      const Pos q = decode(g);
+      const int32_t *nbr_k = p.nbr + (size_t)q.k * p.n_rows;
+      const uint32_t row0 = (q.st * R + q.r) * kTileM + lane;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t grow = row0 + i * 32;
+        dst[i] = (grow < p.n_rows) ? __ldg(nbr_k + grow) : -1;
+      }
+    };
+    // consecutive stages of one warp must be at most one ring revolution apart (parity waits)
+    const uint32_t step = p.nA < (uint32_t)NP ? p.nA : (uint32_t)NP;
+    uint32_t g = warp < step ? warp : total;
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&mapB);
+    if (g < total) load_idx(g, idx_cur);
+    const uint32_t lane_lt = (1u << lane) - 1u;
+    for (; g < total; g += step) {
+      if (g + step < total) load_idx(g + step, idx_nxt);
+      const Pos q = decode(g);
+      const uint32_t sa = g % p.nA, pha = (g / p.nA) & 1u;
+      const uint32_t c0 = q.mc * p.cps * BK;
+      // ---- compact the valid rows of this stage into the warp's scratch list ----------
+      uint32_t V = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool ok = idx_cur[i] >= 0;
+        const uint32_t m = __ballot_sync(0xffffffffu, ok);
+        if (ok) scratch[V + __popc(m & lane_lt)] = make_uint2((uint32_t)idx_cur[i], (uint32_t)(i * 32 + lane));
+        V += __popc(m);
+      }
+      __syncwarp();
+      const uint32_t dstA = sA + sa * p.a_stage_bytes;
+      bool slot_ready = false;
+      for (uint32_t s = 0; s < p.cps; ++s) {
+        const T *srcA = A + c0 + s * BK + chunk * 8;
+        const uint32_t dstS = dstA + s * p.a_sub_bytes;
+        uint32_t e0 = 0;
+        do {
+          // loads for VALID rows only go out first (registers are the landing zone) ...
+          uint4 v[kRsBatch];
+#pragma unroll
+          for (int it = 0; it < kRsBatch; ++it) {
+            const uint32_t e = e0 + it * S::kRowsPerInstr + sub_row;
+            if (e < V) {
+              uint32_t srow;
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(srow) : "r"(scratch_s + e * 8));
+              v[it] = ldg128(srcA + (size_t)srow * p.c_red);
+            }
+          }
+          // ... and only then do we need the ring slot: wait for it, zero it, fill it
+          if (!slot_ready) {
+            mbar_wait(bar_emptyA(bar0, sa), pha ^ 1u);
+            // (the B wait must follow the A wait: passing the A wait is what bounds how far the
+            //  B ring can have advanced, which keeps the one-bit parity wait unambiguous)
+            if (q.r == 0 && lane == 0) {
+              const uint32_t gb = g / R, sb = gb % p.nB, phb = (gb / p.nB) & 1u;
+              mbar_wait(bar_emptyB(bar0, sb), phb ^ 1u);
+              mbar_arrive_expect_tx(bar_fullB(bar0, sb), p.cps * p.c_cols * BK * 2);
+              const uint32_t dstB = sB + sb * p.b_stage_bytes;
+              const int32_t brow = (int32_t)(q.k * p.wb_rows_per_k + p.wb_row0);
+              for (uint32_t sbi = 0; sbi < p.cps; ++sbi)
+                tma_load_2d(dstB + sbi * p.b_sub_bytes, &mapB, (int32_t)(c0 + sbi * BK), brow,
+                            bar_fullB(bar0, sb));
+            }
+            for (uint32_t off = lane * 16; off < p.a_stage_bytes; off += 512)
+              sts128(dstA + off, make_uint4(0, 0, 0, 0));
+            __syncwarp();
+            slot_ready = true;
+          }
+#pragma unroll
+          for (int it = 0; it < kRsBatch; ++it) {
+            const uint32_t e = e0 + it * S::kRowsPerInstr + sub_row;
+            if (e < V) {
+              uint32_t trow;
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(trow) : "r"(scratch_s + e * 8 + 4));
+              sts128(dstS + S::offset(trow, chunk), v[it]);
+            }
+          }
+          e0 += kRsBatch * S::kRowsPerInstr;
+        } while (e0 < V);
+      }
+      fence_proxy_async();          // this lane's st.shared -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_fullA(bar0, sa));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) idx_cur[i] = idx_nxt[i];
+    }
+  } else if (warp < NP + kEpilogueWarps) {
+    epilogue_role<T, RT>(p, bar0, tmem_base, warp & 3u, lane);
+  } else if (lane == 0) {
+    mma_role<T, BK, RT>(p, sA, sB, bar0, tmem_base);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == NP + kEpilogueWarps) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
 // TMA = true : operands are fetched by the TMA unit (row gather4 for A, tile loads for B);
 // TMA = false: cp.async path (kept as a fallback; the LSU-driven copies top out near
 //              20 B/cycle/SM on B200).
@@ -468,14 +747,47 @@ static int make_map_2d(CUtensorMap *m, int dtype, const void *base, uint64_t row
   return MEB200_OK;
 }
 
-static bool tma_enabled() {
+// operand-A fetch strategy: 2 = register staged (default), 1 = TMA row gather, 0 = cp.async
+static int gather_mode() {
   static int v = -1;
   if (v < 0) {
-    const char *e = getenv("MEB200_TC_GATHER");   // "tma" (default) | "cpasync"
-    v = (e && e[0] == 'c') ? 0 : 1;
-    if (v == 1 && encode_tiled_fn() == nullptr) v = 0;
+    const char *e = getenv("MEB200_TC_GATHER");   // "rs" (default) | "tma" | "cpasync"
+    v = (e && e[0] == 'c') ? 0 : ((e && e[0] == 't') ? 1 : 2);
+    if (v != 0 && encode_tiled_fn() == nullptr) v = 0;
   }
-  return v == 1;
+  return v;
+}
+
+template <typename T, int BK, int RT>
+static int launch_rs(const CUtensorMap &mB, const TcParams &p, size_t smem_bytes, unsigned grid,
+                     cudaStream_t stream) {
+  auto kern = k_conv_rs<T, BK, RT>;
+  static bool configured = false;
+  if (!configured) {
+    MEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  kern<<<grid, kRsThreads, smem_bytes, stream>>>(mB, p);
+  count_tc_launch();
+  MEB_LAUNCH_OK();
+  return MEB200_OK;
+}
+
+template <typename T>
+static int launch_rs_bk_r(int bk, uint32_t R, const CUtensorMap &mB, const TcParams &p, size_t smem,
+                          unsigned grid, cudaStream_t s) {
+#define MEB_RS_R(BKV)                                                  \
+  switch (R) {                                                         \
+    case 4: return launch_rs<T, BKV, 4>(mB, p, smem, grid, s);         \
+    case 2: return launch_rs<T, BKV, 2>(mB, p, smem, grid, s);         \
+    default: return launch_rs<T, BKV, 1>(mB, p, smem, grid, s);        \
+  }
+  switch (bk) {
+    case 64: MEB_RS_R(64)
+    case 32: MEB_RS_R(32)
+    default: MEB_RS_R(16)
+  }
+#undef MEB_RS_R
 }
 
 template <typename T, int BK, int RT, bool TMA>
@@ -538,7 +850,14 @@ static int launch_tc_slice(const void *A, int dtype, uint32_t n_a, uint32_t c_re
     max_stage_kb = e ? atoi(e) : 32;
     if (max_stage_kb <= 0) max_stage_kb = 32;
   }
-  const tc::FwdCfg cfg = tc::fwd_config(c_reduce, c_cols, n_rows, (uint32_t)max_stage_kb * 1024);
+  const bool aligned = (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(Wb_full) & 15) == 0;
+  const int mode = (n_a > 0 && aligned) ? gather_mode() : 0;
+  // register-staged mode: one channel chunk per stage (many small stages keep all producer
+  // warps busy; the bytes in flight live in registers, not in the ring)
+  const tc::FwdCfg cfg = mode == 2
+      ? tc::fwd_config(c_reduce, c_cols, n_rows, 16 * 1024, tc::kRsScratchBytes)
+      : tc::fwd_config(c_reduce, c_cols, n_rows, (uint32_t)max_stage_kb * 1024, 0);
   if (cfg.bk == 0 || cfg.pipe.lag < 1) {
     set_error("conv tc: no pipeline configuration fits (c_red=%u c_cols=%u)", c_reduce, c_cols);
     return MEB200_ERR_UNSUPPORTED;
@@ -555,14 +874,19 @@ static int launch_tc_slice(const void *A, int dtype, uint32_t n_a, uint32_t c_re
   CUtensorMap mA, mB;
   memset(&mA, 0, sizeof(mA));
   memset(&mB, 0, sizeof(mB));
-  const bool tma = tma_enabled() && n_a > 0 &&
-                   (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
-                   (reinterpret_cast<uintptr_t>(Wb_full) & 15) == 0;
-  if (tma) {
-    int rc = make_map_2d(&mA, dtype, A, n_a, c_reduce, (uint32_t)bk, 1);
+  const bool tma = mode == 1;
+  if (mode != 0) {
+    int rc = make_map_2d(&mB, dtype, Wb_full, (uint64_t)K * c_cols_full, c_reduce, (uint32_t)bk, c_cols);
     if (rc != MEB200_OK) return rc;
-    rc = make_map_2d(&mB, dtype, Wb_full, (uint64_t)K * c_cols_full, c_reduce, (uint32_t)bk, c_cols);
-    if (rc != MEB200_OK) return rc;
+    if (mode == 1) {
+      rc = make_map_2d(&mA, dtype, A, n_a, c_reduce, (uint32_t)bk, 1);
+      if (rc != MEB200_OK) return rc;
+    }
+  }
+  if (mode == 2) {
+    if (dtype == MEB200_BF16)
+      return launch_rs_bk_r<__nv_bfloat16>(bk, R, mB, p, smem_bytes, grid, stream);
+    return launch_rs_bk_r<__half>(bk, R, mB, p, smem_bytes, grid, stream);
   }
   if (dtype == MEB200_BF16)
     return launch_tc_bk_r<__nv_bfloat16>(bk, R, tma, mA, mB, p, smem_bytes, grid, stream);

@@ -51,7 +51,10 @@ struct FwdCfg {
   PipeCfg pipe;
   uint32_t smem_bytes;
 };
-inline FwdCfg fwd_config(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, uint32_t max_stage_bytes = 32 * 1024) {
+constexpr uint32_t kRsScratchBytes = 12 * 128 * 8;     // register-staged kernel: per-warp compaction lists
+
+inline FwdCfg fwd_config(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, uint32_t max_stage_bytes = 32 * 1024,
+                         uint32_t extra_bytes = 0) {
   FwdCfg c{};
   uint32_t R = kTmemCols / (2 * c_cols);                // accumulator set is double buffered
   R = R >= 4 ? 4 : (R >= 2 ? 2 : 1);
@@ -68,7 +71,7 @@ inline FwdCfg fwd_config(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, uint3
     const uint32_t b_sub = ((c_cols * cand * 2 + 1023) / 1024) * 1024;
     for (uint32_t cps = chunks; cps >= 1; --cps) {
       if (chunks % cps != 0 || (cps * a_sub > max_stage_bytes && cps > 1)) continue;
-      PipeCfg p = pick_pipeline(cps * a_sub, cps * b_sub, R, kSmemBudget - kBarBytes - 1024);
+      PipeCfg p = pick_pipeline(cps * a_sub, cps * b_sub, R, kSmemBudget - kBarBytes - 1024 - extra_bytes);
       if (p.lag < 3) continue;
       // bytes of A in flight, with a mild preference for fat stages (fewer barrier round trips)
       uint64_t score = (uint64_t)p.lag * cps * a_sub * 8 + (uint64_t)cps * a_sub;
@@ -80,7 +83,7 @@ inline FwdCfg fwd_config(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, uint3
       break;  // the fattest feasible stage for this chunk width
     }
   }
-  c.smem_bytes = 1024 + c.pipe.nA * c.a_stage_bytes + c.pipe.nB * c.b_stage_bytes + kBarBytes;
+  c.smem_bytes = 1024 + c.pipe.nA * c.a_stage_bytes + c.pipe.nB * c.b_stage_bytes + kBarBytes + extra_bytes;
   return c;
 }
 
