@@ -207,6 +207,89 @@ __device__ __forceinline__ void mma_role(const TcParams &p, uint32_t sA, uint32_
   }
 }
 
+// MMA issuer, lean version: the WHOLE warp runs the loop with warp-uniform state (ring
+// addresses advance by adds, descriptor words are 32-bit adds of compile-time offsets) and one
+// elected lane issues.  A single thread can retire only ~1 dependent instruction per 4-6 cycles,
+// so every instruction here is on the critical path of the tensor pipe (ncu: the first version,
+// ~250 instructions per stage, held the pipe to ~13% busy).
+template <typename T, int BK, int RT, int CPS>
+__device__ __forceinline__ void mma_role_fast(const TcParams &p, uint32_t sA, uint32_t sB,
+                                              uint32_t bar0, uint32_t tmem_base) {
+  using S = Swz<BK>;
+  constexpr uint32_t R = RT;
+  constexpr uint32_t kHi = umma_desc_hi(S::kSbo, S::kLayout);
+  constexpr uint32_t kASub16 = (kTileM * BK * 2) >> 4;
+  const uint32_t idesc = umma_idesc_f16(Fmt<T>::v, kTileM, p.c_cols, 0, 0);
+  const uint32_t a_lo0 = umma_desc_lo(sA, 16), b_lo0 = umma_desc_lo(sB, 16);
+  const uint32_t a_inc = p.a_stage_bytes >> 4, b_inc = p.b_stage_bytes >> 4, b_sub16 = p.b_sub_bytes >> 4;
+  uint32_t a_lo = a_lo0, b_lo = b_lo0;
+  uint32_t sa = 0, pha = 0, sb = 0, phb = 0, t = 0;
+  const uint32_t n_groups = p.K * p.n_macro;
+  for (uint32_t st = blockIdx.x; st < p.n_super; st += gridDim.x, ++t) {
+    const uint32_t acc = t & 1u, par = (t >> 1) & 1u;
+    mbar_wait(bar_tempty(bar0, acc), par ^ 1u);
+    tc_fence_after();
+    const uint32_t d0 = tmem_base + acc * R * p.c_cols;
+    for (uint32_t grp = 0; grp < n_groups; ++grp) {
+      mbar_wait(bar_fullB(bar0, sb), phb);
+#pragma unroll
+      for (int r = 0; r < RT; ++r) {
+        mbar_wait(bar_fullA(bar0, sa), pha);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t d = d0 + r * p.c_cols;
+#pragma unroll
+          for (int sc = 0; sc < CPS; ++sc) {
+#pragma unroll
+            for (int j = 0; j < BK / 16; ++j) {
+              const uint64_t da = pack_desc(a_lo + sc * kASub16 + j * 2, kHi);
+              const uint64_t db = pack_desc(b_lo + sc * b_sub16 + j * 2, kHi);
+              umma_f16(d, da, db, idesc, (sc | j) != 0 ? 1u : (grp != 0u));
+            }
+          }
+          umma_commit(bar_emptyA(bar0, sa));
+          if (r == RT - 1) umma_commit(bar_emptyB(bar0, sb));
+        }
+        __syncwarp();
+        a_lo += a_inc;
+        if (++sa == p.nA) { sa = 0; pha ^= 1u; a_lo = a_lo0; }
+      }
+      b_lo += b_inc;
+      if (++sb == p.nB) { sb = 0; phb ^= 1u; b_lo = b_lo0; }
+    }
+    if (elect_one()) umma_commit(bar_tfull(bar0, acc));
+    __syncwarp();
+  }
+}
+
+// Flow control for the register-staged kernels.  The producer warps do not wait on the
+// "empty" mbarriers themselves: with more producer warps than ring slots a one-bit parity wait
+// could be satisfied by a phase two uses back.  Instead ONE thread (lane 1 of the MMA warp)
+// consumes the empty-barrier completions strictly in order and publishes monotonically
+// increasing counters in shared memory; a producer may fill stage g once consumed + ring > g.
+template <int RT>
+__device__ __forceinline__ void release_role(const TcParams &p, uint32_t bar0,
+                                             volatile uint32_t *consumed /* [0]=A stages, [1]=B */) {
+  uint32_t sa = 0, pha = 0, sb = 0, phb = 0, nA_done = 0, nB_done = 0;
+  for (uint32_t st = blockIdx.x; st < p.n_super; st += gridDim.x) {
+    for (uint32_t k = 0; k < p.K; ++k) {
+      for (uint32_t mc = 0; mc < p.n_macro; ++mc) {
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+          mbar_wait(bar_emptyA(bar0, sa), pha);
+          __threadfence_block();
+          consumed[0] = ++nA_done;
+          if (++sa == p.nA) { sa = 0; pha ^= 1u; }
+        }
+        mbar_wait(bar_emptyB(bar0, sb), phb);
+        __threadfence_block();
+        consumed[1] = ++nB_done;
+        if (++sb == p.nB) { sb = 0; phb ^= 1u; }
+      }
+    }
+  }
+}
+
 // =====================================================================================
 // Register-staged gather kernel (default forward/dgrad path).
 //
@@ -219,9 +302,27 @@ __device__ __forceinline__ void mma_role(const TcParams &p, uint32_t sA, uint32_
 // swizzled stage with st.shared and publish it (fence.proxy.async + mbarrier arrive).  The B
 // slice comes through the TMA unit (one tile load per channel chunk).
 // =====================================================================================
-constexpr int kRsProducerWarps = 12;
-constexpr int kRsThreads = (kRsProducerWarps + kEpilogueWarps + 1) * 32;
-constexpr int kRsBatch = 16;   // 16-byte loads in flight per lane
+constexpr int kRsProducerWarps = 10;
+constexpr int kRsThreads = (kRsProducerWarps + kEpilogueWarps + 2) * 32;   // + MMA warp + release warp
+constexpr int kRsBatch = 16;   // 16-byte loads in flight per lane (18 with 3 chunks per stage)
+
+// Wait until `*ctr + ring > g` (slot of stage g recycled): lane 0 polls with back-off, the rest
+// of the warp parks at the __syncwarp instead of hammering shared memory.
+__device__ __forceinline__ void wait_consumed(volatile uint32_t *ctr, uint32_t g, uint32_t ring,
+                                              uint32_t lane) {
+  if (lane == 0) {
+    while ((int32_t)(g - *ctr) >= (int32_t)ring) __nanosleep(40);
+  }
+  __syncwarp();
+  __threadfence_block();
+}
+
+// Make the thread wait until the given loaded words have really arrived (their first use is
+// what blocks on the scoreboard).  Called BEFORE a ring slot is acquired: a slot must never be
+// held across a global-memory latency.
+__device__ __forceinline__ void force_arrival(uint32_t x) {
+  if (x == 0x9e3779b9u) asm volatile("nanosleep.u32 1;" ::: "memory");
+}
 
 __device__ __forceinline__ uint4 ldg128(const void *p) {
   uint4 v;
@@ -233,7 +334,7 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-template <typename T, int BK, int RT>
+template <typename T, int BK, int RT, int CPS>
 __global__ void __launch_bounds__(kRsThreads, 1)
 k_conv_rs(const __grid_constant__ CUtensorMap mapB, const TcParams p) {
   using S = Swz<BK>;
@@ -248,8 +349,10 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapB, const TcParams p) {
   uint64_t *bars = reinterpret_cast<uint64_t *>(tail);
   const uint32_t bar0 = smem_u32(bars);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * kMaxStages + 4);
-  // per-warp compaction scratch: 128 x (source row, tile row)
+  // per-warp compaction scratch: 128 x (source row, tile row); then the flow-control counters
   uint2 *scratch_all = reinterpret_cast<uint2 *>(tail + tc::kBarBytes);
+  volatile uint32_t *consumed = reinterpret_cast<volatile uint32_t *>(
+      tail + tc::kBarBytes + kRsProducerWarps * kTileM * 8);
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -258,6 +361,8 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapB, const TcParams p) {
     for (uint32_t i = 0; i < p.nB; ++i) { mbar_init(bar_fullB(bar0, i), 1); mbar_init(bar_emptyB(bar0, i), 1); }
     for (uint32_t i = 0; i < 2; ++i) { mbar_init(bar_tfull(bar0, i), 1); mbar_init(bar_tempty(bar0, i), kEpilogueWarps * 32); }
     mbar_fence_init();
+    consumed[0] = 0;
+    consumed[1] = 0;
   }
   if (warp == NP + kEpilogueWarps) {
     tmem_alloc(smem_u32(tmem_slot), kTmemCols);
@@ -300,16 +405,15 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapB, const TcParams p) {
         dst[i] = (grow < p.n_rows) ? __ldg(nbr_k + grow) : -1;
       }
     };
-    // consecutive stages of one warp must be at most one ring revolution apart (parity waits)
-    const uint32_t step = p.nA < (uint32_t)NP ? p.nA : (uint32_t)NP;
-    uint32_t g = warp < step ? warp : total;
+    constexpr uint32_t step = NP;   // every producer warp takes stages (see release_role)
+    uint32_t g = warp;
     if (warp == 0 && lane == 0) tma_prefetch_desc(&mapB);
     if (g < total) load_idx(g, idx_cur);
     const uint32_t lane_lt = (1u << lane) - 1u;
     for (; g < total; g += step) {
       if (g + step < total) load_idx(g + step, idx_nxt);
       const Pos q = decode(g);
-      const uint32_t sa = g % p.nA, pha = (g / p.nA) & 1u;
+      const uint32_t sa = g % p.nA;
       const uint32_t c0 = q.mc * p.cps * BK;
       // ---- compact the valid rows of this stage into the warp's scratch list ----------
       uint32_t V = 0;
@@ -323,54 +427,59 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapB, const TcParams p) {
       __syncwarp();
       const uint32_t dstA = sA + sa * p.a_stage_bytes;
       bool slot_ready = false;
-      for (uint32_t s = 0; s < p.cps; ++s) {
-        const T *srcA = A + c0 + s * BK + chunk * 8;
-        const uint32_t dstS = dstA + s * p.a_sub_bytes;
-        uint32_t e0 = 0;
-        do {
-          // loads for VALID rows only go out first (registers are the landing zone) ...
-          uint4 v[kRsBatch];
+      constexpr int kRowIters = (CPS == 3 ? 18 : kRsBatch) / CPS;      // row groups per batch
+      constexpr uint32_t kRowsPerBatch = kRowIters * S::kRowsPerInstr;
+      const T *srcA = A + c0 + chunk * 8;
+      uint32_t e0 = 0;
+      do {
+        // loads for VALID rows only go out first (registers are the landing zone) ...
+        uint4 v[kRowIters * CPS];
 #pragma unroll
-          for (int it = 0; it < kRsBatch; ++it) {
-            const uint32_t e = e0 + it * S::kRowsPerInstr + sub_row;
-            if (e < V) {
-              uint32_t srow;
-              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(srow) : "r"(scratch_s + e * 8));
-              v[it] = ldg128(srcA + (size_t)srow * p.c_red);
-            }
-          }
-          // ... and only then do we need the ring slot: wait for it, zero it, fill it
-          if (!slot_ready) {
-            mbar_wait(bar_emptyA(bar0, sa), pha ^ 1u);
-            // (the B wait must follow the A wait: passing the A wait is what bounds how far the
-            //  B ring can have advanced, which keeps the one-bit parity wait unambiguous)
-            if (q.r == 0 && lane == 0) {
-              const uint32_t gb = g / R, sb = gb % p.nB, phb = (gb / p.nB) & 1u;
-              mbar_wait(bar_emptyB(bar0, sb), phb ^ 1u);
-              mbar_arrive_expect_tx(bar_fullB(bar0, sb), p.cps * p.c_cols * BK * 2);
-              const uint32_t dstB = sB + sb * p.b_stage_bytes;
-              const int32_t brow = (int32_t)(q.k * p.wb_rows_per_k + p.wb_row0);
-              for (uint32_t sbi = 0; sbi < p.cps; ++sbi)
-                tma_load_2d(dstB + sbi * p.b_sub_bytes, &mapB, (int32_t)(c0 + sbi * BK), brow,
-                            bar_fullB(bar0, sb));
-            }
-            for (uint32_t off = lane * 16; off < p.a_stage_bytes; off += 512)
-              sts128(dstA + off, make_uint4(0, 0, 0, 0));
-            __syncwarp();
-            slot_ready = true;
-          }
+        for (int ri = 0; ri < kRowIters; ++ri) {
+          const uint32_t e = e0 + ri * S::kRowsPerInstr + sub_row;
+          if (e < V) {
+            uint32_t srow;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(srow) : "r"(scratch_s + e * 8));
+            const T *src = srcA + (size_t)srow * p.c_red;
 #pragma unroll
-          for (int it = 0; it < kRsBatch; ++it) {
-            const uint32_t e = e0 + it * S::kRowsPerInstr + sub_row;
-            if (e < V) {
-              uint32_t trow;
-              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(trow) : "r"(scratch_s + e * 8 + 4));
-              sts128(dstS + S::offset(trow, chunk), v[it]);
-            }
+            for (int sc = 0; sc < CPS; ++sc) v[ri * CPS + sc] = ldg128(src + sc * BK);
+          } else {
+#pragma unroll
+            for (int sc = 0; sc < CPS; ++sc) v[ri * CPS + sc] = make_uint4(0, 0, 0, 0);
           }
-          e0 += kRsBatch * S::kRowsPerInstr;
-        } while (e0 < V);
-      }
+        }
+        // ... and only then take the ring slot: wait for it, zero it, fill it
+        if (!slot_ready) {
+          wait_consumed(consumed, g, p.nA, lane);   // ring slot still in use?
+          if (q.r == 0 && lane == 0) {
+            const uint32_t gb = g / R, sb = gb % p.nB;
+            while ((int32_t)(gb - consumed[1]) >= (int32_t)p.nB) __nanosleep(40);
+            __threadfence_block();
+            mbar_arrive_expect_tx(bar_fullB(bar0, sb), CPS * p.c_cols * BK * 2);
+            const uint32_t dstB = sB + sb * p.b_stage_bytes;
+            const int32_t brow = (int32_t)(q.k * p.wb_rows_per_k + p.wb_row0);
+            for (uint32_t sbi = 0; sbi < (uint32_t)CPS; ++sbi)
+              tma_load_2d(dstB + sbi * p.b_sub_bytes, &mapB, (int32_t)(c0 + sbi * BK), brow,
+                          bar_fullB(bar0, sb));
+          }
+          for (uint32_t off = lane * 16; off < p.a_stage_bytes; off += 512)
+            sts128(dstA + off, make_uint4(0, 0, 0, 0));
+          __syncwarp();
+          slot_ready = true;
+        }
+#pragma unroll
+        for (int ri = 0; ri < kRowIters; ++ri) {
+          const uint32_t e = e0 + ri * S::kRowsPerInstr + sub_row;
+          if (e < V) {
+            uint32_t trow;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(trow) : "r"(scratch_s + e * 8 + 4));
+            const uint32_t dst = dstA + S::offset(trow, chunk);
+#pragma unroll
+            for (int sc = 0; sc < CPS; ++sc) sts128(dst + sc * p.a_sub_bytes, v[ri * CPS + sc]);
+          }
+        }
+        e0 += kRowsPerBatch;
+      } while (e0 < V);
       fence_proxy_async();          // this lane's st.shared -> visible to the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_fullA(bar0, sa));
@@ -379,8 +488,11 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapB, const TcParams p) {
     }
   } else if (warp < NP + kEpilogueWarps) {
     epilogue_role<T, RT>(p, bar0, tmem_base, warp & 3u, lane);
+  } else if (warp == NP + kEpilogueWarps) {
+    mma_role_fast<T, BK, RT, CPS>(p, sA, sB, bar0, tmem_base);   // whole warp, one lane issues
   } else if (lane == 0) {
-    mma_role<T, BK, RT>(p, sA, sB, bar0, tmem_base);
+    // its own warp: a thread parked in mbarrier.try_wait must not hold up the MMA issuer
+    release_role<RT>(p, bar0, consumed);
   }
 
   tc_fence_before();
@@ -758,10 +870,10 @@ static int gather_mode() {
   return v;
 }
 
-template <typename T, int BK, int RT>
+template <typename T, int BK, int RT, int CPS>
 static int launch_rs(const CUtensorMap &mB, const TcParams &p, size_t smem_bytes, unsigned grid,
                      cudaStream_t stream) {
-  auto kern = k_conv_rs<T, BK, RT>;
+  auto kern = k_conv_rs<T, BK, RT, CPS>;
   static bool configured = false;
   if (!configured) {
     MEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -774,19 +886,24 @@ static int launch_rs(const CUtensorMap &mB, const TcParams &p, size_t smem_bytes
 }
 
 template <typename T>
-static int launch_rs_bk_r(int bk, uint32_t R, const CUtensorMap &mB, const TcParams &p, size_t smem,
-                          unsigned grid, cudaStream_t s) {
-#define MEB_RS_R(BKV)                                                  \
-  switch (R) {                                                         \
-    case 4: return launch_rs<T, BKV, 4>(mB, p, smem, grid, s);         \
-    case 2: return launch_rs<T, BKV, 2>(mB, p, smem, grid, s);         \
-    default: return launch_rs<T, BKV, 1>(mB, p, smem, grid, s);        \
+static int launch_rs_bk_r(int bk, uint32_t R, uint32_t cps, const CUtensorMap &mB, const TcParams &p,
+                          size_t smem, unsigned grid, cudaStream_t s) {
+#define MEB_RS_R(BKV, CP)                                                  \
+  switch (R) {                                                             \
+    case 4: return launch_rs<T, BKV, 4, CP>(mB, p, smem, grid, s);         \
+    case 2: return launch_rs<T, BKV, 2, CP>(mB, p, smem, grid, s);         \
+    default: return launch_rs<T, BKV, 1, CP>(mB, p, smem, grid, s);        \
   }
-  switch (bk) {
-    case 64: MEB_RS_R(64)
-    case 32: MEB_RS_R(32)
-    default: MEB_RS_R(16)
+  if (bk == 64) {
+    if (cps == 2) { MEB_RS_R(64, 2) }
+    MEB_RS_R(64, 1)
   }
+  if (bk == 32) {
+    if (cps == 3) { MEB_RS_R(32, 3) }
+    MEB_RS_R(32, 1)
+  }
+  if (cps == 3) { MEB_RS_R(16, 3) }
+  MEB_RS_R(16, 1)
 #undef MEB_RS_R
 }
 
@@ -853,11 +970,10 @@ static int launch_tc_slice(const void *A, int dtype, uint32_t n_a, uint32_t c_re
   const bool aligned = (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
                        (reinterpret_cast<uintptr_t>(Wb_full) & 15) == 0;
   const int mode = (n_a > 0 && aligned) ? gather_mode() : 0;
-  // register-staged mode: one channel chunk per stage (many small stages keep all producer
-  // warps busy; the bytes in flight live in registers, not in the ring)
-  const tc::FwdCfg cfg = mode == 2
-      ? tc::fwd_config(c_reduce, c_cols, n_rows, 16 * 1024, tc::kRsScratchBytes)
-      : tc::fwd_config(c_reduce, c_cols, n_rows, (uint32_t)max_stage_kb * 1024, 0);
+  tc::FwdCfg cfg = tc::fwd_config(c_reduce, c_cols, n_rows, (uint32_t)max_stage_kb * 1024,
+                                  mode == 2 ? tc::kRsScratchBytes : 0);
+  if (mode == 2 && !((cfg.bk == 64 && cfg.cps <= 2) || (cfg.bk != 64 && (cfg.cps == 1 || cfg.cps == 3))))
+    cfg = tc::fwd_config(c_reduce, c_cols, n_rows, 1, tc::kRsScratchBytes);   // one chunk per stage
   if (cfg.bk == 0 || cfg.pipe.lag < 1) {
     set_error("conv tc: no pipeline configuration fits (c_red=%u c_cols=%u)", c_reduce, c_cols);
     return MEB200_ERR_UNSUPPORTED;
@@ -885,8 +1001,8 @@ static int launch_tc_slice(const void *A, int dtype, uint32_t n_a, uint32_t c_re
   }
   if (mode == 2) {
     if (dtype == MEB200_BF16)
-      return launch_rs_bk_r<__nv_bfloat16>(bk, R, mB, p, smem_bytes, grid, stream);
-    return launch_rs_bk_r<__half>(bk, R, mB, p, smem_bytes, grid, stream);
+      return launch_rs_bk_r<__nv_bfloat16>(bk, R, cfg.cps, mB, p, smem_bytes, grid, stream);
+    return launch_rs_bk_r<__half>(bk, R, cfg.cps, mB, p, smem_bytes, grid, stream);
   }
   if (dtype == MEB200_BF16)
     return launch_tc_bk_r<__nv_bfloat16>(bk, R, tma, mA, mB, p, smem_bytes, grid, stream);
@@ -1126,6 +1242,245 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(const WgParams p) {
   }
 }
 
+// =====================================================================================
+// wgrad, register-staged with pair compaction (default).  Only the VALID (input row, output
+// row) pairs of an offset enter the reduction: a producer warp scans a 64-row window of the
+// neighbour table, compacts its hits with ballots, loads both rows of every pair through
+// registers and writes them as consecutive K-rows of the stage; the MMA thread reads the pair
+// count of the stage and issues ceil(V/16) K-steps.  No zero rows are fetched, multiplied or
+// kept in the ring (the dense variant above spends ~70% of all three on them).
+// =====================================================================================
+struct WgRsParams {
+  const void *in, *gout;
+  const int32_t *nbr;
+  float *dW;
+  uint32_t c_in, c_out, K, n_out;
+  uint32_t G, n_kgroups, mt_cta, n_mtgroups, rows_per_split, n_splits;
+  uint32_t blkA, blkB, nS, stage_bytes;
+};
+constexpr int kWgRsWarps = (int)tc::kWgRsProducerWarps;
+constexpr int kWgRsThreads = (kWgRsWarps + kEpilogueWarps + 2) * 32;   // + MMA warp + release warp
+
+template <typename T>
+__global__ void __launch_bounds__(kWgRsThreads, 1) k_wgrad_rs(const WgRsParams p) {
+  constexpr int NP = kWgRsWarps;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sS = smem_u32(smem);
+  uint8_t *tail = smem + p.nS * p.stage_bytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(tail);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full = [&](uint32_t i) { return bar0 + 8u * i; };
+  auto empty = [&](uint32_t i) { return bar0 + 8u * (kMaxStages + i); };
+  const uint32_t tfull = bar0 + 8u * (4 * kMaxStages);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * kMaxStages + 4);
+  uint2 *scratch_all = reinterpret_cast<uint2 *>(tail + tc::kBarBytes);
+  volatile uint32_t *cnt = reinterpret_cast<volatile uint32_t *>(tail + tc::kBarBytes + NP * kWgRows * 8);
+  volatile uint32_t *consumed = cnt + kMaxStages;
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t wi = blockIdx.x;
+  const uint32_t kg = wi % p.n_kgroups; wi /= p.n_kgroups;
+  const uint32_t mtg = wi % p.n_mtgroups; wi /= p.n_mtgroups;
+  const uint32_t split = wi;
+  const uint32_t k0 = kg * p.G;
+  const uint32_t G = min(p.G, p.K - k0);
+  const uint32_t r_begin = split * p.rows_per_split;
+  const uint32_t r_end = min(r_begin + p.rows_per_split, p.n_out);
+  const uint32_t n_win = (r_end - r_begin + kWgRows - 1) / kWgRows;
+  const uint32_t total = G * n_win;
+  const uint32_t ch0 = mtg * p.mt_cta * 128;
+  const uint32_t mt = min(p.mt_cta, (p.c_in - ch0 + 127) / 128);
+
+  if (threadIdx.x == 0) {
+    for (uint32_t i = 0; i < p.nS; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); }
+    mbar_init(tfull, 1);
+    mbar_fence_init();
+    consumed[0] = 0;
+  }
+  if (warp == NP + kEpilogueWarps) {
+    tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < NP) {
+    const uint32_t sub_row = lane >> 3, j8 = lane & 7;
+    const T *in = reinterpret_cast<const T *>(p.in);
+    const T *gout = reinterpret_cast<const T *>(p.gout);
+    uint2 *scratch = scratch_all + warp * kWgRows;
+    const uint32_t scratch_s = smem_u32(scratch);
+    const uint32_t lane_lt = (1u << lane) - 1u;
+    int32_t idx_cur[2], idx_nxt[2];
+    auto load_idx = [&](uint32_t g, int32_t (&dst)[2]) {
+      const uint32_t kk = g / n_win, w = g - kk * n_win;
+      const int32_t *nbr_k = p.nbr + (size_t)(k0 + kk) * p.n_out;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const uint32_t o = r_begin + w * kWgRows + i * 32 + lane;
+        dst[i] = (o < r_end) ? __ldg(nbr_k + o) : -1;
+      }
+    };
+    uint32_t g = warp;
+    if (g < total) load_idx(g, idx_cur);
+    for (; g < total; g += NP) {
+      if (g + NP < total) load_idx(g + NP, idx_nxt);
+      const uint32_t kk = g / n_win, w = g - kk * n_win;
+      const uint32_t o0 = r_begin + w * kWgRows;
+      const uint32_t slot = g % p.nS;
+      (void)kk;
+      // ---- compact the hits of this 64-row window ---------------------------------------
+      uint32_t V = 0;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const bool ok = idx_cur[i] >= 0;
+        const uint32_t m = __ballot_sync(0xffffffffu, ok);
+        if (ok) scratch[V + __popc(m & lane_lt)] = make_uint2((uint32_t)idx_cur[i], o0 + i * 32 + lane);
+        V += __popc(m);
+      }
+      __syncwarp();
+      const uint32_t n16 = V == 0 ? 1u : (V + 15u) / 16u;
+      const uint32_t dstS = sS + slot * p.stage_bytes;
+      bool slot_ready = false;
+      // Both operands of a batch of pairs are loaded into registers first (gathered input rows
+      // -> blkA blocks, gathered dOut rows -> blkB blocks); the ring slot is taken only once the
+      // data has arrived.
+      const uint32_t itsA = 10u / p.blkA, itsB = 10u / p.blkB;
+      const uint32_t its = itsA < itsB ? itsA : itsB;
+      const uint32_t dstB0 = dstS + p.blkA * kBlkBytes;
+      uint32_t e0 = 0;
+      do {
+        uint4 va[10], vb[10];
+        uint32_t x = 0;
+#pragma unroll
+        for (int q = 0; q < 10; ++q) {
+          const uint32_t it = (uint32_t)q / p.blkA, blk = (uint32_t)q - it * p.blkA;
+          const uint32_t e = e0 + it * 4 + sub_row;
+          const uint32_t chn = ch0 + blk * 64 + j8 * 8;
+          va[q] = make_uint4(0, 0, 0, 0);
+          if (it < its && e < V && chn < p.c_in) {
+            uint32_t row;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(scratch_s + e * 8));
+            va[q] = ldg128(in + (size_t)row * p.c_in + chn);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 10; ++q) {
+          const uint32_t it = (uint32_t)q / p.blkB, blk = (uint32_t)q - it * p.blkB;
+          const uint32_t e = e0 + it * 4 + sub_row;
+          const uint32_t chn = blk * 64 + j8 * 8;
+          vb[q] = make_uint4(0, 0, 0, 0);
+          if (it < its && e < V && chn < p.c_out) {
+            uint32_t row;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(scratch_s + e * 8 + 4));
+            vb[q] = ldg128(gout + (size_t)row * p.c_out + chn);
+          }
+        }
+        (void)x;
+        if (!slot_ready) {
+          wait_consumed(consumed, g, p.nS, lane);
+          slot_ready = true;
+        }
+        // rows V..16*n16-1 are the zero padding of the last K-step
+#pragma unroll
+        for (int q = 0; q < 10; ++q) {
+          const uint32_t it = (uint32_t)q / p.blkA, blk = (uint32_t)q - it * p.blkA;
+          const uint32_t e = e0 + it * 4 + sub_row;
+          if (it < its && e < n16 * 16u)
+            sts128(dstS + blk * kBlkBytes + e * 128 + ((j8 ^ (e & 7u)) << 4), va[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 10; ++q) {
+          const uint32_t it = (uint32_t)q / p.blkB, blk = (uint32_t)q - it * p.blkB;
+          const uint32_t e = e0 + it * 4 + sub_row;
+          if (it < its && e < n16 * 16u)
+            sts128(dstB0 + blk * kBlkBytes + e * 128 + ((j8 ^ (e & 7u)) << 4), vb[q]);
+        }
+        e0 += its * 4;
+      } while (e0 < n16 * 16u);
+      if (lane == 0) cnt[slot] = V;
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full(slot));
+#pragma unroll
+      for (int i = 0; i < 2; ++i) idx_cur[i] = idx_nxt[i];
+    }
+  } else if (warp < NP + kEpilogueWarps) {
+    const uint32_t q = warp & 3u;
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    for (uint32_t kk = 0; kk < G; ++kk) {
+      for (uint32_t t = 0; t < mt; ++t) {
+        const uint32_t ci = ch0 + t * 128 + q * 32 + lane;
+        const uint32_t col0 = (kk * p.mt_cta + t) * p.c_out;
+        float *dst_row = p.dW + ((size_t)(k0 + kk) * p.c_in + ci) * p.c_out;
+        for (uint32_t c = 0; c < p.c_out; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((q * 32u) << 16) + col0 + c, v);
+          tmem_ld_wait();
+          if (ci < p.c_in && total > 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float f = __uint_as_float(v[i]);
+              if (f != 0.f) atomicAdd(dst_row + c + i, f);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == NP + kEpilogueWarps) {
+    // whole warp runs the loop with uniform state; one elected lane issues (see mma_role_fast)
+    const uint32_t idesc = umma_idesc_f16(Fmt<T>::v, kTileM, p.c_out, 1, 1);
+    constexpr uint32_t kHi = umma_desc_hi(1024, 2);
+    const uint32_t s_lo0 = umma_desc_lo(sS, kBlkBytes);
+    const uint32_t s_inc = p.stage_bytes >> 4, b_off = (p.blkA * kBlkBytes) >> 4;
+    const uint32_t t1_off = (2 * kBlkBytes) >> 4;
+    uint32_t s_lo = s_lo0, s = 0, ph = 0, w = 0, d = tmem_base;
+    const uint32_t d_step = p.mt_cta * p.c_out;
+    for (uint32_t g = 0; g < total; ++g) {
+      mbar_wait(full(s), ph);
+      tc_fence_after();
+      const uint32_t V = cnt[s];
+      const uint32_t n16 = V == 0 ? 1u : (V + 15u) >> 4;
+      if (elect_one()) {
+        for (uint32_t j = 0; j < n16; ++j) {
+          const uint32_t acc_flag = (w | j) != 0u;
+          const uint64_t db = pack_desc(s_lo + b_off + j * 128, kHi);
+          umma_f16(d, pack_desc(s_lo + j * 128, kHi), db, idesc, acc_flag);
+          if (mt > 1) umma_f16(d + p.c_out, pack_desc(s_lo + t1_off + j * 128, kHi), db, idesc, acc_flag);
+        }
+        umma_commit(empty(s));
+      }
+      __syncwarp();
+      s_lo += s_inc;
+      if (++s == p.nS) { s = 0; ph ^= 1u; s_lo = s_lo0; }
+      if (++w == n_win) { w = 0; d += d_step; }
+    }
+    if (elect_one()) umma_commit(tfull);
+    __syncwarp();
+  } else if (lane == 0) {
+    // release warp: consumes the empty-barrier completions in order, publishes the count
+    uint32_t s = 0, ph = 0;
+    for (uint32_t g = 0; g < total; ++g) {
+      mbar_wait(empty(s), ph);
+      __threadfence_block();
+      consumed[0] = g + 1;
+      if (++s == p.nS) { s = 0; ph ^= 1u; }
+    }
+  }
+done:
+  tc_fence_before();
+  __syncthreads();
+  if (warp == NP + kEpilogueWarps) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
 bool conv_wgrad_tc_supported(int dtype, uint32_t c_in, uint32_t c_out) {
   if (dtype != MEB200_BF16 && dtype != MEB200_F16) return false;
   return c_in % 8 == 0 && c_in >= 16 && c_out % 16 == 0 && c_out >= 16 && c_out <= 256;
@@ -1136,6 +1491,35 @@ int conv_wgrad_tc(const void *in, const void *grad_out, int dtype, uint32_t c_in
                   cudaStream_t stream) {
   MEB_CUDA(cudaMemsetAsync(grad_weight, 0, (size_t)K * c_in * c_out * sizeof(float), stream));
   if (n_out == 0 || K == 0) return MEB200_OK;
+  // MEB200_TC_WGRAD=rs selects the pair-compacting register-staged variant (k_wgrad_rs).  It
+  // moves ~3x fewer bytes but is currently slower end to end (32 vs 20 ms per bench step,
+  // profiles/r1_notes.md), so the dense kernel stays the default.
+  static int dense = -1;
+  if (dense < 0) { const char *e = getenv("MEB200_TC_WGRAD"); dense = (e && e[0] == 'r') ? 0 : 1; }
+  if (!dense) {
+    const tc::WgRsCfg cfg = tc::wgrad_rs_config(c_in, c_out, K, n_out, (uint32_t)num_sms());
+    if (cfg.mt_cta != 0) {
+      WgRsParams q{};
+      q.in = in; q.gout = grad_out; q.nbr = out_nbr; q.dW = grad_weight;
+      q.c_in = c_in; q.c_out = c_out; q.K = K; q.n_out = n_out;
+      q.G = cfg.G; q.n_kgroups = cfg.n_kgroups; q.mt_cta = cfg.mt_cta; q.n_mtgroups = cfg.n_mtgroups;
+      q.rows_per_split = cfg.rows_per_split; q.n_splits = cfg.n_splits;
+      q.blkA = cfg.blkA; q.blkB = cfg.blkB; q.nS = cfg.nS; q.stage_bytes = cfg.stage_bytes;
+      unsigned grid = cfg.n_kgroups * cfg.n_mtgroups * cfg.n_splits;
+      if (dtype == MEB200_BF16) {
+        static bool done = false;
+        if (!done) { MEB_CUDA(cudaFuncSetAttribute(k_wgrad_rs<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); done = true; }
+        k_wgrad_rs<__nv_bfloat16><<<grid, kWgRsThreads, cfg.smem_bytes, stream>>>(q);
+      } else {
+        static bool done = false;
+        if (!done) { MEB_CUDA(cudaFuncSetAttribute(k_wgrad_rs<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); done = true; }
+        k_wgrad_rs<__half><<<grid, kWgRsThreads, cfg.smem_bytes, stream>>>(q);
+      }
+      count_tc_launch();
+      MEB_LAUNCH_OK();
+      return MEB200_OK;
+    }
+  }
   WgParams p{};
   p.in = in; p.gout = grad_out; p.nbr = out_nbr; p.dW = grad_weight;
   p.c_in = c_in; p.c_out = c_out; p.K = K; p.n_out = n_out;

@@ -138,6 +138,28 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// One lane of a CONVERGED warp is elected (warp-uniform control flow around tcgen05 issue
+// lets the compiler keep descriptors in uniform registers).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint64_t pack_desc(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+// upper 32 bits of a shared-memory matrix descriptor (stride offset, version 1, swizzle mode)
+__host__ __device__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | ((layout_type & 7u) << 29);
+}
+// lower 32 bits: start address and leading offset, both in 16-byte units
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+
 // ---- UMMA descriptors -------------------------------------------------------------
 // Shared-memory matrix descriptor, sm_100 format (version 1): start address, leading /
 // stride byte offsets in 16-byte units, swizzle mode in bits [61,64).
