@@ -159,11 +159,19 @@ class _KernelMap:
     Replaces gpu_kernel_map's three flat arrays + host offset table (src/kernel_map.cuh:48-429);
     `swapped()` is the reference's swap_in_out (kernel_map.cuh:191-241)."""
 
-    __slots__ = ("out_nbr", "in_nbr", "stride_pairs")
+    __slots__ = ("out_nbr", "in_nbr", "stride_pairs", "_n_pairs")
 
     def __init__(self, out_nbr, in_nbr, stride_pairs=None):
         self.out_nbr, self.in_nbr = out_nbr, in_nbr
         self.stride_pairs = stride_pairs  # (in_rows, out_rows) when built as a stride map
+        self._n_pairs = None
+
+    @property
+    def n_pairs(self):
+        """Number of (in, out) pairs; costs one reduction + host read, cached (profiling only)."""
+        if self._n_pairs is None:
+            self._n_pairs = int((self.out_nbr >= 0).sum().item())
+        return self._n_pairs
 
     @property
     def K(self):
@@ -179,7 +187,9 @@ class _KernelMap:
 
     def swapped(self):
         sp = None if self.stride_pairs is None else (self.stride_pairs[1], self.stride_pairs[0])
-        return _KernelMap(self.in_nbr, self.out_nbr, sp)
+        km = _KernelMap(self.in_nbr, self.out_nbr, sp)
+        km._n_pairs = self._n_pairs
+        return km
 
     def to_dict(self):
         """{k: IntTensor[2, n_k]} as kernel_map_th returns (coordinate_map_manager.cpp:1395-1414);
@@ -475,7 +485,56 @@ def _workspace(n_in, n_out, c_in, c_out, K, code, device):
     return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
 
 
+# ---- live per-kernel timing for bench.py's roofline (CUDA events on the launch stream) ------
+_PROFILE = None   # None, or {"conv_fwd_dgrad": [...], "conv_wgrad": [...]} of event records
+
+
+def _record(kind, fn, flops, nbytes):
+    """Run fn() between two CUDA events on the current stream; keep the record if it launched
+    a tcgen05 kernel (the family the roofline is reported for)."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tc0 = _lib.tc_launch_count()
+    e0.record()
+    out = fn()
+    e1.record()
+    if _lib.tc_launch_count() > tc0:
+        _PROFILE[kind].append((e0, e1, flops, nbytes))
+    return out
+
+
+def profile_conv_kernels(step_fn, steps=2):
+    """Runs `steps` extra steps with every convolution launch bracketed by CUDA events and
+    returns, per kernel family, the summed device time and ALGORITHMIC work:
+    flops = 2*P*Cin*Cout per launch, bytes = the compulsory traffic of SURVEY.md §8d."""
+    global _PROFILE
+    _PROFILE = {"conv_fwd_dgrad": [], "conv_wgrad": []}
+    try:
+        for _ in range(steps):
+            step_fn()
+        torch.cuda.synchronize()
+        res = {}
+        for kind, recs in _PROFILE.items():
+            res[kind] = {"ms": sum(a.elapsed_time(b) for a, b, _, _ in recs),
+                         "flops": float(sum(r[2] for r in recs)),
+                         "bytes": float(sum(r[3] for r in recs)),
+                         "launches": len(recs), "steps": steps}
+        return res
+    finally:
+        _PROFILE = None
+
+
 def _conv_forward(in_feat, kernel, km, out_dtype=None):
+    if _PROFILE is not None:
+        esz = in_feat.element_size()
+        K, c_in, c_out = kernel.shape
+        P = km.n_pairs
+        nbytes = km.n_in * c_in * esz + km.n_out * c_out * esz + K * c_in * c_out * esz + P * 8
+        return _record("conv_fwd_dgrad", lambda: _conv_forward_impl(in_feat, kernel, km, out_dtype),
+                       2.0 * P * c_in * c_out, nbytes)
+    return _conv_forward_impl(in_feat, kernel, km, out_dtype)
+
+
+def _conv_forward_impl(in_feat, kernel, km, out_dtype=None):
     lib = _lib.load()
     code = _lib.dtype_code(in_feat.dtype)
     if kernel.dtype != in_feat.dtype:
@@ -494,6 +553,25 @@ def _conv_forward(in_feat, kernel, km, out_dtype=None):
 
 
 def _conv_backward(in_feat, grad_out, kernel, km, need_in=True, need_w=True):
+    if _PROFILE is not None:
+        esz = in_feat.element_size()
+        K, c_in, c_out = kernel.shape
+        P = km.n_pairs
+        flops = 2.0 * P * c_in * c_out
+        gi = gw = None
+        if need_in:   # dgrad alone: dOut in, dIn out, W, table
+            nb = km.n_out * c_out * esz + km.n_in * c_in * esz + K * c_in * c_out * esz + P * 8
+            gi, _ = _record("conv_fwd_dgrad", lambda: _conv_backward_impl(
+                in_feat, grad_out, kernel, km, True, False), flops, nb)
+        if need_w:    # wgrad alone: In and dOut in, dW (fp32) out, table
+            nb = km.n_in * c_in * esz + km.n_out * c_out * esz + K * c_in * c_out * 4 + P * 8
+            _, gw = _record("conv_wgrad", lambda: _conv_backward_impl(
+                in_feat, grad_out, kernel, km, False, True), flops, nb)
+        return gi, gw
+    return _conv_backward_impl(in_feat, grad_out, kernel, km, need_in, need_w)
+
+
+def _conv_backward_impl(in_feat, grad_out, kernel, km, need_in=True, need_w=True):
     lib = _lib.load()
     code = _lib.dtype_code(in_feat.dtype)
     if grad_out.dtype != in_feat.dtype:

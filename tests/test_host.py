@@ -1,0 +1,119 @@
+"""CPU tests of the host side: the C-ABI library exports what include/meb200.h declares, the
+key / kernel-generator logic mirrors the reference, and the product path refuses CPU tensors
+loudly (there is no fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import minkowskiengine_b200 as ME
+    header = open(os.path.join(ROOT, "include", "meb200.h")).read()
+    declared = set(re.findall(r"\b(meb200_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert os.path.isfile(ME._lib.LIB_PATH), "libmeb200.so missing: run __graft_entry__.build()"
+    lib = ctypes.CDLL(ME._lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/meb200.h but not exported"
+    assert declared == set(ME._lib.PROTOTYPES), "ctypes prototypes out of sync with the header"
+    assert ME._lib.load().meb200_build_arch() == b"sm_100a"
+
+
+def test_library_pure_helpers_without_gpu():
+    import minkowskiengine_b200 as ME
+    lib = ME._lib.load()
+    cap = lib.meb200_hash_capacity(100000)
+    assert cap >= 200000 and cap & (cap - 1) == 0
+    assert lib.meb200_insert_scratch_bytes(1000) >= 8000
+    assert lib.meb200_launch_count() == 0 or lib.meb200_launch_count() > 0
+    assert lib.meb200_conv_workspace_bytes(10, 10, 64, 128, 27, ME._lib.F32) == 0
+    assert lib.meb200_conv_workspace_bytes(10, 10, 64, 128, 27, ME._lib.BF16) >= 27 * 64 * 128 * 2
+
+
+def test_coordinate_map_key_semantics():
+    import minkowskiengine_b200 as ME
+    k = ME.CoordinateMapKey(4)
+    assert not k.is_key_set() and k.get_coordinate_size() == 4
+    with pytest.raises(RuntimeError):
+        k.get_key()
+    k.set_key([2, 2, 2], "")
+    assert k.is_key_set() and k.get_tensor_stride() == [2, 2, 2] and k.get_key() == ([2, 2, 2], "")
+    assert k == ME.CoordinateMapKey([2, 2, 2], "") and k != ME.CoordinateMapKey([2, 2, 2], "a")
+    assert hash(k) == hash(ME.CoordinateMapKey([2, 2, 2], ""))
+    assert "coordinate map key:[2, 2, 2]" in repr(k)
+    with pytest.raises(RuntimeError):
+        ME.CoordinateMapKey(3).set_key([1, 1, 1], "")     # wrong dimension
+
+
+def test_kernel_generator_matches_reference_enumeration():
+    import json
+    import minkowskiengine_b200 as ME
+    from minkowskiengine_b200.kernel_generator import region_offsets
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_goldens.json")))
+    for case in gold["kernel_region"]:
+        D = len(case["kernel_size"])
+        offs = region_offsets(ME.RegionType.HYPER_CUBE, case["kernel_size"], [1] * D, [1] * D)
+        regions = [[c[0]] + [a + b for a, b in zip(c[1:], d)] for c in case["coordinates"] for d in offs]
+        assert regions[:len(case["first_regions"])] == case["first_regions"], case["source"]
+    kg = ME.KernelGenerator(kernel_size=3, stride=2, dimension=3)
+    assert kg.kernel_volume == 27 and kg.kernel_stride == [2, 2, 2]
+    assert not kg.requires_strided_coordinates            # (sic) True iff stride == 1
+    assert ME.KernelGenerator(kernel_size=1, stride=1, dimension=3).requires_strided_coordinates
+    cross = ME.KernelGenerator(kernel_size=3, region_type=ME.RegionType.HYPER_CROSS, dimension=3)
+    assert cross.kernel_volume == 7
+    # dilation and tensor stride scale the offsets
+    assert region_offsets(ME.RegionType.HYPER_CUBE, [3], [2], [4]) == [[-8], [0], [8]]
+    assert region_offsets(ME.RegionType.HYPER_CUBE, [2], [1], [4]) == [[0], [4]]
+
+
+def test_layer_parameter_shapes_match_reference():
+    import minkowskiengine_b200 as ME
+    c = ME.MinkowskiConvolution(3, 8, kernel_size=5, dimension=3)
+    assert tuple(c.kernel.shape) == (125, 3, 8) and c.bias is None
+    c1 = ME.MinkowskiConvolution(8, 4, kernel_size=1, bias=True, dimension=3)
+    assert c1.use_mm and tuple(c1.kernel.shape) == (8, 4) and tuple(c1.bias.shape) == (1, 4)
+    c2 = ME.MinkowskiConvolution(8, 4, kernel_size=1, stride=2, dimension=3)
+    assert not c2.use_mm and tuple(c2.kernel.shape) == (1, 8, 4)
+    t = ME.MinkowskiConvolutionTranspose(8, 4, kernel_size=2, stride=2, dimension=3)
+    assert t.is_transpose and tuple(t.kernel.shape) == (8, 8, 4)
+    assert set(dict(c.named_parameters())) == {"kernel"}
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    """No CPU backend and no silent fallback: the product path must raise."""
+    import minkowskiengine_b200 as ME
+    coords = torch.zeros((4, 4), dtype=torch.int32)
+    feats = torch.rand(4, 3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ME.SparseTensor(feats, coords)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ME.CoordinateManager(D=3, coordinate_map_type=ME.CoordinateMapType.CPU)
+    if not torch.cuda.is_available():
+        mgr = ME.CoordinateManager(D=3)
+        with pytest.raises(RuntimeError):
+            mgr.insert_and_map(coords)
+
+
+def test_product_package_never_imports_the_oracle():
+    """The oracle is test infrastructure: no source file of the product package may import,
+    open or execute anything under oracle/ (doc comments stating exactly that are fine)."""
+    pkg = os.path.join(ROOT, "minkowskiengine_b200")
+    pat = re.compile(r"^\s*(from\s+oracle|import\s+oracle)|oracle[/.](oracle_np|ref|build_ref|_ref)")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                for ln in open(os.path.join(dirpath, fn)).read().splitlines():
+                    assert not pat.search(ln), (fn, ln)
+
+
+def test_minkunet_definition_parameter_count():
+    import minkowskiengine_b200 as ME
+    from examples.minkunet import minkunet
+    net = minkunet("MinkUNet34C", ME, 3, 20, 3)
+    assert sum(p.numel() for p in net.parameters()) == 37_856_052   # SURVEY.md §2 probe count
+    assert sum(1 for m in net.modules() if isinstance(m, ME.MinkowskiBatchNorm)) == 62
