@@ -961,11 +961,13 @@ static int launch_tc_slice(const void *A, int dtype, uint32_t n_a, uint32_t c_re
   p.out_f32 = out_dtype == MEB200_F32;
   p.wb_k_stride = wb_k_stride; p.out_ld = out_ld;
   p.n_a = n_a; p.wb_row0 = n0; p.wb_rows_per_k = c_cols_full;
-  static int max_stage_kb = -1;   // tuning knob: MEB200_TC_STAGE_KB (default 32)
+  // tuning knob MEB200_TC_STAGE_KB: largest A stage.  24 KB = one 128B-swizzle chunk per stage
+  // for BK=64 and three 64B-swizzle chunks for BK=32 — the best of the sweep in profiles/.
+  static int max_stage_kb = -1;
   if (max_stage_kb < 0) {
     const char *e = getenv("MEB200_TC_STAGE_KB");
-    max_stage_kb = e ? atoi(e) : 32;
-    if (max_stage_kb <= 0) max_stage_kb = 32;
+    max_stage_kb = e ? atoi(e) : 24;
+    if (max_stage_kb <= 0) max_stage_kb = 24;
   }
   const bool aligned = (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
                        (reinterpret_cast<uintptr_t>(Wb_full) & 15) == 0;
