@@ -262,6 +262,17 @@ __device__ __forceinline__ void mma_role_fast(const TcParams &p, uint32_t sA, ui
   }
 }
 
+// Flow-control words live in shared memory; access them with shared-space volatile ld/st (a
+// generic `volatile` pointer compiles to LD.E.STRONG.SYS, a far more expensive access).
+__device__ __forceinline__ uint32_t lds_volatile(const volatile uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32((const void *)p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_volatile(volatile uint32_t *p, uint32_t v) {
+  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32((const void *)p)), "r"(v) : "memory");
+}
+
 // Flow control for the register-staged kernels.  The producer warps do not wait on the
 // "empty" mbarriers themselves: with more producer warps than ring slots a one-bit parity wait
 // could be satisfied by a phase two uses back.  Instead ONE thread (lane 1 of the MMA warp)
@@ -278,12 +289,12 @@ __device__ __forceinline__ void release_role(const TcParams &p, uint32_t bar0,
         for (int r = 0; r < RT; ++r) {
           mbar_wait(bar_emptyA(bar0, sa), pha);
           __threadfence_block();
-          consumed[0] = ++nA_done;
+          sts_volatile(consumed, ++nA_done);
           if (++sa == p.nA) { sa = 0; pha ^= 1u; }
         }
         mbar_wait(bar_emptyB(bar0, sb), phb);
         __threadfence_block();
-        consumed[1] = ++nB_done;
+        sts_volatile(consumed + 1, ++nB_done);
         if (++sb == p.nB) { sb = 0; phb ^= 1u; }
       }
     }
@@ -311,7 +322,7 @@ constexpr int kRsBatch = 16;   // 16-byte loads in flight per lane (18 with 3 ch
 __device__ __forceinline__ void wait_consumed(volatile uint32_t *ctr, uint32_t g, uint32_t ring,
                                               uint32_t lane) {
   if (lane == 0) {
-    while ((int32_t)(g - *ctr) >= (int32_t)ring) __nanosleep(40);
+    while ((int32_t)(g - lds_volatile(ctr)) >= (int32_t)ring) __nanosleep(20);
   }
   __syncwarp();
   __threadfence_block();
@@ -453,7 +464,7 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapB, const TcParams p) {
           wait_consumed(consumed, g, p.nA, lane);   // ring slot still in use?
           if (q.r == 0 && lane == 0) {
             const uint32_t gb = g / R, sb = gb % p.nB;
-            while ((int32_t)(gb - consumed[1]) >= (int32_t)p.nB) __nanosleep(40);
+            while ((int32_t)(gb - lds_volatile(consumed + 1)) >= (int32_t)p.nB) __nanosleep(20);
             __threadfence_block();
             mbar_arrive_expect_tx(bar_fullB(bar0, sb), CPS * p.c_cols * BK * 2);
             const uint32_t dstB = sB + sb * p.b_stage_bytes;
@@ -1404,7 +1415,7 @@ __global__ void __launch_bounds__(kWgRsThreads, 1) k_wgrad_rs(const WgRsParams p
         }
         e0 += its * 4;
       } while (e0 < n16 * 16u);
-      if (lane == 0) cnt[slot] = V;
+      if (lane == 0) sts_volatile(cnt + slot, V);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(full(slot));
@@ -1446,7 +1457,7 @@ __global__ void __launch_bounds__(kWgRsThreads, 1) k_wgrad_rs(const WgRsParams p
     for (uint32_t g = 0; g < total; ++g) {
       mbar_wait(full(s), ph);
       tc_fence_after();
-      const uint32_t V = cnt[s];
+      const uint32_t V = lds_volatile(cnt + s);
       const uint32_t n16 = V == 0 ? 1u : (V + 15u) >> 4;
       if (elect_one()) {
         for (uint32_t j = 0; j < n16; ++j) {
@@ -1470,7 +1481,7 @@ __global__ void __launch_bounds__(kWgRsThreads, 1) k_wgrad_rs(const WgRsParams p
     for (uint32_t g = 0; g < total; ++g) {
       mbar_wait(empty(s), ph);
       __threadfence_block();
-      consumed[0] = g + 1;
+      sts_volatile(consumed, g + 1);
       if (++s == p.nS) { s = 0; ph ^= 1u; }
     }
   }
