@@ -160,6 +160,31 @@ int meb200_pool_backward(const void *grad_out, int dtype, uint32_t n_in, uint32_
                          const int32_t *in_nbr, uint32_t K, uint32_t n_out, int mode,
                          const void *aux, void *grad_in, void *stream);
 
+/* ---- batch normalisation over [n, C] feature rows (SURVEY.md 8(f) "next" row 1; the
+ *      reference applies torch.nn.BatchNorm1d to `.F`: MinkowskiEngine/MinkowskiNormalization.py:51-99).
+ *      C must be a multiple of 8.  sums: DEVICE double [2C]; statistics tensors fp32 [C]. ------ */
+/* sums[c] = sum_r x[r,c], sums[C+c] = sum_r x[r,c]^2 (zeroed inside). */
+int meb200_bn_stats(const void *x, int dtype, uint32_t n, uint32_t C, double *sums, void *stream);
+/* mean / invstd (biased variance + eps) from the (possibly all-reduced) sums over `count` rows;
+ * running statistics (may be NULL) updated with momentum and the unbiased variance. */
+/* The row count is `count`, or — for synchronised BN, where it is the all-reduced total that
+ * only exists on the device — read from *d_count when d_count != NULL. */
+int meb200_bn_finalize(const double *sums, double count, const double *d_count, uint32_t C,
+                       float eps, float momentum, float *running_mean, float *running_var,
+                       float *mean, float *invstd, void *stream);
+/* y = (x - mean) * invstd * weight + bias, optionally followed by ReLU (weight/bias may be NULL). */
+int meb200_bn_apply(const void *x, int dtype, uint32_t n, uint32_t C, const float *mean,
+                    const float *invstd, const float *weight, const float *bias, int relu,
+                    void *y, void *stream);
+/* sums[c] = sum_r dy, sums[C+c] = sum_r dy * (x - mean) * invstd  (= grad_bias, grad_weight). */
+int meb200_bn_backward_reduce(const void *dy, const void *x, int dtype, uint32_t n, uint32_t C,
+                              const float *mean, const float *invstd, double *sums, void *stream);
+/* dx = (dy - sums[c]/count - xhat * sums[C+c]/count) * invstd * weight. */
+int meb200_bn_backward_apply(const void *dy, const void *x, int dtype, uint32_t n, uint32_t C,
+                             const float *mean, const float *invstd, const float *weight,
+                             const double *sums, double count, const double *d_count, void *dx,
+                             void *stream);
+
 #ifdef __cplusplus
 }
 #endif

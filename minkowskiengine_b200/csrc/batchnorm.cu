@@ -1,0 +1,297 @@
+// Batch normalisation over the rows of an [N, C] feature matrix (training and inference),
+// the first "next" row of SURVEY.md §8(f): the reference applies torch.nn.BatchNorm1d to `.F`
+// (MinkowskiNormalization.py:51-99); torch's channels-last kernels run ~8x off the HBM
+// roofline on [800k, 96] bf16 and cost 18 % of a MinkUNet34C step, so the four passes are
+// provided here as streaming kernels: 16-byte row-segment loads, per-thread fp32 partials over
+// a strided set of rows, shared-memory combine, one fp64 atomic per channel per CTA.
+//
+//   stats      : S1[c] = sum_r x[r,c],  S2[c] = sum_r x[r,c]^2                 (fp64 [2C])
+//   finalize   : mean, invstd (biased var, eps) + running-stat update (unbiased var)
+//   apply      : y = (x - mean) * invstd * w + b                        (optional ReLU)
+//   bwd_reduce : G1[c] = sum_r dy,  G2[c] = sum_r dy * (x - mean) * invstd   (fp64 [2C])
+//   bwd_apply  : dx = (dy - G1/n - xhat * G2/n) * invstd * w
+#include "common.cuh"
+
+namespace meb200 {
+
+constexpr int kBnThreads = 256;
+
+template <typename T> struct Vec8;   // eight consecutive channels = one 16-byte (bf16/fp16) load
+template <> struct Vec8<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float (&f)[8]) {
+    uint4 v = *reinterpret_cast<const uint4 *>(p);
+    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16 *p, const float (&f)[8]) {
+    uint4 v;
+    __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    *reinterpret_cast<uint4 *>(p) = v;
+  }
+};
+template <> struct Vec8<__half> {
+  static __device__ __forceinline__ void load(const __half *p, float (&f)[8]) {
+    uint4 v = *reinterpret_cast<const uint4 *>(p);
+    const __half2 *h = reinterpret_cast<const __half2 *>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  }
+  static __device__ __forceinline__ void store(__half *p, const float (&f)[8]) {
+    uint4 v;
+    __half2 *h = reinterpret_cast<__half2 *>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    *reinterpret_cast<uint4 *>(p) = v;
+  }
+};
+template <> struct Vec8<float> {
+  static __device__ __forceinline__ void load(const float *p, float (&f)[8]) {
+    float4 a = reinterpret_cast<const float4 *>(p)[0], b = reinterpret_cast<const float4 *>(p)[1];
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float *p, const float (&f)[8]) {
+    reinterpret_cast<float4 *>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+    reinterpret_cast<float4 *>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
+};
+
+// Thread t of a CTA owns channel group (t % G) — 8 channels — and walks rows
+// (t / G) + i * rows_per_pass of the CTA's row range.  G = C / 8.
+struct BnGeom {
+  uint32_t G, rows_per_pass, active;   // active = G * rows_per_pass threads do work
+};
+__device__ __forceinline__ BnGeom bn_geom(uint32_t C) {
+  BnGeom g;
+  g.G = C / 8;
+  g.rows_per_pass = kBnThreads / g.G;
+  g.active = g.G * g.rows_per_pass;
+  return g;
+}
+
+// TWO per-channel sums: MODE 0: (x, x^2); MODE 1: (dy, dy * xhat)
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kBnThreads)
+k_bn_reduce(const T *__restrict__ a, const T *__restrict__ x, const float *__restrict__ mean,
+            const float *__restrict__ invstd, uint32_t n, uint32_t C, uint32_t rows_per_cta,
+            double *__restrict__ sums) {
+  extern __shared__ float s_acc[];   // [2C]
+  for (uint32_t i = threadIdx.x; i < 2 * C; i += kBnThreads) s_acc[i] = 0.f;
+  __syncthreads();
+  const BnGeom g = bn_geom(C);
+  if (threadIdx.x < g.active) {
+    const uint32_t cg = threadIdx.x % g.G, r0 = threadIdx.x / g.G;
+    const uint32_t row_begin = blockIdx.x * rows_per_cta;
+    const uint32_t row_end = min(row_begin + rows_per_cta, n);
+    float s1[8], s2[8], m[8], is[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; m[i] = 0.f; is[i] = 1.f; }
+    if (MODE == 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { m[i] = mean[cg * 8 + i]; is[i] = invstd[cg * 8 + i]; }
+    }
+    for (uint32_t r = row_begin + r0; r < row_end; r += g.rows_per_pass) {
+      float va[8];
+      Vec8<T>::load(a + (size_t)r * C + cg * 8, va);
+      if (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s1[i] += va[i]; s2[i] = fmaf(va[i], va[i], s2[i]); }
+      } else {
+        float vx[8];
+        Vec8<T>::load(x + (size_t)r * C + cg * 8, vx);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s1[i] += va[i]; s2[i] = fmaf(va[i], (vx[i] - m[i]) * is[i], s2[i]); }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&s_acc[cg * 8 + i], s1[i]);
+      atomicAdd(&s_acc[C + cg * 8 + i], s2[i]);
+    }
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < 2 * C; i += kBnThreads) atomicAdd(&sums[i], (double)s_acc[i]);
+}
+
+__global__ void k_bn_finalize(const double *__restrict__ sums, double count,
+                              const double *__restrict__ d_count, uint32_t C, float eps,
+                              float momentum, float *__restrict__ running_mean,
+                              float *__restrict__ running_var, float *__restrict__ mean,
+                              float *__restrict__ invstd) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (d_count != nullptr) count = *d_count;
+  double mu = sums[c] / count;
+  double var = sums[C + c] / count - mu * mu;
+  if (var < 0) var = 0;
+  mean[c] = (float)mu;
+  invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean != nullptr) {
+    double unbiased = count > 1 ? var * count / (count - 1) : var;
+    running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mu);
+    running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+  }
+}
+
+// MODE 0: y = (x - mean) * invstd * w + b (+ ReLU);  MODE 1: dx from dy (see file header)
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kBnThreads)
+k_bn_apply(const T *__restrict__ a, const T *__restrict__ x, const float *__restrict__ mean,
+           const float *__restrict__ invstd, const float *__restrict__ weight,
+           const float *__restrict__ bias, const double *__restrict__ gsums, double count,
+           const double *__restrict__ d_count, uint32_t n, uint32_t C, uint32_t rows_per_cta,
+           int relu, T *__restrict__ out) {
+  const BnGeom g = bn_geom(C);
+  if (threadIdx.x >= g.active) return;
+  if (d_count != nullptr) count = *d_count;
+  const uint32_t cg = threadIdx.x % g.G, r0 = threadIdx.x / g.G;
+  const uint32_t row_begin = blockIdx.x * rows_per_cta;
+  const uint32_t row_end = min(row_begin + rows_per_cta, n);
+  float sc[8], sh[8], m[8], is[8], k1[8], k2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t c = cg * 8 + i;
+    m[i] = mean[c];
+    is[i] = invstd[c];
+    const float w = weight != nullptr ? weight[c] : 1.f;
+    if (MODE == 0) {
+      sc[i] = is[i] * w;
+      sh[i] = (bias != nullptr ? bias[c] : 0.f) - m[i] * sc[i];
+    } else {
+      sc[i] = is[i] * w;
+      k1[i] = (float)(gsums[c] / count);
+      k2[i] = (float)(gsums[C + c] / count);
+    }
+  }
+  for (uint32_t r = row_begin + r0; r < row_end; r += g.rows_per_pass) {
+    float va[8], vo[8];
+    Vec8<T>::load(a + (size_t)r * C + cg * 8, va);
+    if (MODE == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float y = fmaf(va[i], sc[i], sh[i]);
+        vo[i] = relu ? fmaxf(y, 0.f) : y;
+      }
+    } else {
+      float vx[8];
+      Vec8<T>::load(x + (size_t)r * C + cg * 8, vx);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float xhat = (vx[i] - m[i]) * is[i];
+        vo[i] = (va[i] - k1[i] - xhat * k2[i]) * sc[i];
+      }
+    }
+    Vec8<T>::store(out + (size_t)r * C + cg * 8, vo);
+  }
+}
+
+static inline uint32_t bn_rows_per_cta(uint32_t n, uint32_t C, unsigned *grid) {
+  const uint32_t rows_per_pass = kBnThreads / (C / 8);
+  // ~8 CTAs per SM, at least 4 passes each
+  uint32_t want = 8u * (uint32_t)num_sms();
+  uint32_t rows = cdiv(n, want);
+  uint32_t min_rows = 4 * rows_per_pass;
+  if (rows < min_rows) rows = min_rows;
+  rows = cdiv(rows, rows_per_pass) * rows_per_pass;
+  *grid = cdiv(n, rows);
+  return rows;
+}
+
+}  // namespace meb200
+
+using namespace meb200;
+
+#define MEB_BN_CHECK(C)                                                                   \
+  MEB_CHECK_ARG((C) % 8 == 0 && (C) >= 8 && (C) <= 2048, "batch norm: C must be a multiple of 8 in [8, 2048] (got %u)", (unsigned)(C))
+
+extern "C" {
+
+int meb200_bn_stats(const void *x, int dtype, uint32_t n, uint32_t C, double *sums, void *stream_) {
+  cudaStream_t s = (cudaStream_t)stream_;
+  MEB_BN_CHECK(C);
+  MEB_CHECK_ARG(sums != nullptr, "sums");
+  MEB_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(double), s));
+  if (n == 0) return MEB200_OK;
+  unsigned grid;
+  uint32_t rows = bn_rows_per_cta(n, C, &grid);
+  size_t smem = 2 * (size_t)C * sizeof(float);
+  switch (dtype) {
+    case MEB200_F32: k_bn_reduce<float, 0><<<grid, kBnThreads, smem, s>>>((const float *)x, nullptr, nullptr, nullptr, n, C, rows, sums); break;
+    case MEB200_BF16: k_bn_reduce<__nv_bfloat16, 0><<<grid, kBnThreads, smem, s>>>((const __nv_bfloat16 *)x, nullptr, nullptr, nullptr, n, C, rows, sums); break;
+    case MEB200_F16: k_bn_reduce<__half, 0><<<grid, kBnThreads, smem, s>>>((const __half *)x, nullptr, nullptr, nullptr, n, C, rows, sums); break;
+    default: set_error("batch norm: unsupported dtype %d", dtype); return MEB200_ERR_UNSUPPORTED;
+  }
+  MEB_LAUNCH_OK();
+  return MEB200_OK;
+}
+
+int meb200_bn_finalize(const double *sums, double count, const double *d_count, uint32_t C,
+                       float eps, float momentum, float *running_mean, float *running_var,
+                       float *mean, float *invstd, void *stream_) {
+  cudaStream_t s = (cudaStream_t)stream_;
+  MEB_CHECK_ARG(sums && mean && invstd && (count > 0 || d_count != nullptr), "finalize arguments");
+  k_bn_finalize<<<cdiv(C, 128), 128, 0, s>>>(sums, count, d_count, C, eps, momentum, running_mean, running_var, mean, invstd);
+  MEB_LAUNCH_OK();
+  return MEB200_OK;
+}
+
+int meb200_bn_apply(const void *x, int dtype, uint32_t n, uint32_t C, const float *mean,
+                    const float *invstd, const float *weight, const float *bias, int relu,
+                    void *y, void *stream_) {
+  cudaStream_t s = (cudaStream_t)stream_;
+  MEB_BN_CHECK(C);
+  if (n == 0) return MEB200_OK;
+  unsigned grid;
+  uint32_t rows = bn_rows_per_cta(n, C, &grid);
+  switch (dtype) {
+    case MEB200_F32: k_bn_apply<float, 0><<<grid, kBnThreads, 0, s>>>((const float *)x, nullptr, mean, invstd, weight, bias, nullptr, 1.0, nullptr, n, C, rows, relu, (float *)y); break;
+    case MEB200_BF16: k_bn_apply<__nv_bfloat16, 0><<<grid, kBnThreads, 0, s>>>((const __nv_bfloat16 *)x, nullptr, mean, invstd, weight, bias, nullptr, 1.0, nullptr, n, C, rows, relu, (__nv_bfloat16 *)y); break;
+    case MEB200_F16: k_bn_apply<__half, 0><<<grid, kBnThreads, 0, s>>>((const __half *)x, nullptr, mean, invstd, weight, bias, nullptr, 1.0, nullptr, n, C, rows, relu, (__half *)y); break;
+    default: set_error("batch norm: unsupported dtype %d", dtype); return MEB200_ERR_UNSUPPORTED;
+  }
+  MEB_LAUNCH_OK();
+  return MEB200_OK;
+}
+
+int meb200_bn_backward_reduce(const void *dy, const void *x, int dtype, uint32_t n, uint32_t C,
+                              const float *mean, const float *invstd, double *sums, void *stream_) {
+  cudaStream_t s = (cudaStream_t)stream_;
+  MEB_BN_CHECK(C);
+  MEB_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(double), s));
+  if (n == 0) return MEB200_OK;
+  unsigned grid;
+  uint32_t rows = bn_rows_per_cta(n, C, &grid);
+  size_t smem = 2 * (size_t)C * sizeof(float);
+  switch (dtype) {
+    case MEB200_F32: k_bn_reduce<float, 1><<<grid, kBnThreads, smem, s>>>((const float *)dy, (const float *)x, mean, invstd, n, C, rows, sums); break;
+    case MEB200_BF16: k_bn_reduce<__nv_bfloat16, 1><<<grid, kBnThreads, smem, s>>>((const __nv_bfloat16 *)dy, (const __nv_bfloat16 *)x, mean, invstd, n, C, rows, sums); break;
+    case MEB200_F16: k_bn_reduce<__half, 1><<<grid, kBnThreads, smem, s>>>((const __half *)dy, (const __half *)x, mean, invstd, n, C, rows, sums); break;
+    default: set_error("batch norm: unsupported dtype %d", dtype); return MEB200_ERR_UNSUPPORTED;
+  }
+  MEB_LAUNCH_OK();
+  return MEB200_OK;
+}
+
+int meb200_bn_backward_apply(const void *dy, const void *x, int dtype, uint32_t n, uint32_t C,
+                             const float *mean, const float *invstd, const float *weight,
+                             const double *sums, double count, const double *d_count, void *dx,
+                             void *stream_) {
+  cudaStream_t s = (cudaStream_t)stream_;
+  MEB_BN_CHECK(C);
+  if (n == 0) return MEB200_OK;
+  MEB_CHECK_ARG(count > 0 || d_count != nullptr, "count");
+  unsigned grid;
+  uint32_t rows = bn_rows_per_cta(n, C, &grid);
+  switch (dtype) {
+    case MEB200_F32: k_bn_apply<float, 1><<<grid, kBnThreads, 0, s>>>((const float *)dy, (const float *)x, mean, invstd, weight, nullptr, sums, count, d_count, n, C, rows, 0, (float *)dx); break;
+    case MEB200_BF16: k_bn_apply<__nv_bfloat16, 1><<<grid, kBnThreads, 0, s>>>((const __nv_bfloat16 *)dy, (const __nv_bfloat16 *)x, mean, invstd, weight, nullptr, sums, count, d_count, n, C, rows, 0, (__nv_bfloat16 *)dx); break;
+    case MEB200_F16: k_bn_apply<__half, 1><<<grid, kBnThreads, 0, s>>>((const __half *)dy, (const __half *)x, mean, invstd, weight, nullptr, sums, count, d_count, n, C, rows, 0, (__half *)dx); break;
+    default: set_error("batch norm: unsupported dtype %d", dtype); return MEB200_ERR_UNSUPPORTED;
+  }
+  MEB_LAUNCH_OK();
+  return MEB200_OK;
+}
+
+}

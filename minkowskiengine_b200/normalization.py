@@ -1,9 +1,116 @@
-"""Batch-norm wrappers: torch modules applied to `.F`
-(reference: MinkowskiNormalization.py:51-192 — no native code on this part of the path)."""
+"""Batch normalisation on the feature matrix of a sparse tensor
+(reference: MinkowskiNormalization.py:51-192, which wraps torch.nn.BatchNorm1d / SyncBatchNorm).
+
+The modules keep a torch `BatchNorm1d` / `SyncBatchNorm` as the PARAMETER HOLDER (`bn.weight`,
+`bn.bias`, `bn.running_mean`, ... — state_dict compatible with the reference) but, for CUDA
+features with C % 8 == 0, run the four passes through libmeb200's streaming kernels
+(csrc/batchnorm.cu).  Semantics are torch's: biased variance for
+normalisation, unbiased for the running estimate, momentum update, per-channel affine; the
+synchronised variant all-reduces (sum, sum of squares, count) forward and (sum dy, sum dy*xhat)
+backward over the process group, exactly the exchange torch.nn.SyncBatchNorm performs.
+`MEB200_TORCH_BN=1` routes everything through torch's own kernels (A/B comparisons).
+"""
+import os
+
 import torch
 import torch.nn as nn
 
+from . import _lib
 from .sparse_tensor import SparseTensor
+
+_USE_TORCH = os.environ.get("MEB200_TORCH_BN", "0") not in ("", "0")
+
+
+class _BatchNormFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, group):
+        lib = _lib.load()
+        x = x.contiguous()
+        n, C = x.shape
+        code = _lib.dtype_code(x.dtype)
+        stream = _lib.current_stream()
+        dev = x.device
+        w32 = None if weight is None else weight.detach().float().contiguous()
+        b32 = None if bias is None else bias.detach().float().contiguous()
+        sums = torch.empty(2 * C + 1, dtype=torch.float64, device=dev)
+        _lib.check(lib.meb200_bn_stats(_lib.ptr(x), code, n, C, _lib.ptr(sums), stream))
+        d_count = None
+        if group is not None:
+            sums[2 * C] = float(n)
+            torch.distributed.all_reduce(sums, group=group)
+            d_count = sums[2 * C:]
+        mean = torch.empty(C, dtype=torch.float32, device=dev)
+        invstd = torch.empty(C, dtype=torch.float32, device=dev)
+        _lib.check(lib.meb200_bn_finalize(
+            _lib.ptr(sums), float(n), _lib.ptr(d_count), C, float(eps), float(momentum),
+            _lib.ptr(running_mean), _lib.ptr(running_var), _lib.ptr(mean), _lib.ptr(invstd), stream))
+        y = torch.empty_like(x)
+        _lib.check(lib.meb200_bn_apply(_lib.ptr(x), code, n, C, _lib.ptr(mean), _lib.ptr(invstd),
+                                       _lib.ptr(w32), _lib.ptr(b32), 0, _lib.ptr(y), stream))
+        ctx.save_for_backward(x, mean, invstd, w32 if w32 is not None else mean.new_empty(0),
+                              d_count if d_count is not None else sums.new_empty(0))
+        ctx.group = group
+        ctx.has_affine = weight is not None
+        ctx.param_dtype = None if weight is None else weight.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, mean, invstd, w32, d_count = ctx.saved_tensors
+        dy = dy.contiguous()
+        if dy.dtype != x.dtype:
+            dy = dy.to(x.dtype)
+        n, C = x.shape
+        code = _lib.dtype_code(x.dtype)
+        stream = _lib.current_stream()
+        gs = torch.empty(2 * C, dtype=torch.float64, device=x.device)
+        _lib.check(lib.meb200_bn_backward_reduce(_lib.ptr(dy), _lib.ptr(x), code, n, C,
+                                                 _lib.ptr(mean), _lib.ptr(invstd), _lib.ptr(gs),
+                                                 stream))
+        grad_w = grad_b = None
+        if ctx.has_affine:   # local sums; DDP averages parameter gradients across ranks
+            grad_b = gs[:C].to(ctx.param_dtype)
+            grad_w = gs[C:].to(ctx.param_dtype)
+        if ctx.group is not None:
+            gs = gs.clone() if ctx.has_affine else gs
+            torch.distributed.all_reduce(gs, group=ctx.group)
+        dx = torch.empty_like(x)
+        _lib.check(lib.meb200_bn_backward_apply(
+            _lib.ptr(dy), _lib.ptr(x), code, n, C, _lib.ptr(mean), _lib.ptr(invstd),
+            _lib.ptr(w32) if w32.numel() else None, _lib.ptr(gs), float(n),
+            _lib.ptr(d_count) if d_count.numel() else None, _lib.ptr(dx), stream))
+        return dx, grad_w, grad_b, None, None, None, None, None
+
+
+def _native_ok(bn, x):
+    return (not _USE_TORCH and x.is_cuda and x.dim() == 2 and x.shape[1] % 8 == 0
+            and x.shape[1] <= 2048 and x.dtype in (torch.float32, torch.bfloat16, torch.float16)
+            and bn.track_running_stats and bn.momentum is not None and x.shape[0] > 0)
+
+
+def _batch_norm(bn, x, group=None):
+    """Functional core shared by the two modules."""
+    if not _native_ok(bn, x):
+        return bn(x)
+    if bn.training:
+        if bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        return _BatchNormFunction.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                        bn.momentum, bn.eps, group)
+    # inference: normalise with the running statistics
+    lib = _lib.load()
+    x = x.contiguous()
+    n, C = x.shape
+    invstd = torch.rsqrt(bn.running_var.float() + bn.eps)
+    y = torch.empty_like(x)
+    w = None if bn.weight is None else bn.weight.detach().float().contiguous()
+    b = None if bn.bias is None else bn.bias.detach().float().contiguous()
+    _lib.check(lib.meb200_bn_apply(_lib.ptr(x), _lib.dtype_code(x.dtype), n, C,
+                                   _lib.ptr(bn.running_mean.float().contiguous()),
+                                   _lib.ptr(invstd), _lib.ptr(w), _lib.ptr(b), 0, _lib.ptr(y),
+                                   _lib.current_stream()))
+    return y
 
 
 class MinkowskiBatchNorm(nn.Module):
@@ -14,7 +121,7 @@ class MinkowskiBatchNorm(nn.Module):
                                        track_running_stats=track_running_stats)
 
     def forward(self, input):
-        output = self.bn(input.F)
+        output = _batch_norm(self.bn, input.F)
         return SparseTensor(output, coordinate_map_key=input.coordinate_map_key,
                             coordinate_manager=input.coordinate_manager)
 
@@ -33,6 +140,17 @@ class MinkowskiSyncBatchNorm(MinkowskiBatchNorm):
                                          affine=affine,
                                          track_running_stats=track_running_stats,
                                          process_group=process_group)
+
+    def forward(self, input):
+        bn = self.bn
+        group = None
+        if bn.training and torch.distributed.is_available() and torch.distributed.is_initialized():
+            group = bn.process_group or torch.distributed.group.WORLD
+            if torch.distributed.get_world_size(group) == 1:
+                group = None
+        output = _batch_norm(bn, input.F, group) if _native_ok(bn, input.F) else bn(input.F)
+        return SparseTensor(output, coordinate_map_key=input.coordinate_map_key,
+                            coordinate_manager=input.coordinate_manager)
 
     @classmethod
     def convert_sync_batchnorm(cls, module, process_group=None):
