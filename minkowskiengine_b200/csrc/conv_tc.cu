@@ -1256,41 +1256,39 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(const WgParams p) {
 }
 
 // =====================================================================================
-// wgrad, register-staged with pair compaction (default).  Only the VALID (input row, output
-// row) pairs of an offset enter the reduction: a producer warp scans a 64-row window of the
-// neighbour table, compacts its hits with ballots, loads both rows of every pair through
-// registers and writes them as consecutive K-rows of the stage; the MMA thread reads the pair
-// count of the stage and issues ceil(V/16) K-steps.  No zero rows are fetched, multiplied or
-// kept in the ring (the dense variant above spends ~70% of all three on them).
+// wgrad with the forward kernel's producer scheme (default when its stages fit): dense 128-row
+// windows, one producer warp per stage (ballot compaction, valid rows through registers,
+// zero-filled MN-major stage), the window's dOut rows fetched by TMA once per group of G offsets.
 // =====================================================================================
-struct WgRsParams {
-  const void *in, *gout;
+struct Wg2Params {
+  const void *in;
   const int32_t *nbr;
   float *dW;
   uint32_t c_in, c_out, K, n_out;
   uint32_t G, n_kgroups, mt_cta, n_mtgroups, rows_per_split, n_splits;
-  uint32_t blkA, blkB, nS, stage_bytes;
+  uint32_t blkA, blkB, nA, nB, a_stage_bytes, b_stage_bytes;
 };
-constexpr int kWgRsWarps = (int)tc::kWgRsProducerWarps;
-constexpr int kWgRsThreads = (kWgRsWarps + kEpilogueWarps + 2) * 32;   // + MMA warp + release warp
+constexpr int kWg2Warps = (int)tc::kWg2ProducerWarps;
+constexpr int kWg2Threads = (kWg2Warps + kEpilogueWarps + 2) * 32;
+constexpr uint32_t kWg2Blk = tc::kWg2BlkBytes;
 
 template <typename T>
-__global__ void __launch_bounds__(kWgRsThreads, 1) k_wgrad_rs(const WgRsParams p) {
-  constexpr int NP = kWgRsWarps;
+__global__ void __launch_bounds__(kWg2Threads, 1)
+k_wgrad_rs2(const __grid_constant__ CUtensorMap mapG, const Wg2Params p) {
+  constexpr int NP = kWg2Warps;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t sS = smem_u32(smem);
-  uint8_t *tail = smem + p.nS * p.stage_bytes;
+  const uint32_t sA = smem_u32(smem);
+  const uint32_t sB = sA + p.nA * p.a_stage_bytes;
+  uint8_t *tail = smem + p.nA * p.a_stage_bytes + p.nB * p.b_stage_bytes;
   uint64_t *bars = reinterpret_cast<uint64_t *>(tail);
   const uint32_t bar0 = smem_u32(bars);
-  auto full = [&](uint32_t i) { return bar0 + 8u * i; };
-  auto empty = [&](uint32_t i) { return bar0 + 8u * (kMaxStages + i); };
-  const uint32_t tfull = bar0 + 8u * (4 * kMaxStages);
+  const uint32_t tfull = bar_tfull(bar0, 0);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * kMaxStages + 4);
   uint2 *scratch_all = reinterpret_cast<uint2 *>(tail + tc::kBarBytes);
-  volatile uint32_t *cnt = reinterpret_cast<volatile uint32_t *>(tail + tc::kBarBytes + NP * kWgRows * 8);
-  volatile uint32_t *consumed = cnt + kMaxStages;
+  volatile uint32_t *consumed = reinterpret_cast<volatile uint32_t *>(
+      tail + tc::kBarBytes + NP * tc::kWg2Rows * 8);
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t wi = blockIdx.x;
@@ -1301,16 +1299,18 @@ __global__ void __launch_bounds__(kWgRsThreads, 1) k_wgrad_rs(const WgRsParams p
   const uint32_t G = min(p.G, p.K - k0);
   const uint32_t r_begin = split * p.rows_per_split;
   const uint32_t r_end = min(r_begin + p.rows_per_split, p.n_out);
-  const uint32_t n_win = (r_end - r_begin + kWgRows - 1) / kWgRows;
+  const uint32_t n_win = (r_end - r_begin + tc::kWg2Rows - 1) / tc::kWg2Rows;
   const uint32_t total = G * n_win;
   const uint32_t ch0 = mtg * p.mt_cta * 128;
   const uint32_t mt = min(p.mt_cta, (p.c_in - ch0 + 127) / 128);
 
   if (threadIdx.x == 0) {
-    for (uint32_t i = 0; i < p.nS; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); }
+    for (uint32_t i = 0; i < p.nA; ++i) { mbar_init(bar_fullA(bar0, i), 1); mbar_init(bar_emptyA(bar0, i), 1); }
+    for (uint32_t i = 0; i < p.nB; ++i) { mbar_init(bar_fullB(bar0, i), 1); mbar_init(bar_emptyB(bar0, i), 1); }
     mbar_init(tfull, 1);
     mbar_fence_init();
     consumed[0] = 0;
+    consumed[1] = 0;
   }
   if (warp == NP + kEpilogueWarps) {
     tmem_alloc(smem_u32(tmem_slot), kTmemCols);
@@ -1322,107 +1322,94 @@ __global__ void __launch_bounds__(kWgRsThreads, 1) k_wgrad_rs(const WgRsParams p
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < NP) {
+    // ------------------------------- producers -----------------------------------------
     const uint32_t sub_row = lane >> 3, j8 = lane & 7;
     const T *in = reinterpret_cast<const T *>(p.in);
-    const T *gout = reinterpret_cast<const T *>(p.gout);
-    uint2 *scratch = scratch_all + warp * kWgRows;
+    uint2 *scratch = scratch_all + warp * tc::kWg2Rows;
     const uint32_t scratch_s = smem_u32(scratch);
     const uint32_t lane_lt = (1u << lane) - 1u;
-    int32_t idx_cur[2], idx_nxt[2];
-    auto load_idx = [&](uint32_t g, int32_t (&dst)[2]) {
-      const uint32_t kk = g / n_win, w = g - kk * n_win;
+    int32_t idx_cur[4], idx_nxt[4];
+    auto load_idx = [&](uint32_t g, int32_t (&dst)[4]) {
+      const uint32_t w = g / G, kk = g - w * G;
       const int32_t *nbr_k = p.nbr + (size_t)(k0 + kk) * p.n_out;
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const uint32_t o = r_begin + w * kWgRows + i * 32 + lane;
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t o = r_begin + w * tc::kWg2Rows + i * 32 + lane;
         dst[i] = (o < r_end) ? __ldg(nbr_k + o) : -1;
       }
     };
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&mapG);
     uint32_t g = warp;
     if (g < total) load_idx(g, idx_cur);
     for (; g < total; g += NP) {
       if (g + NP < total) load_idx(g + NP, idx_nxt);
-      const uint32_t kk = g / n_win, w = g - kk * n_win;
-      const uint32_t o0 = r_begin + w * kWgRows;
-      const uint32_t slot = g % p.nS;
-      (void)kk;
-      // ---- compact the hits of this 64-row window ---------------------------------------
+      const uint32_t w = g / G, kk = g - w * G;
+      const uint32_t sa = g % p.nA;
       uint32_t V = 0;
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < 4; ++i) {
         const bool ok = idx_cur[i] >= 0;
         const uint32_t m = __ballot_sync(0xffffffffu, ok);
-        if (ok) scratch[V + __popc(m & lane_lt)] = make_uint2((uint32_t)idx_cur[i], o0 + i * 32 + lane);
+        if (ok) scratch[V + __popc(m & lane_lt)] = make_uint2((uint32_t)idx_cur[i], (uint32_t)(i * 32 + lane));
         V += __popc(m);
       }
       __syncwarp();
-      const uint32_t n16 = V == 0 ? 1u : (V + 15u) / 16u;
-      const uint32_t dstS = sS + slot * p.stage_bytes;
+      const uint32_t dstA = sA + sa * p.a_stage_bytes;
+      const uint32_t its = 16u / p.blkA;          // row groups (4 rows each) per batch of 16 loads
       bool slot_ready = false;
-      // Both operands of a batch of pairs are loaded into registers first (gathered input rows
-      // -> blkA blocks, gathered dOut rows -> blkB blocks); the ring slot is taken only once the
-      // data has arrived.
-      const uint32_t itsA = 10u / p.blkA, itsB = 10u / p.blkB;
-      const uint32_t its = itsA < itsB ? itsA : itsB;
-      const uint32_t dstB0 = dstS + p.blkA * kBlkBytes;
       uint32_t e0 = 0;
       do {
-        uint4 va[10], vb[10];
-        uint32_t x = 0;
+        uint4 v[16];
 #pragma unroll
-        for (int q = 0; q < 10; ++q) {
+        for (int q = 0; q < 16; ++q) {
           const uint32_t it = (uint32_t)q / p.blkA, blk = (uint32_t)q - it * p.blkA;
           const uint32_t e = e0 + it * 4 + sub_row;
           const uint32_t chn = ch0 + blk * 64 + j8 * 8;
-          va[q] = make_uint4(0, 0, 0, 0);
           if (it < its && e < V && chn < p.c_in) {
             uint32_t row;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(scratch_s + e * 8));
-            va[q] = ldg128(in + (size_t)row * p.c_in + chn);
+            v[q] = ldg128(in + (size_t)row * p.c_in + chn);
+          } else {
+            v[q] = make_uint4(0, 0, 0, 0);
           }
         }
-#pragma unroll
-        for (int q = 0; q < 10; ++q) {
-          const uint32_t it = (uint32_t)q / p.blkB, blk = (uint32_t)q - it * p.blkB;
-          const uint32_t e = e0 + it * 4 + sub_row;
-          const uint32_t chn = blk * 64 + j8 * 8;
-          vb[q] = make_uint4(0, 0, 0, 0);
-          if (it < its && e < V && chn < p.c_out) {
-            uint32_t row;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(scratch_s + e * 8 + 4));
-            vb[q] = ldg128(gout + (size_t)row * p.c_out + chn);
-          }
-        }
-        (void)x;
         if (!slot_ready) {
-          wait_consumed(consumed, g, p.nS, lane);
+          wait_consumed(consumed, g, p.nA, lane);
+          if (kk == 0 && lane == 0) {   // this stage opens window w: fetch its dOut rows
+            const uint32_t sb = w % p.nB;
+            while ((int32_t)(w - lds_volatile(consumed + 1)) >= (int32_t)p.nB) __nanosleep(20);
+            __threadfence_block();
+            mbar_arrive_expect_tx(bar_fullB(bar0, sb), p.blkB * kWg2Blk);
+            const uint32_t dstB = sB + sb * p.b_stage_bytes;
+            for (uint32_t b = 0; b < p.blkB; ++b)
+              tma_load_2d(dstB + b * kWg2Blk, &mapG, (int32_t)(b * 64),
+                          (int32_t)(r_begin + w * tc::kWg2Rows), bar_fullB(bar0, sb));
+          }
+          for (uint32_t off = lane * 16; off < p.a_stage_bytes; off += 512)
+            sts128(dstA + off, make_uint4(0, 0, 0, 0));
+          __syncwarp();
           slot_ready = true;
         }
-        // rows V..16*n16-1 are the zero padding of the last K-step
 #pragma unroll
-        for (int q = 0; q < 10; ++q) {
+        for (int q = 0; q < 16; ++q) {
           const uint32_t it = (uint32_t)q / p.blkA, blk = (uint32_t)q - it * p.blkA;
           const uint32_t e = e0 + it * 4 + sub_row;
-          if (it < its && e < n16 * 16u)
-            sts128(dstS + blk * kBlkBytes + e * 128 + ((j8 ^ (e & 7u)) << 4), va[q]);
-        }
-#pragma unroll
-        for (int q = 0; q < 10; ++q) {
-          const uint32_t it = (uint32_t)q / p.blkB, blk = (uint32_t)q - it * p.blkB;
-          const uint32_t e = e0 + it * 4 + sub_row;
-          if (it < its && e < n16 * 16u)
-            sts128(dstB0 + blk * kBlkBytes + e * 128 + ((j8 ^ (e & 7u)) << 4), vb[q]);
+          if (it < its && e < V) {
+            uint32_t trow;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(trow) : "r"(scratch_s + e * 8 + 4));
+            sts128(dstA + blk * kWg2Blk + trow * 128 + ((j8 ^ (trow & 7u)) << 4), v[q]);
+          }
         }
         e0 += its * 4;
-      } while (e0 < n16 * 16u);
-      if (lane == 0) sts_volatile(cnt + slot, V);
+      } while (e0 < V);
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(full(slot));
+      if (lane == 0) mbar_arrive(bar_fullA(bar0, sa));
 #pragma unroll
-      for (int i = 0; i < 2; ++i) idx_cur[i] = idx_nxt[i];
+      for (int i = 0; i < 4; ++i) idx_cur[i] = idx_nxt[i];
     }
   } else if (warp < NP + kEpilogueWarps) {
+    // ------------------------------- epilogue ------------------------------------------
     const uint32_t q = warp & 3u;
     mbar_wait(tfull, 0);
     tc_fence_after();
@@ -1446,46 +1433,56 @@ __global__ void __launch_bounds__(kWgRsThreads, 1) k_wgrad_rs(const WgRsParams p
       }
     }
   } else if (warp == NP + kEpilogueWarps) {
-    // whole warp runs the loop with uniform state; one elected lane issues (see mma_role_fast)
+    // ------------------------------- MMA (whole warp, one lane issues) -----------------
     const uint32_t idesc = umma_idesc_f16(Fmt<T>::v, kTileM, p.c_out, 1, 1);
     constexpr uint32_t kHi = umma_desc_hi(1024, 2);
-    const uint32_t s_lo0 = umma_desc_lo(sS, kBlkBytes);
-    const uint32_t s_inc = p.stage_bytes >> 4, b_off = (p.blkA * kBlkBytes) >> 4;
-    const uint32_t t1_off = (2 * kBlkBytes) >> 4;
-    uint32_t s_lo = s_lo0, s = 0, ph = 0, w = 0, d = tmem_base;
-    const uint32_t d_step = p.mt_cta * p.c_out;
-    for (uint32_t g = 0; g < total; ++g) {
-      mbar_wait(full(s), ph);
-      tc_fence_after();
-      const uint32_t V = lds_volatile(cnt + s);
-      const uint32_t n16 = V == 0 ? 1u : (V + 15u) >> 4;
-      if (elect_one()) {
-        for (uint32_t j = 0; j < n16; ++j) {
-          const uint32_t acc_flag = (w | j) != 0u;
-          const uint64_t db = pack_desc(s_lo + b_off + j * 128, kHi);
-          umma_f16(d, pack_desc(s_lo + j * 128, kHi), db, idesc, acc_flag);
-          if (mt > 1) umma_f16(d + p.c_out, pack_desc(s_lo + t1_off + j * 128, kHi), db, idesc, acc_flag);
+    const uint32_t a_lo0 = umma_desc_lo(sA, kWg2Blk), b_lo0 = umma_desc_lo(sB, kWg2Blk);
+    const uint32_t a_inc = p.a_stage_bytes >> 4, b_inc = p.b_stage_bytes >> 4;
+    const uint32_t t1_off = (2 * kWg2Blk) >> 4;
+    uint32_t a_lo = a_lo0, b_lo = b_lo0, sa = 0, pha = 0, sb = 0, phb = 0;
+    for (uint32_t w = 0; w < n_win; ++w) {
+      mbar_wait(bar_fullB(bar0, sb), phb);
+      for (uint32_t kk = 0; kk < G; ++kk) {
+        mbar_wait(bar_fullA(bar0, sa), pha);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t d = tmem_base + kk * p.mt_cta * p.c_out;
+#pragma unroll
+          for (int j = 0; j < (int)tc::kWg2Rows / 16; ++j) {
+            const uint32_t acc_flag = (w | (uint32_t)j) != 0u;
+            const uint64_t db = pack_desc(b_lo + j * 128, kHi);
+            umma_f16(d, pack_desc(a_lo + j * 128, kHi), db, idesc, acc_flag);
+            if (mt > 1) umma_f16(d + p.c_out, pack_desc(a_lo + t1_off + j * 128, kHi), db, idesc, acc_flag);
+          }
+          umma_commit(bar_emptyA(bar0, sa));
+          if (kk == G - 1) umma_commit(bar_emptyB(bar0, sb));
         }
-        umma_commit(empty(s));
+        __syncwarp();
+        a_lo += a_inc;
+        if (++sa == p.nA) { sa = 0; pha ^= 1u; a_lo = a_lo0; }
       }
-      __syncwarp();
-      s_lo += s_inc;
-      if (++s == p.nS) { s = 0; ph ^= 1u; s_lo = s_lo0; }
-      if (++w == n_win) { w = 0; d += d_step; }
+      b_lo += b_inc;
+      if (++sb == p.nB) { sb = 0; phb ^= 1u; b_lo = b_lo0; }
     }
     if (elect_one()) umma_commit(tfull);
     __syncwarp();
   } else if (lane == 0) {
-    // release warp: consumes the empty-barrier completions in order, publishes the count
-    uint32_t s = 0, ph = 0;
-    for (uint32_t g = 0; g < total; ++g) {
-      mbar_wait(empty(s), ph);
+    // ------------------------------- release warp --------------------------------------
+    uint32_t sa = 0, pha = 0, sb = 0, phb = 0, nA_done = 0;
+    for (uint32_t w = 0; w < n_win; ++w) {
+      for (uint32_t kk = 0; kk < G; ++kk) {
+        mbar_wait(bar_emptyA(bar0, sa), pha);
+        __threadfence_block();
+        sts_volatile(consumed, ++nA_done);
+        if (++sa == p.nA) { sa = 0; pha ^= 1u; }
+      }
+      mbar_wait(bar_emptyB(bar0, sb), phb);
       __threadfence_block();
-      sts_volatile(consumed, g + 1);
-      if (++s == p.nS) { s = 0; ph ^= 1u; }
+      sts_volatile(consumed + 1, w + 1);
+      if (++sb == p.nB) { sb = 0; phb ^= 1u; }
     }
   }
-done:
+
   tc_fence_before();
   __syncthreads();
   if (warp == NP + kEpilogueWarps) {
@@ -1504,29 +1501,40 @@ int conv_wgrad_tc(const void *in, const void *grad_out, int dtype, uint32_t c_in
                   cudaStream_t stream) {
   MEB_CUDA(cudaMemsetAsync(grad_weight, 0, (size_t)K * c_in * c_out * sizeof(float), stream));
   if (n_out == 0 || K == 0) return MEB200_OK;
-  // MEB200_TC_WGRAD=rs selects the pair-compacting register-staged variant (k_wgrad_rs).  It
-  // moves ~3x fewer bytes but is currently slower end to end (32 vs 20 ms per bench step,
-  // profiles/r1_notes.md), so the dense kernel stays the default.
-  static int dense = -1;
-  if (dense < 0) { const char *e = getenv("MEB200_TC_WGRAD"); dense = (e && e[0] == 'r') ? 0 : 1; }
-  if (!dense) {
-    const tc::WgRsCfg cfg = tc::wgrad_rs_config(c_in, c_out, K, n_out, (uint32_t)num_sms());
+  // MEB200_TC_WGRAD=win selects k_wgrad_rs2 (the forward kernel's register-staged producers over
+  // 128-row windows).  Measured slower than the cp.async kernel below (2.7 vs 1.8 ms on the
+  // largest layer, profiles/r1_notes.md), so it is opt-in; a pair-compacting variant was slower
+  // still and has been removed.
+  static int dense = -1;   // 1 = k_wgrad_tc (default), 2 = k_wgrad_rs2
+  if (dense < 0) {
+    const char *e = getenv("MEB200_TC_WGRAD");
+    dense = (e && e[0] == 'w') ? 2 : 1;
+    if (dense == 2 && encode_tiled_fn() == nullptr) dense = 1;
+  }
+  // (needs full 64-channel TMA boxes of dOut: c_out >= 64)
+  if (dense == 2 && c_out >= 64 && (reinterpret_cast<uintptr_t>(grad_out) & 15) == 0) {
+    const tc::Wg2Cfg cfg = tc::wgrad2_config(c_in, c_out, K, n_out, (uint32_t)num_sms());
     if (cfg.mt_cta != 0) {
-      WgRsParams q{};
-      q.in = in; q.gout = grad_out; q.nbr = out_nbr; q.dW = grad_weight;
+      CUtensorMap mG;
+      memset(&mG, 0, sizeof(mG));
+      int rc = make_map_2d(&mG, dtype, grad_out, n_out, c_out, 64, tc::kWg2Rows);
+      if (rc != MEB200_OK) return rc;
+      Wg2Params q{};
+      q.in = in; q.nbr = out_nbr; q.dW = grad_weight;
       q.c_in = c_in; q.c_out = c_out; q.K = K; q.n_out = n_out;
       q.G = cfg.G; q.n_kgroups = cfg.n_kgroups; q.mt_cta = cfg.mt_cta; q.n_mtgroups = cfg.n_mtgroups;
       q.rows_per_split = cfg.rows_per_split; q.n_splits = cfg.n_splits;
-      q.blkA = cfg.blkA; q.blkB = cfg.blkB; q.nS = cfg.nS; q.stage_bytes = cfg.stage_bytes;
+      q.blkA = cfg.blkA; q.blkB = cfg.blkB; q.nA = cfg.pipe.nA; q.nB = cfg.pipe.nB;
+      q.a_stage_bytes = cfg.a_stage_bytes; q.b_stage_bytes = cfg.b_stage_bytes;
       unsigned grid = cfg.n_kgroups * cfg.n_mtgroups * cfg.n_splits;
       if (dtype == MEB200_BF16) {
         static bool done = false;
-        if (!done) { MEB_CUDA(cudaFuncSetAttribute(k_wgrad_rs<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); done = true; }
-        k_wgrad_rs<__nv_bfloat16><<<grid, kWgRsThreads, cfg.smem_bytes, stream>>>(q);
+        if (!done) { MEB_CUDA(cudaFuncSetAttribute(k_wgrad_rs2<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); done = true; }
+        k_wgrad_rs2<__nv_bfloat16><<<grid, kWg2Threads, cfg.smem_bytes, stream>>>(mG, q);
       } else {
         static bool done = false;
-        if (!done) { MEB_CUDA(cudaFuncSetAttribute(k_wgrad_rs<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); done = true; }
-        k_wgrad_rs<__half><<<grid, kWgRsThreads, cfg.smem_bytes, stream>>>(q);
+        if (!done) { MEB_CUDA(cudaFuncSetAttribute(k_wgrad_rs2<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); done = true; }
+        k_wgrad_rs2<__half><<<grid, kWg2Threads, cfg.smem_bytes, stream>>>(mG, q);
       }
       count_tc_launch();
       MEB_LAUNCH_OK();

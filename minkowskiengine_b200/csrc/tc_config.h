@@ -129,45 +129,51 @@ inline WgCfg wgrad_config(uint32_t c_in, uint32_t c_out, uint32_t K, uint32_t n_
   return best;
 }
 
-// ---- wgrad, register-staged + compacted pairs (default) ---------------------------------
-// One ring of stages, each holding up to 64 compacted (input row, output row) pairs: blkA
-// 64-channel blocks of gathered input rows followed by blkB blocks of gathered dOut rows.
-constexpr uint32_t kWgRsProducerWarps = 8;
-constexpr uint32_t kWgRsScratchBytes = kWgRsProducerWarps * kWgRows * 8 + kMaxStages * 4 + 64;
-struct WgRsCfg {
-  uint32_t mt_cta;   // 0 = unsupported
-  uint32_t n_mtgroups, G, n_kgroups, blkA, blkB, stage_bytes, nS;
+// ---- wgrad, register-staged producers over dense 128-row windows (opt-in variant) ----
+// Stage A = the gathered (zero padded) input rows of one (window, offset): blkA blocks of
+// [128 rows][128 B]; stage B = the window's dOut rows, blkB blocks, shared by the G offsets of
+// the CTA's group.  Same producer scheme as the forward kernel (k_conv_rs).
+constexpr uint32_t kWg2ProducerWarps = 10;
+constexpr uint32_t kWg2Rows = 128;
+constexpr uint32_t kWg2BlkBytes = kWg2Rows * 128;
+constexpr uint32_t kWg2ScratchBytes = kWg2ProducerWarps * kWg2Rows * 8 + 64;
+struct Wg2Cfg {
+  uint32_t mt_cta;   // 0 = use the 64-row dense kernel instead
+  uint32_t n_mtgroups, G, n_kgroups, blkA, blkB, a_stage_bytes, b_stage_bytes;
+  PipeCfg pipe;
   uint32_t rows_per_split, n_splits, smem_bytes;
 };
-inline WgRsCfg wgrad_rs_config(uint32_t c_in, uint32_t c_out, uint32_t K, uint32_t n_out, uint32_t n_sms) {
-  WgRsCfg c{};
+inline Wg2Cfg wgrad2_config(uint32_t c_in, uint32_t c_out, uint32_t K, uint32_t n_out, uint32_t n_sms) {
+  Wg2Cfg best{};
   const uint32_t mt_total = cdiv_u(c_in, 128);
   uint32_t mt_max = mt_total < kTmemCols / c_out ? mt_total : kTmemCols / c_out;
   if (mt_max > 2) mt_max = 2;
-  const uint32_t budget = kSmemBudget - kBarBytes - 1024 - kWgRsScratchBytes;
+  const uint32_t budget = kSmemBudget - kBarBytes - 1024 - kWg2ScratchBytes;
   for (uint32_t mt = mt_max; mt >= 1; --mt) {
-    const uint32_t blkA = mt * 2, blkB = cdiv_u(c_out, 64);
-    const uint32_t stage = (blkA + blkB) * kBlkBytes;
-    uint32_t nS = budget / stage;
-    if (nS > 8) nS = 8;
-    if (nS < 2) continue;
-    c.mt_cta = mt; c.blkA = blkA; c.blkB = blkB; c.stage_bytes = stage; c.nS = nS;
-    break;
+    Wg2Cfg c{};
+    c.mt_cta = mt;
+    c.n_mtgroups = cdiv_u(mt_total, mt);
+    c.G = kTmemCols / (mt * c_out);
+    if (c.G > K) c.G = K;
+    if (c.G > 8) c.G = 8;
+    c.n_kgroups = cdiv_u(K, c.G);
+    c.blkA = mt * 2;
+    c.blkB = cdiv_u(c_out, 64);
+    c.a_stage_bytes = c.blkA * kWg2BlkBytes;
+    c.b_stage_bytes = c.blkB * kWg2BlkBytes;
+    c.pipe = pick_pipeline(c.a_stage_bytes, c.b_stage_bytes, c.G, budget);
+    if (c.pipe.nA >= 3 && c.pipe.nB >= 2) { best = c; break; }
   }
-  if (c.mt_cta == 0) return c;
-  c.n_mtgroups = cdiv_u(mt_total, c.mt_cta);
-  c.G = kTmemCols / (c.mt_cta * c_out);
-  if (c.G > K) c.G = K;
-  if (c.G > 8) c.G = 8;
-  c.n_kgroups = cdiv_u(K, c.G);
-  uint32_t base = c.n_kgroups * c.n_mtgroups;
+  if (best.mt_cta == 0) return best;
+  uint32_t base = best.n_kgroups * best.n_mtgroups;
   uint32_t want = cdiv_u(2ull * n_sms, base);
-  uint32_t max_splits = cdiv_u(n_out, 8 * kWgRows);
+  uint32_t max_splits = cdiv_u(n_out, 4 * kWg2Rows);
   uint32_t splits = want < 1 ? 1 : (want > max_splits ? max_splits : want);
-  c.rows_per_split = cdiv_u(cdiv_u(n_out, splits), kWgRows) * kWgRows;
-  c.n_splits = cdiv_u(n_out, c.rows_per_split);
-  c.smem_bytes = 1024 + c.nS * c.stage_bytes + kBarBytes + kWgRsScratchBytes;
-  return c;
+  best.rows_per_split = cdiv_u(cdiv_u(n_out, splits), kWg2Rows) * kWg2Rows;
+  best.n_splits = cdiv_u(n_out, best.rows_per_split);
+  best.smem_bytes = 1024 + best.pipe.nA * best.a_stage_bytes + best.pipe.nB * best.b_stage_bytes +
+                    kBarBytes + kWg2ScratchBytes;
+  return best;
 }
 
 }  // namespace tc

@@ -36,6 +36,15 @@ int main() {
     if (!ok) { printf("WG BAD ci=%u co=%u K=%u rows=%u\n", ci, co, K, rows); ++bad; }
     printf("wg %u %u %u %u : mt=%u G=%u lag=%u nA=%u nB=%u splits=%u smem=%u\n", ci, co, K, rows, w.mt_cta, w.G, w.pipe.lag, w.pipe.nA, w.pipe.nB, w.n_splits, w.smem_bytes);
   }
+  for (unsigned ci : cins) for (unsigned co : ncs) for (unsigned K : {1u, 8u, 27u, 125u}) for (unsigned rows : {1u, 300u, 800000u}) {
+    Wg2Cfg w = wgrad2_config(ci, co, K, rows, 148);
+    if (w.mt_cta == 0) continue;   // falls back to the 64-row kernel
+    bool ok = w.pipe.nA >= 3 && w.pipe.nB >= 2 && w.smem_bytes <= 227 * 1024 &&
+              w.G * w.mt_cta * co <= kTmemCols && w.n_splits * w.rows_per_split >= rows &&
+              w.a_stage_bytes == w.blkA * kWg2BlkBytes && w.blkB * 64 >= co;
+    if (!ok) { printf("WG2 BAD ci=%u co=%u K=%u rows=%u\n", ci, co, K, rows); ++bad; }
+    printf("wg2 %u %u %u %u : mt=%u G=%u nA=%u nB=%u splits=%u smem=%u\n", ci, co, K, rows, w.mt_cta, w.G, w.pipe.nA, w.pipe.nB, w.n_splits, w.smem_bytes);
+  }
   printf("bad=%d\n", bad);
   return bad != 0;
 }
