@@ -8,6 +8,8 @@
 // output row is produced by exactly one CTA from the k-major neighbour table.
 #include "conv_simt.cuh"
 
+#include <algorithm>
+
 namespace meb200 {
 
 constexpr int TM = 64, TN = 64, TK = 16;
@@ -166,9 +168,36 @@ k_conv_wgrad(const T *__restrict__ in, const T *__restrict__ grad_out, uint32_t 
 }
 
 // ---- tiny input-channel count (the network stem: c_in <= 4, e.g. RGB -> 32, K = 125) -------
-// Too few channels for a GEMM tile; the layer is bound by the neighbour-table scan.  One
-// thread per output row keeps all CO outputs in registers; the table column is read
-// coalesced, W (fp32, [K, c_in, CO]) is broadcast from shared memory.
+// Too few channels for a GEMM tile; both passes are bound by the latency of the neighbour-table
+// scan and of the row gathers behind it, so both keep many independent loads in flight.
+//
+// Forward: persistent CTAs (W staged to shared memory once per CTA as fp32 [K][c_in][CO]),
+// one thread per output row with all CO outputs in registers.  Offsets are walked in batches
+// of SK: the SK table entries of the NEXT batch and the SK gathered rows of THIS batch are
+// issued before the FMAs, so a thread has up to 2*SK independent loads outstanding instead of
+// a dependent (index -> row) chain per offset.
+constexpr int SK = 8;
+
+template <typename TOut, int CO>
+__device__ __forceinline__ void store_row(TOut *__restrict__ dst, const float (&acc)[CO],
+                                          uint32_t c_out) {
+  if constexpr (sizeof(TOut) == 2) {
+    if (c_out == (uint32_t)CO) {  // rows are CO*2 bytes: 16 B aligned for CO in {32, 64}
+#pragma unroll
+      for (int v = 0; v < CO / 8; ++v) {
+        TOut t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = from_f32<TOut>(acc[8 * v + j]);
+        reinterpret_cast<uint4 *>(dst)[v] = *reinterpret_cast<const uint4 *>(t);
+      }
+      return;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < CO; ++i)
+    if ((uint32_t)i < c_out) dst[i] = from_f32<TOut>(acc[i]);
+}
+
 template <typename T, typename TOut, int CO>
 __global__ void __launch_bounds__(128)
 k_conv_small_cin_fwd(const T *__restrict__ in, uint32_t c_in, const T *__restrict__ W, uint32_t K,
@@ -180,79 +209,172 @@ k_conv_small_cin_fwd(const T *__restrict__ in, uint32_t c_in, const T *__restric
     Ws[e] = co < c_out ? to_f32<T>(W[(size_t)kc * c_out + co]) : 0.f;
   }
   __syncthreads();
-  const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
-  float acc[CO];
+  const uint32_t n_tiles = (n_out + 127) / 128;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t o = tile * 128 + threadIdx.x;
+    const bool live = o < n_out;
+    const int32_t *col = nbr + o;
+    float acc[CO];
 #pragma unroll
-  for (int i = 0; i < CO; ++i) acc[i] = 0.f;
-  for (uint32_t k = 0; k < K; ++k) {
-    int32_t i = (o < n_out) ? __ldg(nbr + (size_t)k * n_out + o) : -1;
-    if (i < 0) continue;
-    for (uint32_t c = 0; c < c_in; ++c) {
-      const float x = to_f32<T>(in[(size_t)i * c_in + c]);
-      const float4 *w4 = reinterpret_cast<const float4 *>(Ws + (size_t)(k * c_in + c) * CO);
+    for (int i = 0; i < CO; ++i) acc[i] = 0.f;
+    int32_t idx[SK];
 #pragma unroll
-      for (int v = 0; v < CO / 4; ++v) {
-        float4 w = w4[v];
-        acc[4 * v + 0] = fmaf(x, w.x, acc[4 * v + 0]);
-        acc[4 * v + 1] = fmaf(x, w.y, acc[4 * v + 1]);
-        acc[4 * v + 2] = fmaf(x, w.z, acc[4 * v + 2]);
-        acc[4 * v + 3] = fmaf(x, w.w, acc[4 * v + 3]);
+    for (int j = 0; j < SK; ++j)
+      idx[j] = (live && (uint32_t)j < K) ? __ldg(col + (size_t)j * n_out) : -1;
+    for (uint32_t k0 = 0; k0 < K; k0 += SK) {
+      int32_t nxt[SK];
+#pragma unroll
+      for (int j = 0; j < SK; ++j) {
+        const uint32_t kk = k0 + SK + j;
+        nxt[j] = (live && kk < K) ? __ldg(col + (size_t)kk * n_out) : -1;
       }
-    }
-  }
-  if (o < n_out) {
+      float x[SK][4];
 #pragma unroll
-    for (int i = 0; i < CO; ++i)
-      if ((uint32_t)i < c_out) out[(size_t)o * c_out + i] = from_f32<TOut>(acc[i]);
+      for (int j = 0; j < SK; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          x[j][c] = (idx[j] >= 0 && (uint32_t)c < c_in)
+                        ? to_f32<T>(in[(size_t)idx[j] * c_in + c]) : 0.f;
+#pragma unroll
+      for (int j = 0; j < SK; ++j) {
+        if (idx[j] < 0) continue;
+        const float *wk = Ws + (size_t)(k0 + j) * c_in * CO;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if ((uint32_t)c >= c_in) break;
+          const float4 *w4 = reinterpret_cast<const float4 *>(wk + c * CO);
+#pragma unroll
+          for (int v = 0; v < CO / 4; ++v) {
+            const float4 w = w4[v];
+            acc[4 * v + 0] = fmaf(x[j][c], w.x, acc[4 * v + 0]);
+            acc[4 * v + 1] = fmaf(x[j][c], w.y, acc[4 * v + 1]);
+            acc[4 * v + 2] = fmaf(x[j][c], w.z, acc[4 * v + 2]);
+            acc[4 * v + 3] = fmaf(x[j][c], w.w, acc[4 * v + 3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < SK; ++j) idx[j] = nxt[j];
+    }
+    if (live) store_row<TOut, CO>(out + (size_t)o * c_out, acc, c_out);
   }
 }
 
 // dW[k][c][co] = sum_o in[nbr[k][o]][c] * dOut[o][co] for c_in <= 4, c_out <= 64.
-// Warp <-> offset k, lane <-> output channel; a batch of 32 table entries is read coalesced,
-// the hits are walked with ballot/shfl; partial sums stay in registers until the row slice ends.
+// Warp <-> (offset k, row slice, 32-channel slab).  The table column is scanned 256 rows at a
+// time (8 independent coalesced loads per lane); hits are compacted with ballot/popc into a
+// per-warp shared-memory list, and the list is consumed 32 hits at a time with lane <-> hit:
+// every lane fetches its own dOut row slab (vector loads) and input row and accumulates a private
+// [CIN][32] tile in registers, so 32 row fetches are in flight per warp instead of one.  The
+// 32 private tiles are folded with butterfly shuffles once per warp and added to dW atomically.
+constexpr int WG_SCAN = 256;             // table entries scanned per round (8 per lane)
+constexpr int WG_LIST = WG_SCAN + 32;    // + carried remainder (< 32)
+
 template <typename T>
-__global__ void __launch_bounds__(256)
-k_conv_small_cin_wgrad(const T *__restrict__ in, const T *__restrict__ gout, uint32_t c_in,
-                       uint32_t c_out, uint32_t K, const int32_t *__restrict__ nbr, uint32_t n_out,
-                       uint32_t rows_per_block, float *__restrict__ dW) {
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t k = blockIdx.y * 8 + warp;
-  if (k >= K) return;
-  const uint32_t r0 = blockIdx.x * rows_per_block;
-  const uint32_t r1 = min(r0 + rows_per_block, n_out);
-  float acc[4][2] = {};
-  const int32_t *nbr_k = nbr + (size_t)k * n_out;
-  for (uint32_t o0 = r0; o0 < r1; o0 += 32) {
-    const uint32_t o = o0 + lane;
-    const int32_t idx = (o < r1) ? __ldg(nbr_k + o) : -1;
-    unsigned mask = __ballot_sync(0xffffffffu, idx >= 0);
-    while (mask) {
-      const int b = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const int32_t i = __shfl_sync(0xffffffffu, idx, b);
-      const T *grow = gout + (size_t)(o0 + b) * c_out;
-      const float g0 = lane < c_out ? to_f32<T>(grow[lane]) : 0.f;
-      const float g1 = lane + 32 < c_out ? to_f32<T>(grow[lane + 32]) : 0.f;
+__device__ __forceinline__ void load_slab32(const T *__restrict__ p, uint32_t nco, bool vec,
+                                            float (&g)[32]) {
+  if (vec) {  // nco == 32 and p is 16 B aligned
+    constexpr int PER = 16 / sizeof(T);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if ((uint32_t)c < c_in) {
-          const float x = to_f32<T>(in[(size_t)i * c_in + c]);
-          acc[c][0] = fmaf(x, g0, acc[c][0]);
-          acc[c][1] = fmaf(x, g1, acc[c][1]);
-        }
-      }
+    for (int v = 0; v < 32 / PER; ++v) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4 *>(p) + v);
+      T t[PER];
+      *reinterpret_cast<uint4 *>(t) = q;
+#pragma unroll
+      for (int j = 0; j < PER; ++j) g[v * PER + j] = to_f32<T>(t[j]);
     }
-  }
+  } else {
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    if ((uint32_t)c >= c_in) continue;
-    float *dst = dW + ((size_t)k * c_in + c) * c_out;
-    if (lane < c_out && acc[c][0] != 0.f) atomicAdd(dst + lane, acc[c][0]);
-    if (lane + 32 < c_out && acc[c][1] != 0.f) atomicAdd(dst + lane + 32, acc[c][1]);
+    for (int j = 0; j < 32; ++j) g[j] = (uint32_t)j < nco ? to_f32<T>(p[j]) : 0.f;
   }
 }
 
-bool conv_small_cin_supported(uint32_t c_in, uint32_t c_out) { return c_in <= 4 && c_out <= 64; }
+template <typename T, int CIN>
+__global__ void __launch_bounds__(256, 1)
+k_conv_small_cin_wgrad(const T *__restrict__ in, const T *__restrict__ gout, uint32_t c_out,
+                       uint32_t K, const int32_t *__restrict__ nbr, uint32_t n_out,
+                       uint32_t rows_per_block, float *__restrict__ dW) {
+  __shared__ uint2 s_hits[8][WG_LIST];  // (output row, input row) per warp
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t k = blockIdx.y * 8 + warp;
+  if (k >= K) return;  // warps never synchronise with each other below
+  const uint32_t co0 = blockIdx.z * 32;
+  const uint32_t nco = min(32u, c_out - co0);
+  const bool vec = nco == 32 && ((size_t)c_out * sizeof(T)) % 16 == 0 &&
+                   ((size_t)co0 * sizeof(T)) % 16 == 0 &&
+                   (reinterpret_cast<uintptr_t>(gout) & 15) == 0;
+  const uint32_t r0 = blockIdx.x * rows_per_block;
+  const uint32_t r1 = min(r0 + rows_per_block, n_out);
+  const int32_t *nbr_k = nbr + (size_t)k * n_out;
+  uint2 *list = s_hits[warp];
+  const uint32_t lt = (1u << lane) - 1u;
+
+  float acc[CIN][32];
+#pragma unroll
+  for (int c = 0; c < CIN; ++c)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[c][j] = 0.f;
+
+  auto consume = [&](const uint2 h) {
+    float g[32];
+    load_slab32<T>(gout + (size_t)h.x * c_out + co0, nco, vec, g);
+    float x[CIN];
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) x[c] = to_f32<T>(in[(size_t)h.y * CIN + c]);
+#pragma unroll
+    for (int c = 0; c < CIN; ++c)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[c][j] = fmaf(x[c], g[j], acc[c][j]);
+  };
+
+  uint32_t cnt = 0;
+  for (uint32_t o0 = r0; o0 < r1; o0 += WG_SCAN) {
+    int32_t idx[WG_SCAN / 32];
+#pragma unroll
+    for (int j = 0; j < WG_SCAN / 32; ++j) {
+      const uint32_t o = o0 + j * 32 + lane;
+      idx[j] = o < r1 ? __ldg(nbr_k + o) : -1;
+    }
+#pragma unroll
+    for (int j = 0; j < WG_SCAN / 32; ++j) {
+      const unsigned m = __ballot_sync(0xffffffffu, idx[j] >= 0);
+      if (idx[j] >= 0) list[cnt + __popc(m & lt)] = make_uint2(o0 + j * 32 + lane, (uint32_t)idx[j]);
+      cnt += __popc(m);
+    }
+    __syncwarp();
+    uint32_t done = 0;
+    while (cnt - done >= 32) {
+      consume(list[done + lane]);
+      done += 32;
+    }
+    if (done) {  // move the remainder (< 32 hits) to the front of the list
+      const uint32_t rem = cnt - done;
+      uint2 t = make_uint2(0, 0);
+      if (lane < rem) t = list[done + lane];
+      __syncwarp();
+      if (lane < rem) list[lane] = t;
+      cnt = rem;
+    }
+    __syncwarp();
+  }
+  if (lane < cnt) consume(list[lane]);
+
+#pragma unroll
+  for (int c = 0; c < CIN; ++c) {
+    float *dst = dW + ((size_t)k * CIN + c) * c_out + co0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float v = acc[c][j];
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+      if (lane == (uint32_t)j && (uint32_t)j < nco && v != 0.f) atomicAdd(dst + j, v);
+    }
+  }
+}
+
+bool conv_small_cin_supported(uint32_t c_in, uint32_t c_out) {
+  return c_in >= 1 && c_in <= 4 && c_out <= 64;
+}
 
 template <typename T, typename TOut>
 static int launch_small_fwd(const void *in, uint32_t c_in, const void *W, uint32_t K,
@@ -261,7 +383,9 @@ static int launch_small_fwd(const void *in, uint32_t c_in, const void *W, uint32
   const int CO = c_out <= 32 ? 32 : 64;
   size_t smem = (size_t)K * c_in * CO * sizeof(float);
   if (smem > 200 * 1024) return MEB200_ERR_UNSUPPORTED;
-  unsigned grid = cdiv(n_out, 128);
+  // persistent CTAs: as many as fit beside each other (shared memory bound), W staged once each
+  unsigned per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (smem + 1024)));
+  unsigned grid = std::min<unsigned>(cdiv(n_out, 128), per_sm * num_sms());
   if (CO == 32) {
     auto kern = k_conv_small_cin_fwd<T, TOut, 32>;
     MEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -292,31 +416,43 @@ int conv_small_cin_forward(const void *in, int in_dtype, uint32_t c_in, const vo
   return MEB200_ERR_UNSUPPORTED;
 }
 
+template <typename T>
+static int launch_small_wgrad(const void *in, const void *gout, uint32_t c_in, uint32_t K,
+                              uint32_t c_out, const int32_t *nbr, uint32_t n_out, float *dW,
+                              cudaStream_t stream) {
+  const uint32_t kgroups = cdiv(K, 8), slabs = cdiv(c_out, 32);
+  // one 8-warp CTA per SM (register tiles); aim at ~4 CTAs per SM over the whole grid
+  uint32_t want_slices = std::max(1u, cdiv(4ull * num_sms(), (uint64_t)kgroups * slabs));
+  uint32_t rows_per_block = cdiv(cdiv(n_out, want_slices), WG_SCAN) * WG_SCAN;
+  if (rows_per_block < 4 * WG_SCAN) rows_per_block = 4 * WG_SCAN;
+  dim3 grid(cdiv(n_out, rows_per_block), kgroups, slabs);
+  const T *x = (const T *)in, *g = (const T *)gout;
+  switch (c_in) {
+    case 1: k_conv_small_cin_wgrad<T, 1><<<grid, 256, 0, stream>>>(x, g, c_out, K, nbr, n_out, rows_per_block, dW); break;
+    case 2: k_conv_small_cin_wgrad<T, 2><<<grid, 256, 0, stream>>>(x, g, c_out, K, nbr, n_out, rows_per_block, dW); break;
+    case 3: k_conv_small_cin_wgrad<T, 3><<<grid, 256, 0, stream>>>(x, g, c_out, K, nbr, n_out, rows_per_block, dW); break;
+    case 4: k_conv_small_cin_wgrad<T, 4><<<grid, 256, 0, stream>>>(x, g, c_out, K, nbr, n_out, rows_per_block, dW); break;
+    default: return MEB200_ERR_UNSUPPORTED;
+  }
+  MEB_LAUNCH_OK();
+  return MEB200_OK;
+}
+
 int conv_small_cin_wgrad(const void *in, const void *grad_out, int dtype, uint32_t c_in, uint32_t K,
                          uint32_t c_out, const int32_t *out_nbr, uint32_t n_out, float *grad_weight,
                          cudaStream_t stream) {
   MEB_CUDA(cudaMemsetAsync(grad_weight, 0, (size_t)K * c_in * c_out * sizeof(float), stream));
   if (n_out == 0 || K == 0) return MEB200_OK;
-  const uint32_t kgroups = cdiv(K, 8);
-  uint32_t want_blocks = cdiv(8ull * num_sms(), kgroups);
-  uint32_t rows_per_block = cdiv(cdiv(n_out, want_blocks), 32) * 32;
-  if (rows_per_block < 1024) rows_per_block = 1024;
-  dim3 grid(cdiv(n_out, rows_per_block), kgroups);
   switch (dtype) {
     case MEB200_F32:
-      k_conv_small_cin_wgrad<float><<<grid, 256, 0, stream>>>((const float *)in, (const float *)grad_out, c_in, c_out, K, out_nbr, n_out, rows_per_block, grad_weight);
-      break;
+      return launch_small_wgrad<float>(in, grad_out, c_in, K, c_out, out_nbr, n_out, grad_weight, stream);
     case MEB200_BF16:
-      k_conv_small_cin_wgrad<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16 *)in, (const __nv_bfloat16 *)grad_out, c_in, c_out, K, out_nbr, n_out, rows_per_block, grad_weight);
-      break;
+      return launch_small_wgrad<__nv_bfloat16>(in, grad_out, c_in, K, c_out, out_nbr, n_out, grad_weight, stream);
     case MEB200_F16:
-      k_conv_small_cin_wgrad<__half><<<grid, 256, 0, stream>>>((const __half *)in, (const __half *)grad_out, c_in, c_out, K, out_nbr, n_out, rows_per_block, grad_weight);
-      break;
+      return launch_small_wgrad<__half>(in, grad_out, c_in, K, c_out, out_nbr, n_out, grad_weight, stream);
     default:
       return MEB200_ERR_UNSUPPORTED;
   }
-  MEB_LAUNCH_OK();
-  return MEB200_OK;
 }
 
 template <typename TIn, typename TOut>

@@ -145,7 +145,7 @@ class MinkowskiSyncBatchNorm(MinkowskiBatchNorm):
         bn = self.bn
         group = None
         if bn.training and torch.distributed.is_available() and torch.distributed.is_initialized():
-            group = bn.process_group or torch.distributed.group.WORLD
+            group = getattr(bn, "process_group", None) or torch.distributed.group.WORLD
             if torch.distributed.get_world_size(group) == 1:
                 group = None
         output = _batch_norm(bn, input.F, group) if _native_ok(bn, input.F) else bn(input.F)
@@ -168,6 +168,7 @@ class MinkowskiSyncBatchNorm(MinkowskiBatchNorm):
             module_output.bn.running_mean = module.bn.running_mean
             module_output.bn.running_var = module.bn.running_var
             module_output.bn.num_batches_tracked = module.bn.num_batches_tracked
+            return module_output         # its only child is the parameter holder just rebuilt
         for name, child in module.named_children():
             module_output.add_module(name, cls.convert_sync_batchnorm(child, process_group))
         del module

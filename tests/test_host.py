@@ -117,3 +117,18 @@ def test_minkunet_definition_parameter_count():
     net = minkunet("MinkUNet34C", ME, 3, 20, 3)
     assert sum(p.numel() for p in net.parameters()) == 37_856_052   # SURVEY.md §2 probe count
     assert sum(1 for m in net.modules() if isinstance(m, ME.MinkowskiBatchNorm)) == 62
+
+
+def test_convert_sync_batchnorm_keeps_sync_holder():
+    """reference MinkowskiNormalization.py:123-192: every MinkowskiBatchNorm becomes a
+    MinkowskiSyncBatchNorm whose parameter holder is a torch SyncBatchNorm sharing the
+    original affine parameters and running statistics."""
+    import torch
+    import minkowskiengine_b200 as ME
+    net = torch.nn.Sequential(ME.MinkowskiBatchNorm(8), torch.nn.Sequential(ME.MinkowskiBatchNorm(16)))
+    w0 = net[0].bn.weight
+    out = ME.MinkowskiSyncBatchNorm.convert_sync_batchnorm(net)
+    bns = [m for m in out.modules() if isinstance(m, ME.MinkowskiBatchNorm)]
+    assert len(bns) == 2 and all(isinstance(m, ME.MinkowskiSyncBatchNorm) for m in bns)
+    assert all(isinstance(m.bn, torch.nn.SyncBatchNorm) for m in bns)
+    assert out[0].bn.weight is w0 and out[1][0].bn.num_features == 16
