@@ -232,7 +232,10 @@ def run_ours(args):
     net = minkunet(args.model, ME, 3, 20, 3).to(dev)
     if world > 1:
         net = ME.MinkowskiSyncBatchNorm.convert_sync_batchnorm(net)
-        net = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank])
+        # SyncBN keeps the running statistics identical on every rank, so the per-step buffer
+        # broadcast is redundant; gradients live in the all-reduce buckets (no extra copy).
+        net = torch.nn.parallel.DistributedDataParallel(
+            net, device_ids=[local_rank], broadcast_buffers=False, gradient_as_bucket_view=True)
     opt = torch.optim.SGD(net.parameters(), lr=1e-2)
     crit = torch.nn.CrossEntropyLoss()
 
