@@ -1108,8 +1108,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(const WgParams p) {
   const uint32_t kg = wi % p.n_kgroups; wi /= p.n_kgroups;
   const uint32_t mtg = wi % p.n_mtgroups; wi /= p.n_mtgroups;
   const uint32_t split = wi;
-  const uint32_t k0 = kg * p.G;
-  const uint32_t G = min(p.G, p.K - k0);
+  const uint32_t k0 = tc::kgroup_begin(kg, p.K, p.n_kgroups);
+  const uint32_t G = tc::kgroup_begin(kg + 1, p.K, p.n_kgroups) - k0;   // <= p.G
   const uint32_t r_begin = split * p.rows_per_split;
   const uint32_t r_end = min(r_begin + p.rows_per_split, p.n_out);
   const uint32_t n_chunks = (r_end - r_begin + kWgRows - 1) / kWgRows;

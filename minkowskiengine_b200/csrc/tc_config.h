@@ -96,6 +96,15 @@ struct WgCfg {
   uint32_t rows_per_split, n_splits;
   uint32_t smem_bytes;
 };
+// First offset of k-group kg when K offsets are dealt to n_kgroups groups whose sizes differ
+// by at most one (the first K % n_kgroups groups get the extra offset).
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline uint32_t kgroup_begin(uint32_t kg, uint32_t K, uint32_t n_kgroups) {
+  const uint32_t base = K / n_kgroups, rem = K % n_kgroups;
+  return kg * base + (kg < rem ? kg : rem);
+}
 inline WgCfg wgrad_config(uint32_t c_in, uint32_t c_out, uint32_t K, uint32_t n_out, uint32_t n_sms) {
   WgCfg best{};
   const uint32_t mt_total = cdiv_u(c_in, 128);
@@ -118,9 +127,12 @@ inline WgCfg wgrad_config(uint32_t c_in, uint32_t c_out, uint32_t K, uint32_t n_
     if (c.pipe.lag >= 3) break;
   }
   if (best.pipe.lag == 0) { best.mt_cta = 0; return best; }
-  // row slices: ~2 waves of CTAs, each slice a multiple of the stage height
+  // row slices: at most 2 full waves of CTAs (one CTA per SM; a third, nearly empty wave
+  // cost a third of the launch on the 96-channel layers), each slice a multiple of the stage
+  // height.  Offsets are dealt to the k-groups evenly (kgroup_begin), so CTAs differ by at
+  // most one offset of work.
   uint32_t base = best.n_kgroups * best.n_mtgroups;
-  uint32_t want = cdiv_u(2ull * n_sms, base);
+  uint32_t want = (2u * n_sms) / base;
   uint32_t max_splits = cdiv_u(n_out, 4 * kWgRows);
   uint32_t splits = want < 1 ? 1 : (want > max_splits ? max_splits : want);
   best.rows_per_split = cdiv_u(cdiv_u(n_out, splits), kWgRows) * kWgRows;

@@ -32,6 +32,17 @@ int main() {
     bool ok = w.mt_cta != 0 && w.pipe.lag >= 1 && w.smem_bytes <= 227 * 1024 &&
               w.G * w.mt_cta * co <= kTmemCols && w.G >= 1 && w.n_splits * w.rows_per_split >= rows
               && w.pipe.nA >= 2 && w.pipe.nB >= 2;
+    /* one CTA per SM: never a third, nearly empty wave; k-groups cover K, sizes <= G, differ by <= 1 */
+    if (ok && w.n_splits > 1) ok = w.n_splits * w.n_kgroups * w.n_mtgroups <= 2 * 148;
+    if (ok) {
+      unsigned lo = K, hi = 0;
+      for (unsigned kg = 0; kg < w.n_kgroups; ++kg) {
+        unsigned g = kgroup_begin(kg + 1, K, w.n_kgroups) - kgroup_begin(kg, K, w.n_kgroups);
+        lo = g < lo ? g : lo; hi = g > hi ? g : hi;
+      }
+      ok = kgroup_begin(0, K, w.n_kgroups) == 0 && kgroup_begin(w.n_kgroups, K, w.n_kgroups) == K
+           && hi <= w.G && hi - lo <= 1 && lo >= 1;
+    }
     if (w.mt_cta == 0 && co == 256 && K == 1) ok = true;  // declared unsupported -> SIMT fallback
     if (!ok) { printf("WG BAD ci=%u co=%u K=%u rows=%u\n", ci, co, K, rows); ++bad; }
     printf("wg %u %u %u %u : mt=%u G=%u lag=%u nA=%u nB=%u splits=%u smem=%u\n", ci, co, K, rows, w.mt_cta, w.G, w.pipe.lag, w.pipe.nA, w.pipe.nB, w.n_splits, w.smem_bytes);
