@@ -335,6 +335,16 @@ def run_ours(args):
                           "frac": tf(wg) / peak, "ms_per_step": wg["ms"] / wg["steps"],
                           "share_of_step": wg["ms"] / wg["steps"] / step_ms,
                           "launches_per_step": wg["launches"] / wg["steps"]}}
+        # DRAM traffic comes from an ncu --set full capture of ONE launch (the largest layer),
+        # not from this run: copy the committed figure and say which launch it describes.
+        try:
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))["k_conv_rs"]
+            roof["traffic"] = cap["dram_bytes_read"] + cap["dram_bytes_write"]
+            roof["traffic_launch"] = cap["launch"]
+            roof["traffic_algorithmic_bytes"] = cap["algorithmic_bytes"]
+            roof["traffic_source"] = cap["capture"]
+        except (OSError, KeyError, ValueError):
+            pass
 
     if rank == 0:
         cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline(args)

@@ -1085,7 +1085,11 @@ struct WgParams {
   uint32_t lag;
 };
 
-template <typename T>
+// PF = how many (chunk, offset) work items ahead of use the neighbour indices are fetched.
+// PF == 0 is the round-1 kernel (one item ahead: every stage then waits out most of one index
+// load latency, profiles/r1_ncu_k_wgrad_tc_block8_96x96.txt); PF > 0 keeps a register ring of
+// PF index sets so the index latency is covered by PF stages of copy issue.
+template <typename T, int PF>
 __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(const WgParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>(
@@ -1136,8 +1140,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(const WgParams p) {
     const T *in = reinterpret_cast<const T *>(p.in);
     const T *gout = reinterpret_cast<const T *>(p.gout);
     uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
-    // neighbour rows for (chunk c, offset kk), fetched one work item ahead of use
-    int32_t idx_cur[kWgRows / 16], idx_nxt[kWgRows / 16];
+    // neighbour rows for (chunk c, offset kk), fetched ahead of use
     auto load_idx = [&](uint32_t c, uint32_t kk, int32_t (&dst)[kWgRows / 16]) {
       const int32_t *nbr_k = p.nbr + (size_t)(k0 + kk) * p.n_out;
 #pragma unroll
@@ -1146,15 +1149,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(const WgParams p) {
         dst[it] = (o < r_end) ? __ldg(nbr_k + o) : -1;
       }
     };
-    if (n_chunks > 0) load_idx(0, 0, idx_cur);
-    for (uint32_t c = 0; c < n_chunks; ++c) {
-      const uint32_t row0 = r_begin + c * kWgRows;
-      for (uint32_t kk = 0; kk < G; ++kk) {
-        {
-          uint32_t nc = c, nkk = kk + 1;
-          if (nkk == G) { nkk = 0; nc = c + 1; }
-          if (nc < n_chunks) load_idx(nc, nkk, idx_nxt);
-        }
+    // one work item: (re)use ring slots, issue the copies of stage (c, kk), publish them
+    auto issue_stage = [&](uint32_t c, uint32_t kk, const int32_t (&idx_cur)[kWgRows / 16]) {
+        const uint32_t row0 = r_begin + c * kWgRows;
         mbar_wait(emptyA(sa), pha ^ 1u);
         if (kk == 0) {
           mbar_wait(emptyB(sb), phb ^ 1u);
@@ -1190,14 +1187,52 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(const WgParams p) {
         }
         cp_async_mbar_arrive(fullA(sa));
         if (++sa == p.nA) { sa = 0; pha ^= 1u; }
+    };
+    if constexpr (PF == 0) {
+      int32_t idx_cur[kWgRows / 16], idx_nxt[kWgRows / 16];
+      if (n_chunks > 0) load_idx(0, 0, idx_cur);
+      for (uint32_t c = 0; c < n_chunks; ++c) {
+        for (uint32_t kk = 0; kk < G; ++kk) {
+          {
+            uint32_t nc = c, nkk = kk + 1;
+            if (nkk == G) { nkk = 0; nc = c + 1; }
+            if (nc < n_chunks) load_idx(nc, nkk, idx_nxt);
+          }
+          issue_stage(c, kk, idx_cur);
 #pragma unroll
-        for (int it = 0; it < kWgRows / 16; ++it) idx_cur[it] = idx_nxt[it];
+          for (int it = 0; it < kWgRows / 16; ++it) idx_cur[it] = idx_nxt[it];
+        }
+      }
+    } else {
+      // register ring of PF index sets, statically indexed (the loop is unrolled by PF): slot d
+      // is refilled with work item w + PF right after item w's copies were issued from it.
+      int32_t ring[PF][kWgRows / 16];
+      const uint32_t n_work = n_chunks * G;
+      uint32_t pc = 0, pkk = 0, c = 0, kk = 0;
+#pragma unroll
+      for (int d = 0; d < PF; ++d) {
+#pragma unroll
+        for (int it = 0; it < kWgRows / 16; ++it) ring[d][it] = -1;
+        if (pc < n_chunks) load_idx(pc, pkk, ring[d]);
+        if (++pkk == G) { pkk = 0; ++pc; }
+      }
+      for (uint32_t w0 = 0; w0 < n_work; w0 += PF) {
+#pragma unroll
+        for (int d = 0; d < PF; ++d) {
+          if (w0 + d < n_work) {
+            issue_stage(c, kk, ring[d]);
+            if (pc < n_chunks) load_idx(pc, pkk, ring[d]);
+            if (++pkk == G) { pkk = 0; ++pc; }
+            if (++kk == G) { kk = 0; ++c; }
+          }
+        }
       }
     }
     cp_async_wait<0>();
   } else if (warp < kProducerWarps + kEpilogueWarps) {
     const uint32_t q = warp & 3u;
-    mbar_wait(tfull, 0);
+    if constexpr (PF == 0) mbar_wait(tfull, 0);
+    else mbar_wait_sleep(tfull, 0, 500);   // parked for the whole main loop
     tc_fence_after();
     for (uint32_t kk = 0; kk < G; ++kk) {
       for (uint32_t t = 0; t < mt; ++t) {
@@ -1556,15 +1591,26 @@ int conv_wgrad_tc(const void *in, const void *grad_out, int dtype, uint32_t c_in
   p.rows_per_split = cfg.rows_per_split; p.n_splits = cfg.n_splits;
   size_t smem_bytes = cfg.smem_bytes;
   unsigned grid = cfg.n_kgroups * cfg.n_mtgroups * cfg.n_splits;
+  // MEB200_WG_PREFETCH = 4 | 8 | 16: experimental deeper index prefetch (see k_wgrad_tc); default 0
+  int pf = 0;
+  if (const char *e = getenv("MEB200_WG_PREFETCH")) pf = atoi(e);
+  auto launch = [&](auto kern) -> int {
+    static bool done = false;   // one flag per kernel instantiation (generic lambda)
+    if (!done) { MEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); done = true; }
+    kern<<<grid, kThreads, smem_bytes, stream>>>(p);
+    return MEB200_OK;
+  };
+  int rc;
   if (dtype == MEB200_BF16) {
-    static bool done = false;
-    if (!done) { MEB_CUDA(cudaFuncSetAttribute(k_wgrad_tc<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); done = true; }
-    k_wgrad_tc<__nv_bfloat16><<<grid, kThreads, smem_bytes, stream>>>(p);
+    rc = pf >= 16 ? launch(k_wgrad_tc<__nv_bfloat16, 16>)
+         : pf >= 8 ? launch(k_wgrad_tc<__nv_bfloat16, 8>)
+         : pf >= 4 ? launch(k_wgrad_tc<__nv_bfloat16, 4>) : launch(k_wgrad_tc<__nv_bfloat16, 0>);
   } else {
-    static bool done = false;
-    if (!done) { MEB_CUDA(cudaFuncSetAttribute(k_wgrad_tc<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); done = true; }
-    k_wgrad_tc<__half><<<grid, kThreads, smem_bytes, stream>>>(p);
+    rc = pf >= 16 ? launch(k_wgrad_tc<__half, 16>)
+         : pf >= 8 ? launch(k_wgrad_tc<__half, 8>)
+         : pf >= 4 ? launch(k_wgrad_tc<__half, 4>) : launch(k_wgrad_tc<__half, 0>);
   }
+  if (rc != MEB200_OK) return rc;
   count_tc_launch();
   MEB_LAUNCH_OK();
   return MEB200_OK;

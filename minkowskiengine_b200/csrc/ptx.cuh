@@ -35,6 +35,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Long waits (a role parked until the end of the CTA's work): back off between polls so the
+// spinning warps do not compete with the producers for issue slots.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, unsigned ns) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
 
 // ---- cp.async (LDGSTS) ------------------------------------------------------------
 // 16-byte global->shared copy; src_bytes = 0 zero-fills the destination (missing row).
