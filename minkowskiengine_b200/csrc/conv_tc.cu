@@ -659,9 +659,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       q.r = rem2 - q.mc * R;
       return q;
     };
-    // lane l holds the neighbour rows of tile rows l, l+32, l+64, l+96 (coalesced table reads),
-    // fetched one stage ahead of use; the copy loop pulls them out with shuffles.
-    int32_t idx_cur[4], idx_nxt[4];
+    // lane l holds the neighbour rows of tile rows l, l+32, l+64, l+96 (coalesced table reads);
+    // the copy loop pulls them out with shuffles.  The indices of the warp's next kCpRing stages
+    // sit in a statically indexed register ring (the stage loop is unrolled by the ring depth):
+    // with one stage of look-ahead every stage waited out most of an index-load latency (the
+    // same stall profiles/r1_ncu_k_wgrad_tc_block8_96x96.txt shows for the wgrad producers).
+    constexpr int kCpRing = 4;
     auto load_idx = [&](uint32_t g, int32_t (&dst)[4]) {
       const Pos q = decode(g);
       const int32_t *nbr_k = p.nbr + (size_t)q.k * p.n_rows;
@@ -676,10 +679,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     // most one ring revolution apart, otherwise the parity wait on the empty barrier could be
     // satisfied by a phase two uses back (the mbarrier only remembers one parity bit).
     const uint32_t step = p.nA < (uint32_t)NP ? p.nA : (uint32_t)NP;
-    uint32_t g = warp < step ? warp : total;
-    if (g < total) load_idx(g, idx_cur);
-    for (; g < total; g += step) {
-      if (g + step < total) load_idx(g + step, idx_nxt);
+    auto fill_stage = [&](uint32_t g, const int32_t (&idx_cur)[4]) {
       const Pos q = decode(g);
       const uint32_t sa = g % p.nA, pha = (g / p.nA) & 1u;
       const uint32_t c0 = q.mc * p.cps * BK + chunk * 8;   // first channel this lane copies
@@ -699,7 +699,6 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       const uint32_t dstA = sA + sa * p.a_stage_bytes;
 #pragma unroll
       for (int it = 0; it < S::kItersA; ++it) {
-        constexpr int dummy = 0; (void)dummy;
         const int slot = (it * S::kRowsPerInstr) / 32;
         const uint32_t row = it * S::kRowsPerInstr + sub_row;
         const int32_t src_row = __shfl_sync(0xffffffffu, idx_cur[slot], row & 31u);
@@ -709,8 +708,24 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         for (uint32_t s = 0; s < p.cps; ++s) cp_async16(dst + s * p.a_sub_bytes, src + s * BK, nbytes);
       }
       cp_async_mbar_arrive(fullA(sa));   // fires once this warp's copies for the stage landed
+    };
+    int32_t ring[kCpRing][4];
+    const uint32_t g0 = warp < step ? warp : total;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) idx_cur[i] = idx_nxt[i];
+    for (int d = 0; d < kCpRing; ++d) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ring[d][i] = -1;
+      if (g0 + d * step < total) load_idx(g0 + d * step, ring[d]);
+    }
+    for (uint32_t g = g0; g < total; g += kCpRing * step) {
+#pragma unroll
+      for (int d = 0; d < kCpRing; ++d) {
+        const uint32_t gg = g + d * step;
+        if (gg < total) {            // warp-uniform
+          fill_stage(gg, ring[d]);
+          if (gg + kCpRing * step < total) load_idx(gg + kCpRing * step, ring[d]);
+        }
+      }
     }
     cp_async_wait<0>();  // nothing of this thread may still be in flight at teardown
   } else if (warp < NP + kEpilogueWarps) {
