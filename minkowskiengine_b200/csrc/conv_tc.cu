@@ -58,29 +58,6 @@ struct TcParams {
   uint32_t out_ld;       // leading dimension (elements) of `out`
 };
 
-// cp.async.wait_group takes an immediate: dispatch the few depths we use.
-__device__ __forceinline__ void cp_async_wait_dyn(uint32_t n) {
-  switch (n) {
-    case 0: cp_async_wait<0>(); break;
-    case 1: cp_async_wait<1>(); break;
-    case 2: cp_async_wait<2>(); break;
-    case 3: cp_async_wait<3>(); break;
-    case 4: cp_async_wait<4>(); break;
-    case 5: cp_async_wait<5>(); break;
-    case 6: cp_async_wait<6>(); break;
-    case 7: cp_async_wait<7>(); break;
-    case 8: cp_async_wait<8>(); break;
-    case 9: cp_async_wait<9>(); break;
-    case 10: cp_async_wait<10>(); break;
-    case 11: cp_async_wait<11>(); break;
-    case 12: cp_async_wait<12>(); break;
-    case 13: cp_async_wait<13>(); break;
-    case 14: cp_async_wait<14>(); break;
-    case 15: cp_async_wait<15>(); break;
-    default: cp_async_wait<16>(); break;
-  }
-}
-
 template <int BK>
 struct Swz {
   static constexpr int kRowBytes = BK * 2;
@@ -166,48 +143,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams &p, uint32_t bar0, 
   }
 }
 
-// MMA issuer (one thread): consumes the A/B rings in order, accumulates in TMEM.
-template <typename T, int BK, int RT>
-__device__ __forceinline__ void mma_role(const TcParams &p, uint32_t sA, uint32_t sB, uint32_t bar0,
-                                         uint32_t tmem_base) {
-  using S = Swz<BK>;
-  constexpr uint32_t R = RT;
-  const uint32_t idesc = umma_idesc_f16(Fmt<T>::v, kTileM, p.c_cols, 0, 0);
-  uint32_t t = 0, sa = 0, pha = 0, sb = 0, phb = 0;
-  for (uint32_t st = blockIdx.x; st < p.n_super; st += gridDim.x, ++t) {
-    const uint32_t acc = t & 1u, par = (t >> 1) & 1u;
-    mbar_wait(bar_tempty(bar0, acc), par ^ 1u);
-    tc_fence_after();
-    for (uint32_t k = 0; k < p.K; ++k) {
-      for (uint32_t mc = 0; mc < p.n_macro; ++mc) {
-        mbar_wait(bar_fullB(bar0, sb), phb);
-        const uint32_t bbase = sB + sb * p.b_stage_bytes;
-#pragma unroll
-        for (int r = 0; r < RT; ++r) {
-          mbar_wait(bar_fullA(bar0, sa), pha);
-          tc_fence_after();
-          const uint32_t abase = sA + sa * p.a_stage_bytes;
-          const uint32_t d = tmem_base + (acc * R + r) * p.c_cols;
-          for (uint32_t s = 0; s < p.cps; ++s) {
-#pragma unroll
-            for (int j = 0; j < BK / 16; ++j) {
-              uint64_t da = umma_desc(abase + s * p.a_sub_bytes + j * 32, 16, S::kSbo, S::kLayout);
-              uint64_t db = umma_desc(bbase + s * p.b_sub_bytes + j * 32, 16, S::kSbo, S::kLayout);
-              umma_f16(d, da, db, idesc, (k | mc | s | (uint32_t)j) != 0u);
-            }
-          }
-          umma_commit(bar_emptyA(bar0, sa));
-          if (++sa == p.nA) { sa = 0; pha ^= 1u; }
-        }
-        umma_commit(bar_emptyB(bar0, sb));
-        if (++sb == p.nB) { sb = 0; phb ^= 1u; }
-      }
-    }
-    umma_commit(bar_tfull(bar0, acc));
-  }
-}
-
-// MMA issuer, lean version: the WHOLE warp runs the loop with warp-uniform state (ring
+// MMA issuer: the WHOLE warp runs the loop with warp-uniform state (ring
 // addresses advance by adds, descriptor words are 32-bit adds of compile-time offsets) and one
 // elected lane issues.  A single thread can retire only ~1 dependent instruction per 4-6 cycles,
 // so every instruction here is on the critical path of the tensor pipe (ncu: the first version,
@@ -326,13 +262,6 @@ __device__ __forceinline__ void wait_consumed(volatile uint32_t *ctr, uint32_t g
   }
   __syncwarp();
   __threadfence_block();
-}
-
-// Make the thread wait until the given loaded words have really arrived (their first use is
-// what blocks on the scoreboard).  Called BEFORE a ring slot is acquired: a slot must never be
-// held across a global-memory latency.
-__device__ __forceinline__ void force_arrival(uint32_t x) {
-  if (x == 0x9e3779b9u) asm volatile("nanosleep.u32 1;" ::: "memory");
 }
 
 __device__ __forceinline__ uint4 ldg128(const void *p) {
