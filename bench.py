@@ -74,6 +74,63 @@ def load_peaks():
             "source": "fallback"}
 
 
+class NvmlClockSampler:
+    """SM clock + clock-event reasons read through NVML (nvidia_ml_py) every 20 ms from a
+    thread, so that even a half-second timed region gets tens of samples.  `start()` returns
+    False when NVML is not usable; the caller then falls back to the nvidia-smi sampler."""
+    # nvmlClocksEventReason* bit masks (nvml.h)
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index=0, period_s=0.02):
+        self.index, self.period, self.sm, self.mask, self.mx = index, period_s, [], 0, None
+        self._stop = threading.Event()
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = None
+            try:   # CUDA_VISIBLE_DEVICES may renumber devices: match on the PCI address
+                import torch
+                pr = torch.cuda.get_device_properties(self.index)
+                bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+                self.h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            except Exception:
+                self.h = None
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self._sample()
+        except Exception:
+            return False
+        self.th = threading.Thread(target=self._loop, daemon=True)
+        self.th.start()
+        return True
+
+    def _sample(self):
+        self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+        get = getattr(self.nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            self.nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        self.mask |= int(get(self.h))
+
+    def _loop(self):
+        while not self._stop.wait(self.period):
+            try:
+                self._sample()
+            except Exception:
+                return
+
+    def stop(self):
+        self._stop.set()
+        self.th.join(timeout=2)
+        sm = sorted(self.sm[1:] or self.sm)      # the first sample predates the timed region
+        reasons = sorted(nm for bit, nm in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.mx, "reasons": reasons,
+                "samples": len(sm), "source": "nvml"}
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -285,11 +342,19 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
-    sampler = ClockSampler(local_rank)
+    sampler = None
     if rank == 0:
-        sampler.start()
+        sampler = NvmlClockSampler(local_rank)
+        if not sampler.start():
+            sampler = ClockSampler(local_rank)
+            sampler.start()
     ms, launches = timed(step_resident, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
+    if rank == 0:
+        try:
+            clocks = sampler.stop()
+        except Exception as exc:                      # never lose the measurement to the sampler
+            clocks = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"sampler failed: {exc}"]}
     step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
 
