@@ -15,7 +15,7 @@ import string
 import torch
 
 from . import _lib
-from .enums import (ConvolutionMode, MinkowskiAlgorithm, PoolingMode, RegionType)
+from .enums import MinkowskiAlgorithm, PoolingMode, RegionType
 from .kernel_generator import region_offsets
 
 ERROR_MAP_NOT_FOUND = "CoordinateMap not found"  # reference: src/errors.hpp:33

@@ -6,7 +6,7 @@ from . import backend as _C
 from .backend import CoordinateMapKey
 from .common import MinkowskiModuleBase
 from .coordinate_manager import CoordinateManager
-from .enums import PoolingMode, RegionType
+from .enums import PoolingMode
 from .kernel_generator import KernelGenerator
 from .sparse_tensor import SparseTensor, _get_coordinate_map_key
 

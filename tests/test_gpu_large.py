@@ -8,7 +8,6 @@ numpy oracle would take too long:
   * convolution linearity and an fp32 torch restatement on the device (tensor-core bf16 path,
     cfg1: 100k coords, 64 -> 128, k=3, s=2), dgrad/wgrad adjointness <dY, conv(X)> identities;
   * 4-D (cfg4: 200k draws, K = 81) hashing stress against a sort-based torch lookup."""
-import numpy as np
 import pytest
 import torch
 

@@ -4,11 +4,10 @@ Parity definition for reduced-precision inputs (SURVEY.md §8a notes): the oracl
 SAME bf16/fp16-rounded features and weights; with fp32 accumulation the CUDA result then
 differs only by summation order (asserted 2e-5 relative with fp32 output) plus one final
 rounding when the output is stored in bf16/fp16 (2^-8 relative, asserted 6e-3 of max)."""
-import numpy as np
 import pytest
 import torch
 
-from helpers import kmap_lists, rel_err, unique_cloud
+from helpers import rel_err, unique_cloud
 from oracle import oracle_np as O
 
 pytestmark = pytest.mark.gpu

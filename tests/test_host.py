@@ -4,6 +4,7 @@ loudly (there is no fallback)."""
 import ctypes
 import os
 import re
+import sys
 
 import pytest
 import torch
@@ -132,3 +133,32 @@ def test_convert_sync_batchnorm_keeps_sync_holder():
     assert len(bns) == 2 and all(isinstance(m, ME.MinkowskiSyncBatchNorm) for m in bns)
     assert all(isinstance(m.bn, torch.nn.SyncBatchNorm) for m in bns)
     assert out[0].bn.weight is w0 and out[1][0].bn.num_features == 16
+
+
+def test_bench_nvml_clock_sampler_with_a_stub(monkeypatch):
+    """bench.py's NVML sampler: median SM clock of the samples taken inside the region, the
+    union of the clock-event reason bits, and a clean `False` when NVML is missing."""
+    import importlib.util
+    import time
+    import types
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    fake = types.ModuleType("pynvml")
+    fake.NVML_CLOCK_SM = 1
+    fake.nvmlInit = lambda: None
+    fake.nvmlDeviceGetHandleByIndex = lambda i: ("h", i)
+    fake.nvmlDeviceGetMaxClockInfo = lambda h, c: 1965
+    clocks = iter([1000] + [1950] * 1000)
+    fake.nvmlDeviceGetClockInfo = lambda h, c: next(clocks)
+    fake.nvmlDeviceGetCurrentClocksEventReasons = lambda h: 0x4 | 0x1     # power cap + idle bit
+    monkeypatch.setitem(sys.modules, "pynvml", fake)
+    s = bench.NvmlClockSampler(0, period_s=0.005)
+    assert s.start() is True
+    time.sleep(0.1)
+    out = s.stop()
+    assert out["sm_mhz"] == 1950.0 and out["sm_max_mhz"] == 1965.0 and out["samples"] >= 3
+    assert out["reasons"] == ["sw_power_cap"] and out["source"] == "nvml"
+    broken = types.ModuleType("pynvml")
+    monkeypatch.setitem(sys.modules, "pynvml", broken)       # no nvmlInit -> AttributeError
+    assert bench.NvmlClockSampler(0).start() is False

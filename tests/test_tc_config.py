@@ -1,10 +1,8 @@
 """Host-side launch configuration of the tcgen05 kernels (csrc/tc_config.h), checked on CPU:
 every channel shape MinkUNet14/34C/... can produce must get a pipeline (lag >= 1) that fits in
 the 227 KB of shared memory a CTA may use and 512 TMEM columns."""
-import itertools
 import os
 import subprocess
-import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
