@@ -98,10 +98,14 @@ __device__ __forceinline__ uint32_t bar_tfull(uint32_t b0, uint32_t i) { return 
 __device__ __forceinline__ uint32_t bar_tempty(uint32_t b0, uint32_t i) { return b0 + 8u * (4 * kMaxStages + 2 + i); }
 
 // Epilogue warps: accumulator (TMEM) -> registers -> converted 16-byte global stores.
-template <typename T, int RT>
+// EXP (experiments, see k_conv_rs): bit 1 = output stores carry an L2 evict-first policy.
+template <typename T, int RT, int EXP = 0>
 __device__ __forceinline__ void epilogue_role(const TcParams &p, uint32_t bar0, uint32_t tmem_base,
                                               uint32_t q, uint32_t lane) {
   constexpr uint32_t R = RT;
+  uint64_t pol_stream = 0;
+  if constexpr ((EXP & 2) != 0) pol_stream = l2_policy_evict_first();
+  (void)pol_stream;
   uint32_t t = 0;
   for (uint32_t st = blockIdx.x; st < p.n_super; st += gridDim.x, ++t) {
     const uint32_t acc = t & 1u, par = (t >> 1) & 1u;   // two accumulator sets
@@ -119,9 +123,14 @@ __device__ __forceinline__ void epilogue_role(const TcParams &p, uint32_t bar0, 
             float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) +
                                                      (size_t)row * p.out_ld + c);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                   __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            for (int i = 0; i < 4; ++i) {
+              if constexpr ((EXP & 2) != 0)
+                stg128_hint(dst + i, make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]),
+                            pol_stream);
+              else
+                dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                     __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            }
           } else {
             uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<T *>(p.out) +
                                                    (size_t)row * p.out_ld + c);
@@ -132,7 +141,8 @@ __device__ __forceinline__ void epilogue_role(const TcParams &p, uint32_t bar0, 
               w.y = pack2<T>(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
               w.z = pack2<T>(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
               w.w = pack2<T>(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
-              dst[i] = w;
+              if constexpr ((EXP & 2) != 0) stg128_hint(dst + i, w, pol_stream);
+              else dst[i] = w;
             }
           }
         }
@@ -274,12 +284,20 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-template <typename T, int BK, int RT, int CPS>
+// EXP selects experiments prepared at the end of round 1 (MEB200_RS_EXP, only instantiated for
+// the 96-channel shape <bf16, 32, 2, 3>; EXP = 0 is the measured kernel, bit for bit):
+//   bit 0: per-slot dirty-row masks - a stage is zeroed once at kernel start, afterwards only
+//          rows that held data in the slot's previous use and hold none now are cleared
+//          (instead of storing the full 24 KB of zeros per stage);
+//   bit 1: the streamed data (neighbour table, output rows) carries an L2 evict-first policy;
+//   bit 2: the gathered feature rows carry an L2 evict-last policy.
+template <typename T, int BK, int RT, int CPS, int EXP = 0>
 __global__ void __launch_bounds__(kRsThreads, 1)
 k_conv_rs(const __grid_constant__ CUtensorMap mapB, const TcParams p) {
   using S = Swz<BK>;
   constexpr int NP = kRsProducerWarps;
   constexpr uint32_t R = RT;
+  constexpr bool kDirty = (EXP & 1) != 0, kStreamHint = (EXP & 2) != 0, kKeepHint = (EXP & 4) != 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -293,9 +311,18 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapB, const TcParams p) {
   uint2 *scratch_all = reinterpret_cast<uint2 *>(tail + tc::kBarBytes);
   volatile uint32_t *consumed = reinterpret_cast<volatile uint32_t *>(
       tail + tc::kBarBytes + kRsProducerWarps * kTileM * 8);
+  // kDirty: [nA][4] row masks (bit = the row holds data), after the scratch area proper
+  uint32_t *dirty = reinterpret_cast<uint32_t *>(tail + tc::kBarBytes + tc::kRsScratchBytes);
+  (void)dirty;
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  if constexpr (kDirty) {
+    for (uint32_t off = threadIdx.x * 16; off < p.nA * p.a_stage_bytes; off += kRsThreads * 16)
+      sts128(sA + off, make_uint4(0, 0, 0, 0));
+    for (uint32_t i = threadIdx.x; i < p.nA * 4; i += kRsThreads) dirty[i] = 0;
+    fence_proxy_async();   // the zeros must be visible to the tensor core's reads
+  }
   if (threadIdx.x == 0) {
     for (uint32_t i = 0; i < p.nA; ++i) { mbar_init(bar_fullA(bar0, i), 1); mbar_init(bar_emptyA(bar0, i), 1); }
     for (uint32_t i = 0; i < p.nB; ++i) { mbar_init(bar_fullB(bar0, i), 1); mbar_init(bar_emptyB(bar0, i), 1); }
@@ -335,6 +362,10 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapB, const TcParams p) {
       return q;
     };
     int32_t idx_cur[4], idx_nxt[4];
+    uint64_t pol_stream = 0, pol_keep = 0;
+    if constexpr (kStreamHint) pol_stream = l2_policy_evict_first();
+    if constexpr (kKeepHint) pol_keep = l2_policy_evict_last();
+    (void)pol_stream; (void)pol_keep;
     auto load_idx = [&](uint32_t g, int32_t (&dst)[4]) {
       const Pos q = decode(g);
       const int32_t *nbr_k = p.nbr + (size_t)q.k * p.n_rows;
@@ -342,7 +373,8 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapB, const TcParams p) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const uint32_t grow = row0 + i * 32;
-        dst[i] = (grow < p.n_rows) ? __ldg(nbr_k + grow) : -1;
+        if constexpr (kStreamHint) dst[i] = (grow < p.n_rows) ? ldg32_hint(nbr_k + grow, pol_stream) : -1;
+        else dst[i] = (grow < p.n_rows) ? __ldg(nbr_k + grow) : -1;
       }
     };
     constexpr uint32_t step = NP;   // every producer warp takes stages (see release_role)
@@ -357,13 +389,16 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapB, const TcParams p) {
       const uint32_t c0 = q.mc * p.cps * BK;
       // ---- compact the valid rows of this stage into the warp's scratch list ----------
       uint32_t V = 0;
+      uint32_t mnew[4];   // kDirty: which tile rows of this stage hold data
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const bool ok = idx_cur[i] >= 0;
         const uint32_t m = __ballot_sync(0xffffffffu, ok);
         if (ok) scratch[V + __popc(m & lane_lt)] = make_uint2((uint32_t)idx_cur[i], (uint32_t)(i * 32 + lane));
         V += __popc(m);
+        mnew[i] = m;
       }
+      (void)mnew;
       __syncwarp();
       const uint32_t dstA = sA + sa * p.a_stage_bytes;
       bool slot_ready = false;
@@ -382,7 +417,10 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapB, const TcParams p) {
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(srow) : "r"(scratch_s + e * 8));
             const T *src = srcA + (size_t)srow * p.c_red;
 #pragma unroll
-            for (int sc = 0; sc < CPS; ++sc) v[ri * CPS + sc] = ldg128(src + sc * BK);
+            for (int sc = 0; sc < CPS; ++sc) {
+              if constexpr (kKeepHint) v[ri * CPS + sc] = ldg128_hint(src + sc * BK, pol_keep);
+              else v[ri * CPS + sc] = ldg128(src + sc * BK);
+            }
           } else {
 #pragma unroll
             for (int sc = 0; sc < CPS; ++sc) v[ri * CPS + sc] = make_uint4(0, 0, 0, 0);
@@ -402,8 +440,32 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapB, const TcParams p) {
               tma_load_2d(dstB + sbi * p.b_sub_bytes, &mapB, (int32_t)(c0 + sbi * BK), brow,
                           bar_fullB(bar0, sb));
           }
-          for (uint32_t off = lane * 16; off < p.a_stage_bytes; off += 512)
-            sts128(dstA + off, make_uint4(0, 0, 0, 0));
+          if constexpr (kDirty) {
+            // clear only rows that were written by the slot's previous user and are empty now
+            constexpr uint32_t kLanesPerRow = CPS * S::kChunks;      // 16-byte pieces of a row
+            constexpr uint32_t kRowsPerPass = 32 / kLanesPerRow;
+            const uint32_t sel = lane / kLanesPerRow, piece = lane % kLanesPerRow;
+            const uint32_t psc = piece / S::kChunks, pchunk = piece % S::kChunks;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint32_t z = dirty[sa * 4 + i] & ~mnew[i];
+              while (z) {                                   // warp-uniform
+                uint32_t zz = z;                            // this lane group's row: the
+                for (uint32_t j = 0; j < sel; ++j) zz &= zz - 1;   // sel-th lowest set bit
+                if (sel < kRowsPerPass && zz) {
+                  const uint32_t row = (uint32_t)i * 32 + (uint32_t)__ffs(zz) - 1u;
+                  sts128(dstA + psc * p.a_sub_bytes + S::offset(row, pchunk), make_uint4(0, 0, 0, 0));
+                }
+                for (uint32_t j = 0; j < kRowsPerPass && z; ++j) z &= z - 1;
+              }
+            }
+            __syncwarp();
+            if (lane < 4)
+              dirty[sa * 4 + lane] = lane == 0 ? mnew[0] : (lane == 1 ? mnew[1] : (lane == 2 ? mnew[2] : mnew[3]));
+          } else {
+            for (uint32_t off = lane * 16; off < p.a_stage_bytes; off += 512)
+              sts128(dstA + off, make_uint4(0, 0, 0, 0));
+          }
           __syncwarp();
           slot_ready = true;
         }
@@ -427,7 +489,7 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapB, const TcParams p) {
       for (int i = 0; i < 4; ++i) idx_cur[i] = idx_nxt[i];
     }
   } else if (warp < NP + kEpilogueWarps) {
-    epilogue_role<T, RT>(p, bar0, tmem_base, warp & 3u, lane);
+    epilogue_role<T, RT, EXP>(p, bar0, tmem_base, warp & 3u, lane);
   } else if (warp == NP + kEpilogueWarps) {
     mma_role_fast<T, BK, RT, CPS>(p, sA, sB, bar0, tmem_base);   // whole warp, one lane issues
   } else if (lane == 0) {
@@ -825,10 +887,10 @@ static int gather_mode() {
   return v;
 }
 
-template <typename T, int BK, int RT, int CPS>
+template <typename T, int BK, int RT, int CPS, int EXP = 0>
 static int launch_rs(const CUtensorMap &mB, const TcParams &p, size_t smem_bytes, unsigned grid,
                      cudaStream_t stream) {
-  auto kern = k_conv_rs<T, BK, RT, CPS>;
+  auto kern = k_conv_rs<T, BK, RT, CPS, EXP>;
   static bool configured = false;
   if (!configured) {
     MEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -927,8 +989,20 @@ static int launch_tc_slice(const void *A, int dtype, uint32_t n_a, uint32_t c_re
   const bool aligned = (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
                        (reinterpret_cast<uintptr_t>(Wb_full) & 15) == 0;
   const int mode = (n_a > 0 && aligned) ? gather_mode() : 0;
+  // MEB200_RS_EXP = 1 | 2 | 6 | 7: experiments inside k_conv_rs (see the kernel), compiled for
+  // the 96-channel bf16 shape only; anything else runs the measured kernel.
+  int rs_exp = 0;
+  if (const char *e = getenv("MEB200_RS_EXP")) rs_exp = atoi(e);
+  if (!(rs_exp == 1 || rs_exp == 2 || rs_exp == 6 || rs_exp == 7) || dtype != MEB200_BF16 || mode != 2)
+    rs_exp = 0;
+  const uint32_t rs_extra = (rs_exp & 1) ? 512u : 0u;   // dirty-row masks behind the scratch area
   tc::FwdCfg cfg = tc::fwd_config(c_reduce, c_cols, n_rows, (uint32_t)max_stage_kb * 1024,
-                                  mode == 2 ? tc::kRsScratchBytes : 0);
+                                  mode == 2 ? tc::kRsScratchBytes + rs_extra : 0);
+  if (rs_exp != 0 && !(cfg.bk == 32 && cfg.R == 2 && cfg.cps == 3)) {
+    rs_exp = 0;
+    if (rs_extra)
+      cfg = tc::fwd_config(c_reduce, c_cols, n_rows, (uint32_t)max_stage_kb * 1024, tc::kRsScratchBytes);
+  }
   if (mode == 2 && !((cfg.bk == 64 && cfg.cps <= 2) || (cfg.bk != 64 && (cfg.cps == 1 || cfg.cps == 3))))
     cfg = tc::fwd_config(c_reduce, c_cols, n_rows, 1, tc::kRsScratchBytes);   // one chunk per stage
   if (cfg.bk == 0 || cfg.pipe.lag < 1) {
@@ -957,6 +1031,13 @@ static int launch_tc_slice(const void *A, int dtype, uint32_t n_a, uint32_t c_re
     }
   }
   if (mode == 2) {
+    switch (rs_exp) {
+      case 1: return launch_rs<__nv_bfloat16, 32, 2, 3, 1>(mB, p, smem_bytes, grid, stream);
+      case 2: return launch_rs<__nv_bfloat16, 32, 2, 3, 2>(mB, p, smem_bytes, grid, stream);
+      case 6: return launch_rs<__nv_bfloat16, 32, 2, 3, 6>(mB, p, smem_bytes, grid, stream);
+      case 7: return launch_rs<__nv_bfloat16, 32, 2, 3, 7>(mB, p, smem_bytes, grid, stream);
+      default: break;
+    }
     if (dtype == MEB200_BF16)
       return launch_rs_bk_r<__nv_bfloat16>(bk, R, cfg.cps, mB, p, smem_bytes, grid, stream);
     return launch_rs_bk_r<__half>(bk, R, cfg.cps, mB, p, smem_bytes, grid, stream);

@@ -165,6 +165,35 @@ __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_by
   return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
 }
 
+// ---- L2 eviction-priority hints (createpolicy + .L2::cache_hint) -----------------------
+// The plain `.L2::evict_*` qualifiers exist only for 256-bit vector accesses on sm_100; any
+// width works through a policy operand.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint4 ldg128_hint(const void *p, uint64_t pol) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ int32_t ldg32_hint(const int32_t *p, uint64_t pol) {
+  int32_t v;
+  asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void stg128_hint(void *p, uint4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
+
 // ---- UMMA descriptors -------------------------------------------------------------
 // Shared-memory matrix descriptor, sm_100 format (version 1): start address, leading /
 // stride byte offsets in 16-byte units, swizzle mode in bits [61,64).
