@@ -185,6 +185,21 @@ int meb200_bn_backward_apply(const void *dy, const void *x, int dtype, uint32_t 
                              const double *sums, double count, const double *d_count, void *dx,
                              void *stream);
 
+/* ---- synchronised batch norm: statistics exchange over NVLink peer memory ----------------
+ * Replaces the per-layer NCCL all-reduce of torch.nn.SyncBatchNorm (reference:
+ * MinkowskiEngine/MinkowskiNormalization.py:101-192, examples/multigpu_ddp.py:91-95) by one
+ * single-CTA kernel on the compute stream.  Every rank owns a buffer in symmetric memory with
+ * the same layout: bytes [0, 1024) hold uint32 flags (flag[r] = last call whose slot of rank r
+ * is complete), slots follow.  `peer_bases_dev` is a DEVICE array of `world` device pointers,
+ * entry r = base of rank r's buffer as mapped into this process.  The kernel publishes `seq`
+ * to every peer, waits for every peer's `seq`, then writes out[i] = sum over ranks (in rank
+ * order: bitwise identical on all ranks) of the n doubles at `slot_offset_bytes`.  `seq` must
+ * increase by one per call on every rank; consecutive calls must use different slots (a rank
+ * can be at most one call ahead of its slowest peer).  Flags must be zero before the first call. */
+int meb200_peer_allreduce_f64(const void *peer_bases_dev, uint64_t slot_offset_bytes, uint32_t n,
+                              uint32_t seq, uint32_t rank, uint32_t world, double *out,
+                              void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,15 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 
+void set_arg_error(const char *file, int line, const char *cond, const char *fmt, ...) {
+  char msg[384];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(msg, sizeof(msg), fmt, ap);
+  va_end(ap);
+  set_error("%s:%d invalid argument (%s): %s", file, line, cond, msg);
+}
+
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 void count_tc_launch() { g_tc_launches.fetch_add(1, std::memory_order_relaxed); }
 uint64_t tc_launches() { return g_tc_launches.load(std::memory_order_relaxed); }

@@ -18,11 +18,14 @@ void count_launch(unsigned n = 1);
 void count_tc_launch();
 uint64_t tc_launches();
 
+void set_arg_error(const char *file, int line, const char *cond, const char *fmt, ...);
+
+// MEB_CHECK_ARG(cond, "message with %u", value): message arguments are formatted first, the
+// location and the failed condition are prepended by set_arg_error.
 #define MEB_CHECK_ARG(cond, ...)                                                         \
   do {                                                                                   \
     if (!(cond)) {                                                                       \
-      ::meb200::set_error("%s:%d invalid argument (%s): " __VA_ARGS__, __FILE__,         \
-                          __LINE__, #cond);                                              \
+      ::meb200::set_arg_error(__FILE__, __LINE__, #cond, __VA_ARGS__);                   \
       return MEB200_ERR_INVALID;                                                         \
     }                                                                                    \
   } while (0)

@@ -19,6 +19,7 @@
 // ring in TMEM (acc_stages x R accumulators of c_cols columns).
 #include <cuda.h>
 #include <stdlib.h>
+#include <type_traits>
 #include <string.h>
 
 #include "conv_tc.cuh"
@@ -57,6 +58,19 @@ struct TcParams {
   uint32_t wb_k_stride;  // elements between consecutive offsets in Wb
   uint32_t out_ld;       // leading dimension (elements) of `out`
 };
+
+// Runs f(integral_constant<int, d>) for the run-time d in [0, N): a warp-uniform compare chain
+// that lets a REGISTER array (a prefetch ring) be addressed by a run-time position without
+// unrolling the caller by N or demoting the array to local memory.
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_switch(uint32_t d, F &&f) {
+  if constexpr (I + 1 >= N) {
+    f(std::integral_constant<int, I>{});
+  } else {
+    if (d == (uint32_t)I) f(std::integral_constant<int, I>{});
+    else static_switch<I + 1, N>(d, f);
+  }
+}
 
 template <int BK>
 struct Swz {
@@ -652,7 +666,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     };
     // lane l holds the neighbour rows of tile rows l, l+32, l+64, l+96 (coalesced table reads);
     // the copy loop pulls them out with shuffles.  The indices of the warp's next kCpRing stages
-    // sit in a statically indexed register ring (the stage loop is unrolled by the ring depth):
+    // sit in a register ring addressed through static_switch:
     // with one stage of look-ahead every stage waited out most of an index-load latency (the
     // same stall profiles/r1_ncu_k_wgrad_tc_block8_96x96.txt shows for the wgrad producers).
     constexpr int kCpRing = 4;
@@ -708,15 +722,18 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       for (int i = 0; i < 4; ++i) ring[d][i] = -1;
       if (g0 + d * step < total) load_idx(g0 + d * step, ring[d]);
     }
-    for (uint32_t g = g0; g < total; g += kCpRing * step) {
+    uint32_t d = 0;
+    for (uint32_t g = g0; g < total; g += step) {
+      int32_t idx_cur[4];
+      static_switch<0, kCpRing>(d, [&](auto D) {      // waits for ring[d]'s loads only
 #pragma unroll
-      for (int d = 0; d < kCpRing; ++d) {
-        const uint32_t gg = g + d * step;
-        if (gg < total) {            // warp-uniform
-          fill_stage(gg, ring[d]);
-          if (gg + kCpRing * step < total) load_idx(gg + kCpRing * step, ring[d]);
-        }
-      }
+        for (int i = 0; i < 4; ++i) idx_cur[i] = ring[decltype(D)::value][i];
+      });
+      fill_stage(g, idx_cur);
+      const uint32_t gn = g + kCpRing * step;
+      if (gn < total)
+        static_switch<0, kCpRing>(d, [&](auto D) { load_idx(gn, ring[decltype(D)::value]); });
+      if (++d == (uint32_t)kCpRing) d = 0;
     }
     cp_async_wait<0>();  // nothing of this thread may still be in flight at teardown
   } else if (warp < NP + kEpilogueWarps) {
@@ -1229,8 +1246,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(const WgParams p) {
         }
       }
     } else {
-      // register ring of PF index sets, statically indexed (the loop is unrolled by PF): slot d
-      // is refilled with work item w + PF right after item w's copies were issued from it.
+      // register ring of PF index sets, addressed through static_switch: slot d is refilled with
+      // work item w + PF right after item w's copies were issued from it.
       int32_t ring[PF][kWgRows / 16];
       const uint32_t n_work = n_chunks * G;
       uint32_t pc = 0, pkk = 0, c = 0, kk = 0;
@@ -1241,16 +1258,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(const WgParams p) {
         if (pc < n_chunks) load_idx(pc, pkk, ring[d]);
         if (++pkk == G) { pkk = 0; ++pc; }
       }
-      for (uint32_t w0 = 0; w0 < n_work; w0 += PF) {
+      uint32_t d = 0;
+      for (uint32_t w = 0; w < n_work; ++w) {
+        int32_t idx_cur[kWgRows / 16];
+        static_switch<0, PF>(d, [&](auto D) {       // waits for ring[d]'s loads only
 #pragma unroll
-        for (int d = 0; d < PF; ++d) {
-          if (w0 + d < n_work) {
-            issue_stage(c, kk, ring[d]);
-            if (pc < n_chunks) load_idx(pc, pkk, ring[d]);
-            if (++pkk == G) { pkk = 0; ++pc; }
-            if (++kk == G) { kk = 0; ++c; }
-          }
-        }
+          for (int it = 0; it < kWgRows / 16; ++it) idx_cur[it] = ring[decltype(D)::value][it];
+        });
+        issue_stage(c, kk, idx_cur);
+        if (pc < n_chunks)
+          static_switch<0, PF>(d, [&](auto D) { load_idx(pc, pkk, ring[decltype(D)::value]); });
+        if (++pkk == G) { pkk = 0; ++pc; }
+        if (++kk == G) { kk = 0; ++c; }
+        if (++d == (uint32_t)PF) d = 0;
       }
     }
     cp_async_wait<0>();

@@ -162,3 +162,19 @@ def test_bench_nvml_clock_sampler_with_a_stub(monkeypatch):
     broken = types.ModuleType("pynvml")
     monkeypatch.setitem(sys.modules, "pynvml", broken)       # no nvmlInit -> AttributeError
     assert bench.NvmlClockSampler(0).start() is False
+
+
+def test_argument_errors_carry_location_condition_and_values():
+    """Argument checks run before any CUDA call, so they can be exercised without a GPU: the
+    message names the source location, the failed condition and the offending value."""
+    from minkowskiengine_b200 import _lib
+    lib = _lib.load()
+    ts = (ctypes.c_int32 * 3)(2, 2, 2)
+    rc = lib.meb200_stride_coords(None, 5, 1, ts, None, None)       # ncols = 1 is invalid
+    assert rc != 0
+    msg = lib.meb200_last_error().decode()
+    assert "coords.cu" in msg and "ncols >= 2" in msg and msg.rstrip().endswith("ncols=1"), msg
+    rc = lib.meb200_peer_allreduce_f64(None, 1024, 4, 1, 0, 2, None, None)
+    assert rc != 0 and "null buffer" in lib.meb200_last_error().decode()
+    with pytest.raises(_lib.BackendError):
+        _lib.check(rc)
