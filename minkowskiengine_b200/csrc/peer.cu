@@ -36,6 +36,13 @@ __device__ __forceinline__ double ld_relaxed_sys_f64(const double *p) {
   return v;
 }
 
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr uint64_t kPeerTimeoutNs = 30ull * 1000 * 1000 * 1000;   // 30 s
+
 __global__ void __launch_bounds__(256)
 k_peer_allreduce_f64(uint8_t *const *__restrict__ bases, uint64_t slot_offset, uint32_t n,
                      uint32_t seq, uint32_t rank, uint32_t world, double *__restrict__ out) {
@@ -46,7 +53,12 @@ k_peer_allreduce_f64(uint8_t *const *__restrict__ bases, uint64_t slot_offset, u
   if (tid < world) {
     st_release_sys(reinterpret_cast<uint32_t *>(bases[tid]) + rank, seq);       // tell peer `tid`
     const uint32_t *mine = reinterpret_cast<const uint32_t *>(bases[rank]) + tid;
-    while ((int32_t)(ld_acquire_sys(mine) - seq) < 0) __nanosleep(100);         // hear from it
+    const uint64_t t0 = globaltimer_ns();
+    while ((int32_t)(ld_acquire_sys(mine) - seq) < 0) {                         // hear from it
+      __nanosleep(100);
+      // a peer that died or skipped the call must not hang this GPU for ever: fail loudly
+      if (globaltimer_ns() - t0 > kPeerTimeoutNs) __trap();
+    }
   }
   __syncthreads();
   for (uint32_t i = tid; i < n; i += blockDim.x) {

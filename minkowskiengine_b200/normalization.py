@@ -9,6 +9,10 @@ normalisation, unbiased for the running estimate, momentum update, per-channel a
 synchronised variant all-reduces (sum, sum of squares, count) forward and (sum dy, sum dy*xhat)
 backward over the process group, exactly the exchange torch.nn.SyncBatchNorm performs.
 `MEB200_TORCH_BN=1` routes everything through torch's own kernels (A/B comparisons).
+`MEB200_SYNCBN_PEER=1` (experimental, written at the end of round 1 and not yet run on GPUs)
+replaces the two NCCL all-reduces per layer by libmeb200's one-shot exchange over NVLink peer
+memory (`meb200_peer_allreduce_f64`, csrc/peer.cu): one single-CTA kernel on the compute stream,
+no NCCL launch and no cross-stream hand-off.
 """
 import os
 
@@ -19,6 +23,49 @@ from . import _lib
 from .sparse_tensor import SparseTensor
 
 _USE_TORCH = os.environ.get("MEB200_TORCH_BN", "0") not in ("", "0")
+_USE_PEER = os.environ.get("MEB200_SYNCBN_PEER", "0") not in ("", "0")
+
+
+class _PeerExchange:
+    """Symmetric-memory buffer of one (process group, device) for the statistics exchange.
+    Layout (include/meb200.h, meb200_peer_allreduce_f64): 1024 bytes of flags, then SLOTS
+    rotating slots of SLOT_DOUBLES fp64 each; `seq` counts the exchanges (identical on all ranks
+    because every rank runs the same layers in the same order)."""
+    SLOTS = 4
+    SLOT_DOUBLES = 2 * 2048 + 8
+    _cache = {}
+
+    @classmethod
+    def get(cls, group, device):
+        key = (id(group), device.index)
+        if key not in cls._cache:
+            cls._cache[key] = cls(group, device)
+        return cls._cache[key]
+
+    def __init__(self, group, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.world = torch.distributed.get_world_size(group)
+        self.rank = torch.distributed.get_rank(group)
+        nbytes = 1024 + self.SLOTS * self.SLOT_DOUBLES * 8
+        self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        torch.cuda.synchronize(device)
+        torch.distributed.barrier(group)        # every rank's flags are zero before the first call
+        self.bases_dev = int(self.handle.buffer_ptrs_dev)   # device array of the ranks' bases
+        self.seq = 0
+
+    def next_slot(self, n):
+        """-> (byte offset of the slot, fp64 view of its first n entries) for the next exchange."""
+        assert n <= self.SLOT_DOUBLES
+        self.seq = self.seq + 1 if self.seq < 0x7FFFFFFF else 1
+        off = 1024 + (self.seq % self.SLOTS) * self.SLOT_DOUBLES * 8
+        return off, self.buf[off:off + 8 * n].view(torch.float64)
+
+    def allreduce(self, off, n, out):
+        lib = _lib.load()
+        _lib.check(lib.meb200_peer_allreduce_f64(self.bases_dev, off, n, self.seq, self.rank,
+                                                 self.world, _lib.ptr(out), _lib.current_stream()))
 
 
 class _BatchNormFunction(torch.autograd.Function):
@@ -32,12 +79,21 @@ class _BatchNormFunction(torch.autograd.Function):
         dev = x.device
         w32 = None if weight is None else weight.detach().float().contiguous()
         b32 = None if bias is None else bias.detach().float().contiguous()
-        sums = torch.empty(2 * C + 1, dtype=torch.float64, device=dev)
+        peer = _PeerExchange.get(group, dev) if (group is not None and _USE_PEER) else None
+        if peer is not None:
+            off, sums = peer.next_slot(2 * C + 1)      # statistics land in symmetric memory
+        else:
+            sums = torch.empty(2 * C + 1, dtype=torch.float64, device=dev)
         _lib.check(lib.meb200_bn_stats(_lib.ptr(x), code, n, C, _lib.ptr(sums), stream))
         d_count = None
         if group is not None:
             sums[2 * C] = float(n)
-            torch.distributed.all_reduce(sums, group=group)
+            if peer is not None:
+                total = torch.empty(2 * C + 1, dtype=torch.float64, device=dev)
+                peer.allreduce(off, 2 * C + 1, total)
+                sums = total
+            else:
+                torch.distributed.all_reduce(sums, group=group)
             d_count = sums[2 * C:]
         mean = torch.empty(C, dtype=torch.float32, device=dev)
         invstd = torch.empty(C, dtype=torch.float32, device=dev)
@@ -64,16 +120,24 @@ class _BatchNormFunction(torch.autograd.Function):
         n, C = x.shape
         code = _lib.dtype_code(x.dtype)
         stream = _lib.current_stream()
-        gs = torch.empty(2 * C, dtype=torch.float64, device=x.device)
+        peer = _PeerExchange.get(ctx.group, x.device) if (ctx.group is not None and _USE_PEER) \
+            else None
+        if peer is not None:
+            off, gs = peer.next_slot(2 * C)
+        else:
+            gs = torch.empty(2 * C, dtype=torch.float64, device=x.device)
         _lib.check(lib.meb200_bn_backward_reduce(_lib.ptr(dy), _lib.ptr(x), code, n, C,
                                                  _lib.ptr(mean), _lib.ptr(invstd), _lib.ptr(gs),
                                                  stream))
         grad_w = grad_b = None
         if ctx.has_affine:   # local sums; DDP averages parameter gradients across ranks
-            grad_b = gs[:C].to(ctx.param_dtype)
-            grad_w = gs[C:].to(ctx.param_dtype)
-        if ctx.group is not None:
-            gs = gs.clone() if ctx.has_affine else gs
+            grad_b = gs[:C].to(ctx.param_dtype, copy=True)
+            grad_w = gs[C:].to(ctx.param_dtype, copy=True)
+        if peer is not None:
+            total = torch.empty(2 * C, dtype=torch.float64, device=x.device)
+            peer.allreduce(off, 2 * C, total)
+            gs = total
+        elif ctx.group is not None:
             torch.distributed.all_reduce(gs, group=ctx.group)
         dx = torch.empty_like(x)
         _lib.check(lib.meb200_bn_backward_apply(
