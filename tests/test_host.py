@@ -178,3 +178,43 @@ def test_argument_errors_carry_location_condition_and_values():
     assert rc != 0 and "null buffer" in lib.meb200_last_error().decode()
     with pytest.raises(_lib.BackendError):
         _lib.check(rc)
+
+
+def test_batchnorm_host_path_runs_against_a_stub_library(monkeypatch):
+    """Drives `_BatchNormFunction` forward + backward (the single-GPU path and the NCCL-style
+    synchronised path with a fake process group) with the native library replaced by a recorder:
+    checks the call sequence and argument plumbing of the Python host, not the kernels."""
+    import minkowskiengine_b200 as ME
+    from minkowskiengine_b200 import _lib, normalization as N
+
+    calls = []
+
+    class Stub:
+        def __getattr__(self, name):
+            def fn(*args):
+                calls.append((name, args))
+                return 0
+            return fn
+
+    monkeypatch.setattr(_lib, "load", lambda: Stub())
+    monkeypatch.setattr(_lib, "current_stream", lambda: None)
+    x = torch.randn(10, 16, requires_grad=True)
+    w, b = torch.ones(16, requires_grad=True), torch.zeros(16, requires_grad=True)
+    rm, rv = torch.zeros(16), torch.ones(16)
+    y = N._BatchNormFunction.apply(x, w, b, rm, rv, 0.1, 1e-5, None)
+    y.sum().backward()
+    names = [c[0] for c in calls]
+    assert names == ["meb200_bn_stats", "meb200_bn_finalize", "meb200_bn_apply",
+                     "meb200_bn_backward_reduce", "meb200_bn_backward_apply"]
+    assert calls[1][1][2] is None and calls[4][1][10] is None        # no device-side count
+    assert x.grad.shape == x.shape and w.grad.shape == (16,) and b.grad.shape == (16,)
+    # synchronised: the count travels with the sums and is read on the device
+    calls.clear()
+    reduced = []
+    monkeypatch.setattr(torch.distributed, "all_reduce", lambda t, group=None: reduced.append(t.numel()))
+    x2 = torch.randn(10, 16, requires_grad=True)
+    y2 = N._BatchNormFunction.apply(x2, w, b, rm, rv, 0.1, 1e-5, object())
+    y2.sum().backward()
+    assert reduced == [2 * 16 + 1, 2 * 16]
+    assert calls[1][1][2] is not None and calls[4][1][10] is not None
+    assert isinstance(ME.MinkowskiSyncBatchNorm(16).bn, torch.nn.SyncBatchNorm)
