@@ -57,6 +57,9 @@ struct TcParams {
   uint32_t lag;          // cp.async groups each producer thread keeps in flight
   uint32_t wb_k_stride;  // elements between consecutive offsets in Wb
   uint32_t out_ld;       // leading dimension (elements) of `out`
+  // EXP bit 3 (ordered tiles): output row of tile row j when the tiles walk the rows in another
+  // order than the tensor stores them (nbr is then indexed by tile row); nullptr otherwise
+  const int32_t *row_ids;
 };
 
 // Runs f(integral_constant<int, d>) for the run-time d in [0, N): a warp-uniform compare chain
@@ -127,6 +130,10 @@ __device__ __forceinline__ void epilogue_role(const TcParams &p, uint32_t bar0, 
     tc_fence_after();
     for (uint32_t r = 0; r < R; ++r) {
       const uint32_t row = (st * R + r) * kTileM + q * 32 + lane;
+      uint32_t orow = row;       // where the row lives in the output tensor
+      if constexpr ((EXP & 8) != 0) {
+        if (row < p.n_rows) orow = (uint32_t)__ldg(p.row_ids + row);
+      }
       const uint32_t col0 = (acc * R + r) * p.c_cols;
       for (uint32_t c = 0; c < p.c_cols; c += 16) {
         uint32_t v[16];
@@ -135,7 +142,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams &p, uint32_t bar0, 
         if (row < p.n_rows) {
           if (p.out_f32) {
             float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) +
-                                                     (size_t)row * p.out_ld + c);
+                                                     (size_t)orow * p.out_ld + c);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               if constexpr ((EXP & 2) != 0)
@@ -147,7 +154,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams &p, uint32_t bar0, 
             }
           } else {
             uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<T *>(p.out) +
-                                                   (size_t)row * p.out_ld + c);
+                                                   (size_t)orow * p.out_ld + c);
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
               uint4 w;
@@ -294,6 +301,14 @@ __device__ __forceinline__ uint4 ldg128(const void *p) {
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
+// L1-allocating variant: with spatially ordered tiles a CTA gathers the same row for several
+// offsets, so the copy in L1 is worth keeping (EXP bit 3).
+__device__ __forceinline__ uint4 ldg128_l1(const void *p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -304,7 +319,11 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
 //          rows that held data in the slot's previous use and hold none now are cleared
 //          (instead of storing the full 24 KB of zeros per stage);
 //   bit 1: the streamed data (neighbour table, output rows) carries an L2 evict-first policy;
-//   bit 2: the gathered feature rows carry an L2 evict-last policy.
+//   bit 2: the gathered feature rows carry an L2 evict-last policy;
+//   bit 3: ordered tiles - the tiles walk the rows in a spatially coherent order (p.nbr is
+//          indexed by tile row, the epilogue stores to p.row_ids[row]) and the gathers allocate
+//          in L1, where a tile's ~5x re-reads of the same source rows can hit
+//          (meb200_conv_forward_ordered, minkowskiengine_b200/tile_order.py).
 template <typename T, int BK, int RT, int CPS, int EXP = 0>
 __global__ void __launch_bounds__(kRsThreads, 1)
 k_conv_rs(const __grid_constant__ CUtensorMap mapB, const TcParams p) {
@@ -433,6 +452,7 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapB, const TcParams p) {
 #pragma unroll
             for (int sc = 0; sc < CPS; ++sc) {
               if constexpr (kKeepHint) v[ri * CPS + sc] = ldg128_hint(src + sc * BK, pol_keep);
+              else if constexpr ((EXP & 8) != 0) v[ri * CPS + sc] = ldg128_l1(src + sc * BK);
               else v[ri * CPS + sc] = ldg128(src + sc * BK);
             }
           } else {
@@ -986,7 +1006,8 @@ static int launch_tc_bk_r(int bk, uint32_t R, bool tma, const CUtensorMap &mA,
 static int launch_tc_slice(const void *A, int dtype, uint32_t n_a, uint32_t c_reduce,
                            const void *Wb_full, uint32_t c_cols_full, uint32_t n0, uint32_t K,
                            uint32_t c_cols, const int32_t *nbr, uint32_t n_rows, void *out,
-                           uint32_t out_ld, int out_dtype, cudaStream_t stream) {
+                           uint32_t out_ld, int out_dtype, cudaStream_t stream,
+                           const int32_t *row_ids = nullptr) {
   const void *Wb = reinterpret_cast<const uint8_t *>(Wb_full) + (size_t)n0 * c_reduce * 2;
   const uint32_t wb_k_stride = c_cols_full * c_reduce;
   TcParams p{};
@@ -995,6 +1016,7 @@ static int launch_tc_slice(const void *A, int dtype, uint32_t n_a, uint32_t c_re
   p.out_f32 = out_dtype == MEB200_F32;
   p.wb_k_stride = wb_k_stride; p.out_ld = out_ld;
   p.n_a = n_a; p.wb_row0 = n0; p.wb_rows_per_k = c_cols_full;
+  p.row_ids = row_ids;
   // tuning knob MEB200_TC_STAGE_KB: largest A stage.  24 KB = one 128B-swizzle chunk per stage
   // for BK=64 and three 64B-swizzle chunks for BK=32 — the best of the sweep in profiles/.
   static int max_stage_kb = -1;
@@ -1010,12 +1032,33 @@ static int launch_tc_slice(const void *A, int dtype, uint32_t n_a, uint32_t c_re
   // the 96-channel bf16 shape only; anything else runs the measured kernel.
   int rs_exp = 0;
   if (const char *e = getenv("MEB200_RS_EXP")) rs_exp = atoi(e);
-  if (!(rs_exp == 1 || rs_exp == 2 || rs_exp == 6 || rs_exp == 7) || dtype != MEB200_BF16 || mode != 2)
+  uint32_t budget = tc::kSmemBudget;
+  if (row_ids != nullptr) {
+    // ordered tiles (meb200_conv_forward_ordered): bit 3 plus, optionally, the hints (2) or the
+    // hints and the dirty-row masks (3) from MEB200_RS_EXP; MEB200_TC_SMEM_KB shrinks the ring so
+    // that the unified L1/shared array keeps room for L1
+    rs_exp = 8 | ((rs_exp & 3) == 3 ? 3 : (rs_exp & 2));
+    if (const char *e = getenv("MEB200_TC_SMEM_KB")) {
+      const int kb = atoi(e);
+      if (kb >= 64 && kb * 1024 < (int)tc::kSmemBudget) budget = (uint32_t)kb * 1024;
+    }
+    if (dtype != MEB200_BF16 || mode != 2) {
+      set_error("conv tc: ordered tiles need bf16 features and the register-staged kernel");
+      return MEB200_ERR_UNSUPPORTED;
+    }
+  } else if (!(rs_exp == 1 || rs_exp == 2 || rs_exp == 6 || rs_exp == 7) || dtype != MEB200_BF16 ||
+             mode != 2) {
     rs_exp = 0;
+  }
   const uint32_t rs_extra = (rs_exp & 1) ? 512u : 0u;   // dirty-row masks behind the scratch area
   tc::FwdCfg cfg = tc::fwd_config(c_reduce, c_cols, n_rows, (uint32_t)max_stage_kb * 1024,
-                                  mode == 2 ? tc::kRsScratchBytes + rs_extra : 0);
+                                  mode == 2 ? tc::kRsScratchBytes + rs_extra : 0, budget);
   if (rs_exp != 0 && !(cfg.bk == 32 && cfg.R == 2 && cfg.cps == 3)) {
+    if (row_ids != nullptr) {
+      set_error("conv tc: ordered tiles are compiled for the <bf16, 32, 2, 3> shape only "
+                "(got bk=%d R=%u cps=%u)", cfg.bk, cfg.R, cfg.cps);
+      return MEB200_ERR_UNSUPPORTED;
+    }
     rs_exp = 0;
     if (rs_extra)
       cfg = tc::fwd_config(c_reduce, c_cols, n_rows, (uint32_t)max_stage_kb * 1024, tc::kRsScratchBytes);
@@ -1053,6 +1096,9 @@ static int launch_tc_slice(const void *A, int dtype, uint32_t n_a, uint32_t c_re
       case 2: return launch_rs<__nv_bfloat16, 32, 2, 3, 2>(mB, p, smem_bytes, grid, stream);
       case 6: return launch_rs<__nv_bfloat16, 32, 2, 3, 6>(mB, p, smem_bytes, grid, stream);
       case 7: return launch_rs<__nv_bfloat16, 32, 2, 3, 7>(mB, p, smem_bytes, grid, stream);
+      case 8: return launch_rs<__nv_bfloat16, 32, 2, 3, 8>(mB, p, smem_bytes, grid, stream);
+      case 10: return launch_rs<__nv_bfloat16, 32, 2, 3, 10>(mB, p, smem_bytes, grid, stream);
+      case 11: return launch_rs<__nv_bfloat16, 32, 2, 3, 11>(mB, p, smem_bytes, grid, stream);
       default: break;
     }
     if (dtype == MEB200_BF16)
@@ -1072,7 +1118,8 @@ bool conv_tc_supported(int dtype, uint32_t c_reduce, uint32_t c_cols) {
 
 int conv_forward_tc(const void *A, int dtype, uint32_t n_a, uint32_t c_reduce, const void *W,
                     uint32_t K, uint32_t c_cols, bool dgrad, const int32_t *nbr, uint32_t n_rows,
-                    void *out, int out_dtype, void *workspace, cudaStream_t stream) {
+                    void *out, int out_dtype, void *workspace, cudaStream_t stream,
+                    const int32_t *row_ids) {
   if (n_rows == 0) return MEB200_OK;
   MEB_CHECK_ARG(conv_tc_supported(dtype, c_reduce, c_cols), "shape not supported by tc path");
   const uint8_t *Wb = reinterpret_cast<const uint8_t *>(W);
@@ -1095,7 +1142,7 @@ int conv_forward_tc(const void *A, int dtype, uint32_t n_a, uint32_t c_reduce, c
     uint32_t nc = c_cols - n0 < 256 ? c_cols - n0 : 256;
     int rc = launch_tc_slice(A, dtype, n_a, c_reduce, Wb, c_cols, n0, K, nc, nbr, n_rows,
                              reinterpret_cast<uint8_t *>(out) + (size_t)n0 * out_esz, c_cols,
-                             out_dtype, stream);
+                             out_dtype, stream, row_ids);
     if (rc != MEB200_OK) return rc;
   }
   return MEB200_OK;

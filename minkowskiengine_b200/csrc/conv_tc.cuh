@@ -13,7 +13,8 @@ bool conv_wgrad_tc_supported(int dtype, uint32_t c_in, uint32_t c_out);
 // c_cols = c_in.  `workspace` receives the re-laid-out operand-B copy of W.
 int conv_forward_tc(const void *A, int dtype, uint32_t n_a, uint32_t c_reduce, const void *W,
                     uint32_t K, uint32_t c_cols, bool dgrad, const int32_t *nbr, uint32_t n_rows,
-                    void *out, int out_dtype, void *workspace, cudaStream_t stream);
+                    void *out, int out_dtype, void *workspace, cudaStream_t stream,
+                    const int32_t *row_ids = nullptr);   // ordered tiles: see TcParams::row_ids
 
 int conv_wgrad_tc(const void *in, const void *grad_out, int dtype, uint32_t c_in, uint32_t K,
                   uint32_t c_out, const int32_t *out_nbr, uint32_t n_out, float *grad_weight,

@@ -54,7 +54,7 @@ struct FwdCfg {
 constexpr uint32_t kRsScratchBytes = 10 * 128 * 8 + 64;  // register-staged kernel: per-warp compaction lists + counters
 
 inline FwdCfg fwd_config(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, uint32_t max_stage_bytes = 32 * 1024,
-                         uint32_t extra_bytes = 0) {
+                         uint32_t extra_bytes = 0, uint32_t budget = kSmemBudget) {
   FwdCfg c{};
   uint32_t R = kTmemCols / (2 * c_cols);                // accumulator set is double buffered
   R = R >= 4 ? 4 : (R >= 2 ? 2 : 1);
@@ -71,7 +71,7 @@ inline FwdCfg fwd_config(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, uint3
     const uint32_t b_sub = ((c_cols * cand * 2 + 1023) / 1024) * 1024;
     for (uint32_t cps = chunks; cps >= 1; --cps) {
       if (chunks % cps != 0 || (cps * a_sub > max_stage_bytes && cps > 1)) continue;
-      PipeCfg p = pick_pipeline(cps * a_sub, cps * b_sub, R, kSmemBudget - kBarBytes - 1024 - extra_bytes);
+      PipeCfg p = pick_pipeline(cps * a_sub, cps * b_sub, R, budget - kBarBytes - 1024 - extra_bytes);
       if (p.lag < 3) continue;
       // bytes of A in flight, with a mild preference for fat stages (fewer barrier round trips)
       uint64_t score = (uint64_t)p.lag * cps * a_sub * 8 + (uint64_t)cps * a_sub;

@@ -15,7 +15,13 @@ torch ops (device agnostic, so it is checked on the CPU against numpy):
                         row once per tile into shared memory and build the per-offset operand
                         from there.
 
-Nothing here is on the product path yet; the kernels that consume these tables are round-2 work.
+  * `ordered_tables` / `conv_forward_ordered` - the cheap first step: permute the columns of
+                        the neighbour table so that the kernel's tiles walk the rows in Morton
+                        order and let the L1 cache serve the re-reads
+                        (`meb200_conv_forward_ordered`, `k_conv_rs` EXP bit 3).
+
+Nothing here is on the product path yet; it exists to be measured at the start of round 2
+(`profiles/layer_bench.py --ordered`).
 """
 import torch
 
@@ -89,3 +95,28 @@ def staging_tables(nbr, perm, tile=128):
     loc.scatter_(1, idx, loc_sorted)
     local = loc.view(n_tiles, K, tile).permute(1, 0, 2).reshape(K, n_tiles * tile).int()
     return rows, counts.int(), local
+
+
+def ordered_tables(nbr, coords, tensor_stride=1):
+    """-> (tile_nbr [K, N] int32 with tile_nbr[k, j] = nbr[k, row_ids[j]], row_ids [N] int32):
+    the arguments of `meb200_conv_forward_ordered` for the rows whose coordinates are `coords`."""
+    perm = morton_order(coords, tensor_stride)
+    return nbr[:, perm].contiguous(), perm.int().contiguous()
+
+
+def conv_forward_ordered(in_feat, kernel, tile_nbr, row_ids, out_dtype=None):
+    """Forward convolution with spatially ordered tiles (CUDA tensors, tensor-core shapes only);
+    same result as backend._conv_forward on the unpermuted table."""
+    from . import _lib, backend
+    lib = _lib.load()
+    code = _lib.dtype_code(in_feat.dtype)
+    kernel = kernel.to(in_feat.dtype).contiguous()
+    K, c_in, c_out = kernel.shape
+    n_in, n_out = in_feat.shape[0], tile_nbr.shape[1]
+    out = torch.empty((n_out, c_out), dtype=out_dtype or in_feat.dtype, device=in_feat.device)
+    ws, ws_bytes = backend._workspace(n_in, n_out, c_in, c_out, K, code, in_feat.device)
+    _lib.check(lib.meb200_conv_forward_ordered(
+        _lib.ptr(in_feat), code, n_in, c_in, _lib.ptr(kernel), K, c_out, _lib.ptr(tile_nbr),
+        _lib.ptr(row_ids), n_out, _lib.ptr(out), _lib.dtype_code(out.dtype), _lib.ptr(ws),
+        ws_bytes, _lib.current_stream()))
+    return out

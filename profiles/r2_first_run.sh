@@ -38,6 +38,16 @@ for E in 1 2 6 7; do
   tail -5 "$OUT/layers_rs_exp$E.txt" | cut -c1-150 >> "$OUT/summary.txt"
 done
 
+echo "== ordered (Morton) tiles + L1-allocating gathers, forward of the 96-channel layers" | tee -a "$OUT/summary.txt"
+for KB in 0 176 144; do
+  for E in 0 2; do
+    echo "-- MEB200_TC_SMEM_KB=$KB MEB200_RS_EXP=$E" >> "$OUT/summary.txt"
+    MEB200_TC_SMEM_KB=$KB MEB200_RS_EXP=$E timeout 120 python profiles/layer_bench.py --only "96->96" --ordered \
+      > "$OUT/layers_ordered_kb${KB}_e$E.txt" 2>&1
+    grep -a "ordered\|96->96" "$OUT/layers_ordered_kb${KB}_e$E.txt" | cut -c1-150 >> "$OUT/summary.txt"
+  done
+done
+
 echo "== bench with defaults" | tee -a "$OUT/summary.txt"
 timeout 200 python bench.py 2>/dev/null | tail -1 > "$OUT/bench_default.json"
 cut -c1-330 "$OUT/bench_default.json" | tee -a "$OUT/summary.txt"

@@ -56,3 +56,19 @@ def test_staging_tables_reproduce_the_neighbour_table():
                 hit = blk >= 0
                 assert (lst[lb[hit]] == blk[hit]).all()
                 assert set(lst.tolist()) == set(blk[hit].tolist())
+
+
+def test_ordered_tables_permute_columns_only():
+    c = surface_cloud(2000, 5)
+    nbr = _table(c.numpy())
+    tile_nbr, row_ids = TO.ordered_tables(nbr, c, 1)
+    assert tile_nbr.dtype == torch.int32 and row_ids.dtype == torch.int32
+    assert sorted(row_ids.tolist()) == list(range(len(c)))
+    assert torch.equal(tile_nbr, nbr[:, row_ids.long()])
+    # strided level: coordinates are multiples of the tensor stride
+    c2 = c.clone()
+    c2[:, 1:] = torch.div(c2[:, 1:], 2, rounding_mode="floor") * 2
+    c2 = torch.unique(c2, dim=0)
+    p2 = TO.morton_order(c2, 2)
+    p1 = TO.morton_order(torch.cat([c2[:, :1], c2[:, 1:] // 2], 1), 1)
+    assert torch.equal(p1, p2)
