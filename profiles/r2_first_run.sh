@@ -48,6 +48,10 @@ for KB in 0 176 144; do
   done
 done
 
+echo "== operand A in tensor memory: layout micro-test" | tee -a "$OUT/summary.txt"
+(cd profiles/micro && nvcc -gencode arch=compute_100a,code=sm_100a -ccbin /usr/bin/g++ -std=c++17 \
+   -o tmem_a_layout tmem_a_layout.cu 2>&1 | tail -3; timeout 30 ./tmem_a_layout) 2>&1 | tee -a "$OUT/summary.txt"
+
 echo "== bench with defaults" | tee -a "$OUT/summary.txt"
 timeout 200 python bench.py 2>/dev/null | tail -1 > "$OUT/bench_default.json"
 cut -c1-330 "$OUT/bench_default.json" | tee -a "$OUT/summary.txt"
