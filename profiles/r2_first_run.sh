@@ -2,7 +2,7 @@
 # First GPU call of round 2: run every experiment that was prepared (but not measured) at the
 # end of round 1, each behind its environment switch, and leave the numbers in gpurun_out/.
 #
-#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash profiles/r2_first_run.sh'
+#   /usr/local/graft/bin/gpurun --timeout 1200 -- 'bash profiles/r2_first_run.sh'   (about 12-15 GPU-minutes)
 #
 # Every step runs under `timeout`; a failing variant does not stop the others.
 set -u
