@@ -924,15 +924,33 @@ static int gather_mode() {
   return v;
 }
 
+
+// Opt a kernel in to >48 KB of dynamic shared memory.  The attribute is per (function, device):
+// the flags are keyed on the function pointer VALUE and the current device (round 1 kept one
+// static flag inside a generic lambda, which every k_wgrad_tc<T,PF> instantiation shared because
+// they all decay to the same pointer type -> the second variant launched unconfigured).
+static int ensure_big_smem(const void *fn) {
+  constexpr int kMaxDev = 16, kMaxFn = 256;
+  static const void *fns[kMaxFn];
+  static uint16_t done[kMaxFn];
+  static int n_fns = 0;
+  int dev = 0;
+  MEB_CUDA(cudaGetDevice(&dev));
+  int slot = -1;
+  for (int i = 0; i < n_fns; ++i) if (fns[i] == fn) { slot = i; break; }
+  if (slot >= 0 && dev < kMaxDev && (done[slot] >> dev & 1)) return MEB200_OK;
+  MEB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  if (slot < 0 && n_fns < kMaxFn) { slot = n_fns++; fns[slot] = fn; done[slot] = 0; }
+  if (slot >= 0 && dev < kMaxDev) done[slot] |= (uint16_t)(1u << dev);
+  return MEB200_OK;
+}
+#define MEB_BIG_SMEM(kern) do { int rc__ = ensure_big_smem((const void *)(kern)); if (rc__ != MEB200_OK) return rc__; } while (0)
+
 template <typename T, int BK, int RT, int CPS, int EXP = 0>
 static int launch_rs(const CUtensorMap &mB, const TcParams &p, size_t smem_bytes, unsigned grid,
                      cudaStream_t stream) {
   auto kern = k_conv_rs<T, BK, RT, CPS, EXP>;
-  static bool configured = false;
-  if (!configured) {
-    MEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  MEB_BIG_SMEM(kern);
   kern<<<grid, kRsThreads, smem_bytes, stream>>>(mB, p);
   count_tc_launch();
   MEB_LAUNCH_OK();
@@ -965,11 +983,7 @@ template <typename T, int BK, int RT, bool TMA>
 static int launch_tc(const CUtensorMap &mA, const CUtensorMap &mB, const TcParams &p,
                      size_t smem_bytes, unsigned grid, cudaStream_t stream) {
   auto kern = k_conv_tc<T, BK, RT, TMA>;
-  static bool configured = false;
-  if (!configured) {
-    MEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  MEB_BIG_SMEM(kern);
   kern<<<grid, kFwdThreads, smem_bytes, stream>>>(mA, mB, p);
   count_tc_launch();
   MEB_LAUNCH_OK();
@@ -1655,12 +1669,10 @@ int conv_wgrad_tc(const void *in, const void *grad_out, int dtype, uint32_t c_in
       q.a_stage_bytes = cfg.a_stage_bytes; q.b_stage_bytes = cfg.b_stage_bytes;
       unsigned grid = cfg.n_kgroups * cfg.n_mtgroups * cfg.n_splits;
       if (dtype == MEB200_BF16) {
-        static bool done = false;
-        if (!done) { MEB_CUDA(cudaFuncSetAttribute(k_wgrad_rs2<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); done = true; }
+        MEB_BIG_SMEM(k_wgrad_rs2<__nv_bfloat16>);
         k_wgrad_rs2<__nv_bfloat16><<<grid, kWg2Threads, cfg.smem_bytes, stream>>>(mG, q);
       } else {
-        static bool done = false;
-        if (!done) { MEB_CUDA(cudaFuncSetAttribute(k_wgrad_rs2<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); done = true; }
+        MEB_BIG_SMEM(k_wgrad_rs2<__half>);
         k_wgrad_rs2<__half><<<grid, kWg2Threads, cfg.smem_bytes, stream>>>(mG, q);
       }
       count_tc_launch();
@@ -1686,9 +1698,8 @@ int conv_wgrad_tc(const void *in, const void *grad_out, int dtype, uint32_t c_in
   // MEB200_WG_PREFETCH = 4 | 8 | 16: experimental deeper index prefetch (see k_wgrad_tc); default 0
   int pf = 0;
   if (const char *e = getenv("MEB200_WG_PREFETCH")) pf = atoi(e);
-  auto launch = [&](auto kern) -> int {
-    static bool done = false;   // one flag per kernel instantiation (generic lambda)
-    if (!done) { MEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); done = true; }
+  auto launch = [&](void (*kern)(const WgParams)) -> int {
+    MEB_BIG_SMEM(kern);
     kern<<<grid, kThreads, smem_bytes, stream>>>(p);
     return MEB200_OK;
   };
