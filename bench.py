@@ -55,7 +55,7 @@ def parse_args():
 def make_batch(n_clouds, n_voxels, seed0):
     """Synthetic 'surface' clouds (SURVEY.md §8d generator), one batch index per cloud."""
     import torch
-    from oracle.oracle_np import surface_cloud  # input generator only (test infrastructure)
+    from examples.synthetic import surface_cloud
     coords = torch.cat([surface_cloud(n_voxels, seed0 + j, batch=j) for j in range(n_clouds)], 0)
     g = torch.Generator().manual_seed(seed0)
     feats = torch.rand(len(coords), 3, generator=g)

@@ -144,6 +144,22 @@ int meb200_conv_backward(const void *in, const void *grad_out, int dtype, uint32
                          void *grad_in, int grad_in_dtype, float *grad_weight,
                          void *workspace, uint64_t workspace_bytes, void *stream);
 
+/* Weight packing for the tensor-core path, once per optimizer step instead of once per call:
+ * fp32 master weight [K, Cin, Cout] -> `dtype` (BF16/F16) copies w_cast [K, Cin, Cout] (pass it
+ * as `weight` to meb200_conv_backward) and w_t [K, Cout, Cin] (for meb200_conv_forward_packed).
+ * The reference keeps weights in the feature dtype and needs no such step
+ * (MinkowskiConvolution.py:264-279); this is the bf16/fp16 operand cache of this backend. */
+int meb200_conv_pack_weights(const float *weight, uint32_t K, uint32_t c_in, uint32_t c_out,
+                             int dtype, void *w_cast, void *w_t, void *stream);
+
+/* meb200_conv_forward with the weight already packed as w_t [K, Cout, Cin] (tensor-core path
+ * only: returns MEB200_ERR_UNSUPPORTED for shapes/dtypes outside it, the caller then uses
+ * meb200_conv_forward).  Same result, no per-call cast/transpose, no workspace. */
+int meb200_conv_forward_packed(const void *in, int in_dtype, uint32_t n_in, uint32_t c_in,
+                               const void *weight_t, uint32_t K, uint32_t c_out,
+                               const int32_t *out_nbr, uint32_t n_out, void *out, int out_dtype,
+                               void *stream);
+
 /* Workspace the two calls above may use (0 is legal: slower fallbacks are chosen). */
 uint64_t meb200_conv_workspace_bytes(uint32_t n_in, uint32_t n_out, uint32_t c_in,
                                      uint32_t c_out, uint32_t K, int dtype);

@@ -37,6 +37,9 @@ PROTOTYPES = {
                                    _i32, _vp, _u64, _vp]),
     "meb200_conv_backward": (_i32, [_vp, _vp, _i32, _u32, _u32, _vp, _u32, _u32, _vp, _vp,
                                     _u32, _vp, _i32, _vp, _vp, _u64, _vp]),
+    "meb200_conv_pack_weights": (_i32, [_vp, _u32, _u32, _u32, _i32, _vp, _vp, _vp]),
+    "meb200_conv_forward_packed": (_i32, [_vp, _i32, _u32, _u32, _vp, _u32, _u32, _vp, _u32, _vp,
+                                          _i32, _vp]),
     "meb200_conv_workspace_bytes": (_u64, [_u32, _u32, _u32, _u32, _u32, _i32]),
     "meb200_pool_forward": (_i32, [_vp, _i32, _u32, _u32, _vp, _u32, _u32, _i32, _vp, _vp, _vp]),
     "meb200_pool_backward": (_i32, [_vp, _i32, _u32, _u32, _vp, _u32, _u32, _i32, _vp, _vp,

@@ -11,6 +11,7 @@ synchronisation is the unique-row count read when a NEW coordinate map is create
 import ctypes
 import random
 import string
+import weakref
 
 import torch
 
@@ -534,9 +535,54 @@ def _conv_forward(in_feat, kernel, km, out_dtype=None):
     return _conv_forward_impl(in_feat, kernel, km, out_dtype)
 
 
+# ---- packed weights: one cast + transpose per optimizer step, not per call -------------------
+_PACKED = {}   # id(kernel tensor) -> (weakref, version, data_ptr, dtype, w_cast, w_t)
+_ERR_UNSUPPORTED = -3
+
+
+def _packed_weights(kernel, dtype):
+    """(w_cast [K,Cin,Cout], w_t [K,Cout,Cin]) of an fp32 master weight in `dtype`, rebuilt only
+    when the tensor was modified in place (its autograd version counter moved) or replaced."""
+    key = id(kernel)
+    ent = _PACKED.get(key)
+    if ent is not None and ent[0]() is kernel and ent[1] == kernel._version \
+            and ent[2] == kernel.data_ptr() and ent[3] == dtype:
+        return ent[4], ent[5]
+    lib = _lib.load()
+    K, c_in, c_out = kernel.shape
+    src = kernel.detach()
+    w_cast = torch.empty((K, c_in, c_out), dtype=dtype, device=kernel.device)
+    w_t = torch.empty((K, c_out, c_in), dtype=dtype, device=kernel.device)
+    _lib.check(lib.meb200_conv_pack_weights(_lib.ptr(src), K, c_in, c_out, _lib.dtype_code(dtype),
+                                            _lib.ptr(w_cast), _lib.ptr(w_t), _lib.current_stream()))
+    if len(_PACKED) > 4096:      # dead entries of discarded networks
+        for k in [k for k, e in _PACKED.items() if e[0]() is None]:
+            del _PACKED[k]
+    _PACKED[key] = (weakref.ref(kernel), kernel._version, kernel.data_ptr(), dtype, w_cast, w_t)
+    return w_cast, w_t
+
+
+def _can_pack(kernel, feat_dtype):
+    return (kernel.dtype == torch.float32 and feat_dtype in (torch.bfloat16, torch.float16)
+            and kernel.is_contiguous() and kernel.dim() == 3)
+
+
 def _conv_forward_impl(in_feat, kernel, km, out_dtype=None):
     lib = _lib.load()
     code = _lib.dtype_code(in_feat.dtype)
+    if _can_pack(kernel, in_feat.dtype):
+        K, c_in, c_out = kernel.shape
+        _assert(K == km.K, "kernel volume", K, "does not match the kernel map", km.K)
+        _, w_t = _packed_weights(kernel, in_feat.dtype)
+        out = torch.empty((km.n_out, c_out), dtype=out_dtype or in_feat.dtype,
+                          device=in_feat.device)
+        rc = lib.meb200_conv_forward_packed(
+            _lib.ptr(in_feat), code, km.n_in, c_in, _lib.ptr(w_t), K, c_out,
+            _lib.ptr(km.out_nbr), km.n_out, _lib.ptr(out), _lib.dtype_code(out.dtype),
+            _lib.current_stream())
+        if rc != _ERR_UNSUPPORTED:
+            _lib.check(rc)
+            return out
     if kernel.dtype != in_feat.dtype:
         kernel = kernel.to(in_feat.dtype)
     kernel = kernel.contiguous()
@@ -577,8 +623,11 @@ def _conv_backward_impl(in_feat, grad_out, kernel, km, need_in=True, need_w=True
     if grad_out.dtype != in_feat.dtype:
         grad_out = grad_out.to(in_feat.dtype)
     grad_out = grad_out.contiguous()
-    w = kernel if kernel.dtype == in_feat.dtype else kernel.to(in_feat.dtype)
-    w = w.contiguous()
+    if _can_pack(kernel, in_feat.dtype):
+        w, _ = _packed_weights(kernel, in_feat.dtype)
+    else:
+        w = kernel if kernel.dtype == in_feat.dtype else kernel.to(in_feat.dtype)
+        w = w.contiguous()
     K, c_in, c_out = w.shape
     n_out, n_in = km.n_out, km.n_in
     grad_in = torch.empty((n_in, c_in), dtype=in_feat.dtype, device=in_feat.device) \

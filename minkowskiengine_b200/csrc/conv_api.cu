@@ -53,6 +53,34 @@ int meb200_conv_forward(const void *in, int in_dtype, uint32_t n_in, uint32_t c_
                            out_nbr, n_out, out, out_dtype, stream);
 }
 
+int meb200_conv_pack_weights(const float *weight, uint32_t K, uint32_t c_in, uint32_t c_out,
+                             int dtype, void *w_cast, void *w_t, void *stream_) {
+  MEB_CHECK_ARG(dtype == MEB200_BF16 || dtype == MEB200_F16, "packed weights are bf16 or fp16");
+  MEB_CHECK_ARG(weight && w_cast && w_t, "null buffer");
+  MEB_CHECK_ARG(c_in > 0 && c_out > 0 && K > 0 && K <= 65535, "empty channel/kernel dims");
+  return conv_pack_weights(weight, K, c_in, c_out, dtype, w_cast, w_t, (cudaStream_t)stream_);
+}
+
+int meb200_conv_forward_packed(const void *in, int in_dtype, uint32_t n_in, uint32_t c_in,
+                               const void *weight_t, uint32_t K, uint32_t c_out,
+                               const int32_t *out_nbr, uint32_t n_out, void *out, int out_dtype,
+                               void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n_out == 0) return MEB200_OK;
+  MEB_CHECK_ARG(in_dtype >= 0 && in_dtype <= 2 && out_dtype >= 0 && out_dtype <= 2, "dtype");
+  MEB_CHECK_ARG(out_dtype == MEB200_F32 || out_dtype == in_dtype,
+                "output dtype must be fp32 or the input dtype");
+  MEB_CHECK_ARG(out && weight_t && out_nbr && (in || n_in == 0), "null buffer");
+  MEB_CHECK_ARG(c_in > 0 && c_out > 0 && K > 0, "empty channel/kernel dims");
+  if (tc_disabled() || !conv_tc_supported(in_dtype, c_in, c_out)) {
+    set_error("packed forward: shape/dtype outside the tensor-core path");
+    return MEB200_ERR_UNSUPPORTED;
+  }
+  // W^T[k][c_out][c_in] is operand B as the kernel wants it: the "no transpose" entry
+  return conv_forward_tc(in, in_dtype, n_in, c_in, weight_t, K, c_out, /*dgrad=*/true, out_nbr,
+                         n_out, out, out_dtype, nullptr, stream);
+}
+
 int meb200_conv_forward_ordered(const void *in, int in_dtype, uint32_t n_in, uint32_t c_in,
                                 const void *weight, uint32_t K, uint32_t c_out,
                                 const int32_t *tile_nbr, const int32_t *row_ids, uint32_t n_out,

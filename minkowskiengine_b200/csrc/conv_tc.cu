@@ -859,6 +859,41 @@ k_transpose_w(const T *__restrict__ W, T *__restrict__ Wb, uint32_t c_in, uint32
     if (co0 + i < c_out && ci0 + tx < c_in) Wbk[(size_t)(co0 + i) * c_in + ci0 + tx] = tile[tx][i];
 }
 
+// Per-optimizer-step weight packing: fp32 master W[k][ci][co] -> feature dtype, both as
+// W[k][ci][co] (operand B of the dgrad kernel) and W^T[k][co][ci] (operand B of the forward
+// kernel), in one pass.  Replaces a torch cast plus k_transpose_w on EVERY forward call.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_pack_w(const float *__restrict__ W, T *__restrict__ Wc, T *__restrict__ Wt, uint32_t c_in,
+         uint32_t c_out) {
+  __shared__ float tile[32][33];
+  const size_t base = (size_t)blockIdx.z * c_in * c_out;
+  const uint32_t ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
+  const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (uint32_t i = ty; i < 32; i += 8)
+    if (ci0 + i < c_in && co0 + tx < c_out) {
+      const float v = W[base + (size_t)(ci0 + i) * c_out + co0 + tx];
+      tile[i][tx] = v;
+      Wc[base + (size_t)(ci0 + i) * c_out + co0 + tx] = from_f32<T>(v);
+    }
+  __syncthreads();
+  for (uint32_t i = ty; i < 32; i += 8)
+    if (co0 + i < c_out && ci0 + tx < c_in)
+      Wt[base + (size_t)(co0 + i) * c_in + ci0 + tx] = from_f32<T>(tile[tx][i]);
+}
+
+int conv_pack_weights(const float *W, uint32_t K, uint32_t c_in, uint32_t c_out, int dtype,
+                      void *w_cast, void *w_t, cudaStream_t stream) {
+  dim3 grid(cdiv(c_out, 32), cdiv(c_in, 32), K);
+  if (dtype == MEB200_BF16)
+    k_pack_w<__nv_bfloat16><<<grid, 256, 0, stream>>>(W, (__nv_bfloat16 *)w_cast,
+                                                      (__nv_bfloat16 *)w_t, c_in, c_out);
+  else
+    k_pack_w<__half><<<grid, 256, 0, stream>>>(W, (__half *)w_cast, (__half *)w_t, c_in, c_out);
+  MEB_LAUNCH_OK();
+  return MEB200_OK;
+}
+
 static int pick_bk(uint32_t c_red) {
   if (c_red % 64 == 0) return 64;
   if (c_red % 32 == 0) return 32;

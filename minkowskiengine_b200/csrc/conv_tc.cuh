@@ -16,6 +16,10 @@ int conv_forward_tc(const void *A, int dtype, uint32_t n_a, uint32_t c_reduce, c
                     void *out, int out_dtype, void *workspace, cudaStream_t stream,
                     const int32_t *row_ids = nullptr);   // ordered tiles: see TcParams::row_ids
 
+// fp32 W[K,c_in,c_out] -> (w_cast [K,c_in,c_out], w_t [K,c_out,c_in]) in `dtype` (bf16/fp16).
+int conv_pack_weights(const float *W, uint32_t K, uint32_t c_in, uint32_t c_out, int dtype,
+                      void *w_cast, void *w_t, cudaStream_t stream);
+
 int conv_wgrad_tc(const void *in, const void *grad_out, int dtype, uint32_t c_in, uint32_t K,
                   uint32_t c_out, const int32_t *out_nbr, uint32_t n_out, float *grad_weight,
                   cudaStream_t stream);

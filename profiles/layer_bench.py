@@ -16,7 +16,7 @@ import torch  # noqa: E402
 
 import minkowskiengine_b200 as ME  # noqa: E402
 from minkowskiengine_b200 import backend  # noqa: E402
-from oracle.oracle_np import surface_cloud  # noqa: E402  (input generator only)
+from examples.synthetic import surface_cloud  # noqa: E402
 
 LAYERS = [  # (name, tensor stride level, cin, cout, ks, stride, transposed)
     ("conv0 3->32 k5", 1, 3, 32, 5, 1, False),
