@@ -357,10 +357,21 @@ class CoordinateMapManagerGPU_c10:
         dev = x_map.coords.device
         x_nbr = torch.empty((K, x_map.size), dtype=torch.int32, device=dev)
         y_nbr = torch.full((K, y_map.size), -1, dtype=torch.int32, device=dev)
-        _lib.check(lib.meb200_kernel_map(
-            _lib.ptr(x_map.coords), x_map.size, _lib.ptr(y_map.coords), y_map.size,
-            _lib.ptr(y_map.table), y_map.capacity, x_map.ncols, _lib.ptr(offsets), K,
-            _lib.ptr(x_nbr), _lib.ptr(y_nbr), None, _lib.current_stream()))
+
+        def launch():
+            _lib.check(lib.meb200_kernel_map(
+                _lib.ptr(x_map.coords), x_map.size, _lib.ptr(y_map.coords), y_map.size,
+                _lib.ptr(y_map.table), y_map.capacity, x_map.ncols, _lib.ptr(offsets), K,
+                _lib.ptr(x_nbr), _lib.ptr(y_nbr), None, _lib.current_stream()))
+        if _PROFILE is not None:
+            # algorithmic bytes: coordinate rows read once, one 4-byte table slot
+            # + one coordinate row compared per probe, both neighbour tables written
+            nc4 = x_map.ncols * 4
+            probes = float(K) * x_map.size
+            nbytes = x_map.size * nc4 + probes * (4 + nc4) + probes * 4 + float(K) * y_map.size * 4
+            _record("kernel_map", launch, probes, nbytes, always=True)
+        else:
+            launch()
         return x_nbr, y_nbr
 
     def _kernel_map(self, in_key, out_key, kernel_size, kernel_stride, kernel_dilation,
@@ -487,18 +498,18 @@ def _workspace(n_in, n_out, c_in, c_out, K, code, device):
 
 
 # ---- live per-kernel timing for bench.py's roofline (CUDA events on the launch stream) ------
-_PROFILE = None   # None, or {"conv_fwd_dgrad": [...], "conv_wgrad": [...]} of event records
+_PROFILE = None   # None, or {"conv_fwd_dgrad": [...], "conv_wgrad": [...], "kernel_map": [...]}
 
 
-def _record(kind, fn, flops, nbytes):
+def _record(kind, fn, flops, nbytes, always=False):
     """Run fn() between two CUDA events on the current stream; keep the record if it launched
-    a tcgen05 kernel (the family the roofline is reported for)."""
+    a tcgen05 kernel (the family the roofline is reported for) or `always`."""
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tc0 = _lib.tc_launch_count()
     e0.record()
     out = fn()
     e1.record()
-    if _lib.tc_launch_count() > tc0:
+    if always or _lib.tc_launch_count() > tc0:
         _PROFILE[kind].append((e0, e1, flops, nbytes))
     return out
 
@@ -508,7 +519,7 @@ def profile_conv_kernels(step_fn, steps=2):
     returns, per kernel family, the summed device time and ALGORITHMIC work:
     flops = 2*P*Cin*Cout per launch, bytes = the compulsory traffic of SURVEY.md §8d."""
     global _PROFILE
-    _PROFILE = {"conv_fwd_dgrad": [], "conv_wgrad": []}
+    _PROFILE = {"conv_fwd_dgrad": [], "conv_wgrad": [], "kernel_map": []}
     try:
         for _ in range(steps):
             step_fn()

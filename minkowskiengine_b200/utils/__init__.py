@@ -35,7 +35,10 @@ def kaiming_normal_(tensor, a=0, mode="fan_in", nonlinearity="leaky_relu"):
     if tensor.dim() == 3:
         fan_in, fan_out = tensor.size(0) * tensor.size(1), tensor.size(0) * tensor.size(2)
     else:
-        fan_in, fan_out = tensor.size(0), tensor.size(1)
+        # 2-D kernels ([Cin, Cout], kernel volume 1) are treated like torch Linear weights by
+        # the reference (utils/init.py:12-14): fan_in = size(1), fan_out = size(0).  Kept so
+        # that a seeded initialisation reproduces the reference's weights bit for bit.
+        fan_in, fan_out = tensor.size(1), tensor.size(0)
     fan = fan_in if mode == "fan_in" else fan_out
     gain = torch.nn.init.calculate_gain(nonlinearity, a)
     std = gain / math.sqrt(fan)

@@ -141,3 +141,77 @@ def test_cfg4_4d_hash_stress(ME, cuda):
         hit = sk[pos] == qk
         exp = torch.where(hit, order[pos], torch.full_like(pos, -1)).int()
         assert torch.equal(km.out_nbr[k], exp)
+
+
+def _cfg4_cloud(n_draws, seed):
+    g = torch.Generator().manual_seed(seed)
+    v = torch.randn(n_draws, 3, generator=g)
+    v = v / v.norm(dim=1, keepdim=True)
+    t = torch.randint(0, 8, (n_draws, 1), generator=g)
+    r = 45.0 * (n_draws / 200_000) ** 0.5
+    c = torch.floor(r * v + 0.5 * t).int()
+    return torch.unique(torch.cat([torch.zeros(n_draws, 1, dtype=torch.int32), c, t.int()], 1), dim=0)
+
+
+def test_cfg4_4d_conv_bf16_vs_oracle_20k(ME, cuda):
+    """BASELINE configs[4] layer (4-D, k=3 => K=81, C=32 -> 32, bf16) through the public API at
+    >= 20k coordinates: kernel map + forward + dgrad + wgrad against the numpy oracle."""
+    import numpy as np
+    from oracle import oracle_np as O
+    coords = _cfg4_cloud(32_000, seed=1)
+    assert len(coords) >= 20_000
+    g = torch.Generator().manual_seed(4)
+    feats = torch.rand(len(coords), 32, generator=g).bfloat16()
+    conv = ME.MinkowskiConvolution(32, 32, kernel_size=3, stride=1, dimension=4).to(cuda)
+    x = ME.SparseTensor(feats, coords, device=cuda, requires_grad=True)
+    y = conv(x)
+    in_c = x.C.cpu().numpy()
+    im, om = O.kernel_map(in_c, in_c, O.region_offsets(O.HYPER_CUBE, [3] * 4, [1] * 4, [1] * 4))
+    km = x.coordinate_manager._manager._kernel_map(
+        x.coordinate_map_key, y.coordinate_map_key, [3] * 4, [1] * 4, [1] * 4,
+        ME.RegionType.HYPER_CUBE, torch.IntTensor(), False, False)
+    nbr = km.out_nbr.cpu().numpy()
+    assert int((nbr >= 0).sum()) == sum(len(i) for i in im)
+    for k in range(81):                         # bit-exact: pairs of offset k, ordered by out row
+        o = np.nonzero(nbr[k] >= 0)[0]
+        order = np.argsort(om[k], kind="stable")
+        assert (o == om[k][order]).all() and (nbr[k][o] == im[k][order]).all()
+    w = conv.kernel.detach().bfloat16().float().cpu().numpy()
+    f = feats.float().numpy()
+    ref = O.conv_forward(f, w, im, om, len(in_c))
+    e = np.abs(y.F.detach().float().cpu().numpy() - ref).max() / np.abs(ref).max()
+    assert e < 6e-3, e                          # one bf16 output rounding
+    gout = (torch.rand(y.F.shape, generator=g) - 0.5).bfloat16()
+    y.F.backward(gout.to(cuda))
+    gi, gw = O.conv_backward(f, gout.float().numpy(), w, im, om)
+    assert np.abs(x.F.grad.float().cpu().numpy() - gi).max() / np.abs(gi).max() < 6e-3
+    assert np.abs(conv.kernel.grad.float().cpu().numpy() - gw).max() / np.abs(gw).max() < 1e-3
+
+
+def test_cfg4_4d_conv_bf16_full_size_properties(ME, cuda):
+    """configs[4] at full size (200k draws -> 131 897 coordinates, K = 81, C = 32): the tcgen05
+    path against an fp32 torch restatement on the device, and the adjoint identities."""
+    from minkowskiengine_b200 import _lib, backend
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator().manual_seed(0)
+    v = torch.randn(200_000, 3, generator=g)
+    v = v / v.norm(dim=1, keepdim=True)
+    t = torch.randint(0, 8, (200_000, 1), generator=g)
+    c = torch.floor(45 * v + 0.5 * t).int()
+    coords = torch.cat([torch.zeros(200_000, 1, dtype=torch.int32), c, t.int()], 1)
+    x, mgr, _, km = _maps(ME, coords, cuda, 3, 1, D=4)
+    n = len(x)
+    assert n == 131_897
+    feats = torch.rand(n, 32, generator=g).bfloat16().to(cuda)
+    w = ((torch.rand(81, 32, 32, generator=g) * 2 - 1) / (81 * 32) ** 0.5).to(cuda)
+    wl = w.bfloat16()
+    before = _lib.tc_launch_count()
+    y = backend._conv_forward(feats, wl, km, out_dtype=torch.float32)
+    assert _lib.tc_launch_count() > before, "4-D forward did not take the tcgen05 path"
+    ref = _torch_conv(feats, wl, km.out_nbr)
+    assert float((y - ref).abs().max() / ref.abs().max()) < 1e-4
+    dy = (torch.rand(n, 32, generator=g) - 0.5).bfloat16().to(cuda)
+    gi, gw = backend._conv_backward(feats, dy, w, km)
+    lhs = float((dy.float() * ref).sum())
+    assert abs(float((gi.float() * feats.float()).sum()) - lhs) / abs(lhs) < 5e-3
+    assert abs(float((gw.float() * wl.float()).sum()) - lhs) / abs(lhs) < 1e-4
