@@ -123,6 +123,20 @@ int meb200_kernel_map(const int32_t *x_coords, uint32_t nx, const int32_t *y_coo
                       uint32_t ncols, const int32_t *offsets, uint32_t K, int32_t *x_nbr,
                       int32_t *y_nbr, uint32_t *d_num_pairs, void *stream);
 
+/* Compacted pair lists of a neighbour table — the reference's own kernel-map representation
+ * (gpu_kernel_map::in_maps / out_maps per offset, src/kernel_map.cuh:48-429; what
+ * CoordinateMapManager::kernel_map returns, coordinate_map_manager.cpp:662-823).  For every offset
+ * k, in table-row order: pairs_other[i] = nbr[k][r], pairs_row[i] = r for the rows r with
+ * nbr[k][r] >= 0; offset k occupies [seg_start[k], seg_start[k+1]), padded with (-1, -1) to a
+ * multiple of `stage` entries.  Deterministic, no atomics, no host synchronisation.
+ * Buffers: pairs_* hold meb200_pair_list_capacity(K, n_rows, stage) int32 each, seg_start K+1
+ * int32, scratch meb200_pair_list_scratch_bytes(K, n_rows) bytes. */
+uint64_t meb200_pair_list_scratch_bytes(uint32_t K, uint32_t n_rows);
+uint64_t meb200_pair_list_capacity(uint32_t K, uint32_t n_rows, uint32_t stage);
+int meb200_kernel_map_pairs(const int32_t *nbr, uint32_t K, uint32_t n_rows, uint32_t stage,
+                            int32_t *pairs_other, int32_t *pairs_row, int32_t *seg_start,
+                            void *scratch, void *stream);
+
 /* ---- sparse convolution (reference a8/a9/a10: ConvolutionForwardKernelCPU /
  *      ConvolutionBackwardKernelCPU src/convolution_kernel.hpp:33-144, GPU
  *      src/convolution_kernel.cu:114-496,553-757) ------------------------------------ */
@@ -145,20 +159,37 @@ int meb200_conv_backward(const void *in, const void *grad_out, int dtype, uint32
                          void *workspace, uint64_t workspace_bytes, void *stream);
 
 /* Weight packing for the tensor-core path, once per optimizer step instead of once per call:
- * fp32 master weight [K, Cin, Cout] -> `dtype` (BF16/F16) copies w_cast [K, Cin, Cout] (pass it
- * as `weight` to meb200_conv_backward) and w_t [K, Cout, Cin] (for meb200_conv_forward_packed).
- * The reference keeps weights in the feature dtype and needs no such step
+ * fp32 master weight [K, Cin, Cout] -> `dtype` (BF16/F16) operand copies
+ *   w_cast [K, Cin, Cout]                 w_t  [K, Cout, Cin]
+ *   w_cp   [K, Cin, perm(Cout)]           w_tp [K, Cout, perm(Cin)]
+ * where perm reorders the reduction axis inside every block of 32 channels to the order in
+ * which the A-in-tensor-memory kernel lays gathered rows out (position 16h+4j+2e+b holds
+ * channel 8j+4h+2e+b).  w_cp / w_tp may be NULL and are skipped when Cout / Cin is not a
+ * multiple of 32.  The reference keeps weights in the feature dtype and needs no such step
  * (MinkowskiConvolution.py:264-279); this is the bf16/fp16 operand cache of this backend. */
 int meb200_conv_pack_weights(const float *weight, uint32_t K, uint32_t c_in, uint32_t c_out,
-                             int dtype, void *w_cast, void *w_t, void *stream);
+                             int dtype, void *w_cast, void *w_t, void *w_cp, void *w_tp,
+                             void *stream);
 
-/* meb200_conv_forward with the weight already packed as w_t [K, Cout, Cin] (tensor-core path
- * only: returns MEB200_ERR_UNSUPPORTED for shapes/dtypes outside it, the caller then uses
- * meb200_conv_forward).  Same result, no per-call cast/transpose, no workspace. */
+/* meb200_conv_forward with the weight already packed (tensor-core path only: returns
+ * MEB200_ERR_UNSUPPORTED for shapes/dtypes outside it, the caller then uses
+ * meb200_conv_forward).  Same result, no per-call cast/transpose, no workspace.
+ * weight_tp (may be NULL) selects the A-in-tensor-memory kernel when Cin % 32 == 0. */
 int meb200_conv_forward_packed(const void *in, int in_dtype, uint32_t n_in, uint32_t c_in,
-                               const void *weight_t, uint32_t K, uint32_t c_out,
-                               const int32_t *out_nbr, uint32_t n_out, void *out, int out_dtype,
-                               void *stream);
+                               const void *weight_t, const void *weight_tp, uint32_t K,
+                               uint32_t c_out, const int32_t *out_nbr, uint32_t n_out, void *out,
+                               int out_dtype, void *stream);
+
+/* meb200_conv_backward on packed weights (w_cast, and w_cp or NULL), tensor-core path only;
+ * grad_in / grad_weight may be NULL to skip dgrad / wgrad.  pairs_in / pairs_out / seg_start
+ * (all three or NULL): the compacted pair lists of out_nbr from meb200_kernel_map_pairs with
+ * stage = 64; with them wgrad reduces over valid pairs only instead of the dense table. */
+int meb200_conv_backward_packed(const void *in, const void *grad_out, int dtype, uint32_t n_in,
+                                uint32_t c_in, const void *w_cast, const void *w_cp, uint32_t K,
+                                uint32_t c_out, const int32_t *out_nbr, const int32_t *in_nbr,
+                                uint32_t n_out, void *grad_in, int grad_in_dtype,
+                                float *grad_weight, const int32_t *pairs_in,
+                                const int32_t *pairs_out, const int32_t *seg_start, void *stream);
 
 /* Workspace the two calls above may use (0 is legal: slower fallbacks are chosen). */
 uint64_t meb200_conv_workspace_bytes(uint32_t n_in, uint32_t n_out, uint32_t c_in,

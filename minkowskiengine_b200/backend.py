@@ -160,12 +160,39 @@ class _KernelMap:
     Replaces gpu_kernel_map's three flat arrays + host offset table (src/kernel_map.cuh:48-429);
     `swapped()` is the reference's swap_in_out (kernel_map.cuh:191-241)."""
 
-    __slots__ = ("out_nbr", "in_nbr", "stride_pairs", "_n_pairs")
+    __slots__ = ("out_nbr", "in_nbr", "stride_pairs", "_n_pairs", "_pairs", "_pair_src")
+    PAIR_STAGE = 64   # pairs per pipeline stage of the wgrad kernel (k_wgrad_pairs)
 
     def __init__(self, out_nbr, in_nbr, stride_pairs=None):
         self.out_nbr, self.in_nbr = out_nbr, in_nbr
         self.stride_pairs = stride_pairs  # (in_rows, out_rows) when built as a stride map
         self._n_pairs = None
+        self._pairs = None      # (pairs_in, pairs_out, seg_start) once built
+        self._pair_src = None   # the map this one is the swapped view of
+
+    def pair_lists(self):
+        """(pairs_in, pairs_out, seg_start): per-offset compacted (input row, output row) lists
+        padded to PAIR_STAGE entries per offset (meb200_kernel_map_pairs) — the reference's own
+        kernel-map representation.  Built on first use; a swapped view shares its source's lists
+        with the two sides exchanged."""
+        if self._pairs is None:
+            if self._pair_src is not None:
+                pin, pout, seg = self._pair_src.pair_lists()
+                self._pairs = (pout, pin, seg)
+                return self._pairs
+            lib = _lib.load()
+            K, n = self.out_nbr.shape
+            dev = self.out_nbr.device
+            cap = int(lib.meb200_pair_list_capacity(K, n, self.PAIR_STAGE))
+            pairs = torch.empty((2, cap), dtype=torch.int32, device=dev)
+            seg = torch.empty(K + 1, dtype=torch.int32, device=dev)
+            scratch = torch.empty(int(lib.meb200_pair_list_scratch_bytes(K, n)), dtype=torch.uint8,
+                                  device=dev)
+            _lib.check(lib.meb200_kernel_map_pairs(
+                _lib.ptr(self.out_nbr), K, n, self.PAIR_STAGE, _lib.ptr(pairs[0]),
+                _lib.ptr(pairs[1]), _lib.ptr(seg), _lib.ptr(scratch), _lib.current_stream()))
+            self._pairs = (pairs[0], pairs[1], seg)   # other side = input rows, row = output rows
+        return self._pairs
 
     @property
     def n_pairs(self):
@@ -190,6 +217,7 @@ class _KernelMap:
         sp = None if self.stride_pairs is None else (self.stride_pairs[1], self.stride_pairs[0])
         km = _KernelMap(self.in_nbr, self.out_nbr, sp)
         km._n_pairs = self._n_pairs
+        km._pair_src = self
         return km
 
     def to_dict(self):
@@ -552,25 +580,31 @@ _ERR_UNSUPPORTED = -3
 
 
 def _packed_weights(kernel, dtype):
-    """(w_cast [K,Cin,Cout], w_t [K,Cout,Cin]) of an fp32 master weight in `dtype`, rebuilt only
-    when the tensor was modified in place (its autograd version counter moved) or replaced."""
+    """(w_cast [K,Cin,Cout], w_t [K,Cout,Cin], w_cp, w_tp) of an fp32 master weight in `dtype`
+    (w_cp / w_tp: the k_conv_ta layouts, None when the reduction width is not a multiple of 32),
+    rebuilt only when the tensor was modified in place (its autograd version counter moved) or
+    replaced."""
     key = id(kernel)
     ent = _PACKED.get(key)
     if ent is not None and ent[0]() is kernel and ent[1] == kernel._version \
             and ent[2] == kernel.data_ptr() and ent[3] == dtype:
-        return ent[4], ent[5]
+        return ent[4]
     lib = _lib.load()
     K, c_in, c_out = kernel.shape
     src = kernel.detach()
-    w_cast = torch.empty((K, c_in, c_out), dtype=dtype, device=kernel.device)
-    w_t = torch.empty((K, c_out, c_in), dtype=dtype, device=kernel.device)
-    _lib.check(lib.meb200_conv_pack_weights(_lib.ptr(src), K, c_in, c_out, _lib.dtype_code(dtype),
-                                            _lib.ptr(w_cast), _lib.ptr(w_t), _lib.current_stream()))
+    buf = torch.empty((4, K * c_in * c_out), dtype=dtype, device=kernel.device)
+    w_cast, w_t = buf[0].view(K, c_in, c_out), buf[1].view(K, c_out, c_in)
+    w_cp = buf[2].view(K, c_in, c_out) if c_out % 32 == 0 else None
+    w_tp = buf[3].view(K, c_out, c_in) if c_in % 32 == 0 else None
+    _lib.check(lib.meb200_conv_pack_weights(
+        _lib.ptr(src), K, c_in, c_out, _lib.dtype_code(dtype), _lib.ptr(w_cast), _lib.ptr(w_t),
+        _lib.ptr(w_cp), _lib.ptr(w_tp), _lib.current_stream()))
     if len(_PACKED) > 4096:      # dead entries of discarded networks
         for k in [k for k, e in _PACKED.items() if e[0]() is None]:
             del _PACKED[k]
-    _PACKED[key] = (weakref.ref(kernel), kernel._version, kernel.data_ptr(), dtype, w_cast, w_t)
-    return w_cast, w_t
+    packed = (w_cast, w_t, w_cp, w_tp)
+    _PACKED[key] = (weakref.ref(kernel), kernel._version, kernel.data_ptr(), dtype, packed)
+    return packed
 
 
 def _can_pack(kernel, feat_dtype):
@@ -584,11 +618,11 @@ def _conv_forward_impl(in_feat, kernel, km, out_dtype=None):
     if _can_pack(kernel, in_feat.dtype):
         K, c_in, c_out = kernel.shape
         _assert(K == km.K, "kernel volume", K, "does not match the kernel map", km.K)
-        _, w_t = _packed_weights(kernel, in_feat.dtype)
+        _, w_t, _, w_tp = _packed_weights(kernel, in_feat.dtype)
         out = torch.empty((km.n_out, c_out), dtype=out_dtype or in_feat.dtype,
                           device=in_feat.device)
         rc = lib.meb200_conv_forward_packed(
-            _lib.ptr(in_feat), code, km.n_in, c_in, _lib.ptr(w_t), K, c_out,
+            _lib.ptr(in_feat), code, km.n_in, c_in, _lib.ptr(w_t), _lib.ptr(w_tp), K, c_out,
             _lib.ptr(km.out_nbr), km.n_out, _lib.ptr(out), _lib.dtype_code(out.dtype),
             _lib.current_stream())
         if rc != _ERR_UNSUPPORTED:
@@ -634,17 +668,27 @@ def _conv_backward_impl(in_feat, grad_out, kernel, km, need_in=True, need_w=True
     if grad_out.dtype != in_feat.dtype:
         grad_out = grad_out.to(in_feat.dtype)
     grad_out = grad_out.contiguous()
-    if _can_pack(kernel, in_feat.dtype):
-        w, _ = _packed_weights(kernel, in_feat.dtype)
-    else:
-        w = kernel if kernel.dtype == in_feat.dtype else kernel.to(in_feat.dtype)
-        w = w.contiguous()
-    K, c_in, c_out = w.shape
+    K, c_in, c_out = kernel.shape
     n_out, n_in = km.n_out, km.n_in
     grad_in = torch.empty((n_in, c_in), dtype=in_feat.dtype, device=in_feat.device) \
         if need_in else None
     grad_w = torch.empty((K, c_in, c_out), dtype=torch.float32, device=in_feat.device) \
         if need_w else None
+    if _can_pack(kernel, in_feat.dtype):
+        w, _, w_cp, _ = _packed_weights(kernel, in_feat.dtype)
+        pin = pout = seg = None
+        if need_w and c_in % 8 == 0 and c_in >= 16 and K <= 1023:
+            pin, pout, seg = km.pair_lists()
+        rc = lib.meb200_conv_backward_packed(
+            _lib.ptr(in_feat), _lib.ptr(grad_out), code, n_in, c_in, _lib.ptr(w), _lib.ptr(w_cp),
+            K, c_out, _lib.ptr(km.out_nbr), _lib.ptr(km.in_nbr), n_out, _lib.ptr(grad_in), code,
+            _lib.ptr(grad_w), _lib.ptr(pin), _lib.ptr(pout), _lib.ptr(seg), _lib.current_stream())
+        if rc != _ERR_UNSUPPORTED:
+            _lib.check(rc)
+            return grad_in, grad_w
+    else:
+        w = kernel if kernel.dtype == in_feat.dtype else kernel.to(in_feat.dtype)
+        w = w.contiguous()
     ws, ws_bytes = _workspace(n_in, n_out, c_in, c_out, K, code, in_feat.device)
     _lib.check(lib.meb200_conv_backward(
         _lib.ptr(in_feat), _lib.ptr(grad_out), code, n_in, c_in, _lib.ptr(w), K, c_out,

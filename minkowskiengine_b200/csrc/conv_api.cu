@@ -54,17 +54,19 @@ int meb200_conv_forward(const void *in, int in_dtype, uint32_t n_in, uint32_t c_
 }
 
 int meb200_conv_pack_weights(const float *weight, uint32_t K, uint32_t c_in, uint32_t c_out,
-                             int dtype, void *w_cast, void *w_t, void *stream_) {
+                             int dtype, void *w_cast, void *w_t, void *w_cp, void *w_tp,
+                             void *stream_) {
   MEB_CHECK_ARG(dtype == MEB200_BF16 || dtype == MEB200_F16, "packed weights are bf16 or fp16");
   MEB_CHECK_ARG(weight && w_cast && w_t, "null buffer");
   MEB_CHECK_ARG(c_in > 0 && c_out > 0 && K > 0 && K <= 65535, "empty channel/kernel dims");
-  return conv_pack_weights(weight, K, c_in, c_out, dtype, w_cast, w_t, (cudaStream_t)stream_);
+  return conv_pack_weights(weight, K, c_in, c_out, dtype, w_cast, w_t, w_cp, w_tp,
+                           (cudaStream_t)stream_);
 }
 
 int meb200_conv_forward_packed(const void *in, int in_dtype, uint32_t n_in, uint32_t c_in,
-                               const void *weight_t, uint32_t K, uint32_t c_out,
-                               const int32_t *out_nbr, uint32_t n_out, void *out, int out_dtype,
-                               void *stream_) {
+                               const void *weight_t, const void *weight_tp, uint32_t K,
+                               uint32_t c_out, const int32_t *out_nbr, uint32_t n_out, void *out,
+                               int out_dtype, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (n_out == 0) return MEB200_OK;
   MEB_CHECK_ARG(in_dtype >= 0 && in_dtype <= 2 && out_dtype >= 0 && out_dtype <= 2, "dtype");
@@ -76,9 +78,54 @@ int meb200_conv_forward_packed(const void *in, int in_dtype, uint32_t n_in, uint
     set_error("packed forward: shape/dtype outside the tensor-core path");
     return MEB200_ERR_UNSUPPORTED;
   }
-  // W^T[k][c_out][c_in] is operand B as the kernel wants it: the "no transpose" entry
+  // W^T[k][c_out][c_in] is operand B as the kernels want it: the "no transpose" entry
   return conv_forward_tc(in, in_dtype, n_in, c_in, weight_t, K, c_out, /*dgrad=*/true, out_nbr,
-                         n_out, out, out_dtype, nullptr, stream);
+                         n_out, out, out_dtype, nullptr, stream, nullptr,
+                         c_in % 32 == 0 ? weight_tp : nullptr);
+}
+
+int meb200_conv_backward_packed(const void *in, const void *grad_out, int dtype, uint32_t n_in,
+                                uint32_t c_in, const void *w_cast, const void *w_cp, uint32_t K,
+                                uint32_t c_out, const int32_t *out_nbr, const int32_t *in_nbr,
+                                uint32_t n_out, void *grad_in, int grad_in_dtype,
+                                float *grad_weight, const int32_t *pairs_in,
+                                const int32_t *pairs_out, const int32_t *seg_start,
+                                void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MEB_CHECK_ARG(dtype == MEB200_BF16 || dtype == MEB200_F16, "packed backward is bf16 or fp16");
+  MEB_CHECK_ARG(grad_in_dtype == MEB200_F32 || grad_in_dtype == dtype,
+                "grad_in dtype must be fp32 or the feature dtype");
+  MEB_CHECK_ARG(c_in > 0 && c_out > 0 && K > 0, "empty channel/kernel dims");
+  // all-or-nothing: decide before anything is launched, the caller falls back as a whole
+  if (tc_disabled() ||
+      (grad_in != nullptr && n_in > 0 && !conv_tc_supported(dtype, c_out, c_in)) ||
+      (grad_weight != nullptr && !conv_wgrad_tc_supported(dtype, c_in, c_out))) {
+    set_error("packed backward: shape outside the tensor-core path");
+    return MEB200_ERR_UNSUPPORTED;
+  }
+  if (grad_in != nullptr && n_in > 0) {
+    MEB_CHECK_ARG(in_nbr && w_cast && (grad_out || n_out == 0), "null buffer");
+    int rc = conv_forward_tc(grad_out, dtype, n_out, c_out, w_cast, K, c_in, /*dgrad=*/true, in_nbr,
+                             n_in, grad_in, grad_in_dtype, nullptr, stream, nullptr,
+                             c_out % 32 == 0 ? w_cp : nullptr);
+    if (rc != MEB200_OK) return rc;
+  }
+  if (grad_weight != nullptr) {
+    MEB_CHECK_ARG(out_nbr && (in || n_in == 0) && (grad_out || n_out == 0), "null buffer");
+    static int use_pairs = -1;    // MEB200_TC_WGRAD=dense keeps the round-1 dense kernel
+    if (use_pairs < 0) {
+      const char *e = getenv("MEB200_TC_WGRAD");
+      use_pairs = (e && e[0] == 'd') ? 0 : 1;
+    }
+    if (use_pairs && pairs_in && pairs_out && seg_start &&
+        conv_wgrad_pairs_supported(dtype, c_in, K, c_out)) {
+      int rc = conv_wgrad_pairs(in, grad_out, dtype, c_in, K, c_out, pairs_in, pairs_out,
+                                seg_start, n_out, grad_weight, stream);
+      if (rc != MEB200_ERR_UNSUPPORTED) return rc;
+    }
+    return conv_wgrad_tc(in, grad_out, dtype, c_in, K, c_out, out_nbr, n_out, grad_weight, stream);
+  }
+  return MEB200_OK;
 }
 
 int meb200_conv_forward_ordered(const void *in, int in_dtype, uint32_t n_in, uint32_t c_in,

@@ -859,13 +859,19 @@ k_transpose_w(const T *__restrict__ W, T *__restrict__ Wb, uint32_t c_in, uint32
     if (co0 + i < c_out && ci0 + tx < c_in) Wbk[(size_t)(co0 + i) * c_in + ci0 + tx] = tile[tx][i];
 }
 
-// Per-optimizer-step weight packing: fp32 master W[k][ci][co] -> feature dtype, both as
-// W[k][ci][co] (operand B of the dgrad kernel) and W^T[k][co][ci] (operand B of the forward
-// kernel), in one pass.  Replaces a torch cast plus k_transpose_w on EVERY forward call.
+// Per-optimizer-step weight packing: fp32 master W[k][ci][co] -> feature dtype in the four
+// operand-B layouts of the tensor-core kernels, in one pass (replaces a torch cast plus
+// k_transpose_w on EVERY forward call):
+//   Wc  [k][ci][co]          dgrad, k_conv_rs          Wt  [k][co][ci]          forward, k_conv_rs
+//   Wcp [k][ci][perm(co)]    dgrad, k_conv_ta          Wtp [k][co][perm(ci)]    forward, k_conv_ta
+// perm = the order in which k_conv_ta's producers lay a 32-channel block out in tensor memory.
+__host__ __device__ constexpr uint32_t ta_perm(uint32_t pos) {   // position -> channel, within 32
+  return 8u * ((pos >> 2) & 3u) + 4u * ((pos >> 4) & 1u) + (pos & 3u);
+}
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_pack_w(const float *__restrict__ W, T *__restrict__ Wc, T *__restrict__ Wt, uint32_t c_in,
-         uint32_t c_out) {
+k_pack_w(const float *__restrict__ W, T *__restrict__ Wc, T *__restrict__ Wt, T *__restrict__ Wcp,
+         T *__restrict__ Wtp, uint32_t c_in, uint32_t c_out) {
   __shared__ float tile[32][33];
   const size_t base = (size_t)blockIdx.z * c_in * c_out;
   const uint32_t ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
@@ -877,19 +883,29 @@ k_pack_w(const float *__restrict__ W, T *__restrict__ Wc, T *__restrict__ Wt, ui
       Wc[base + (size_t)(ci0 + i) * c_out + co0 + tx] = from_f32<T>(v);
     }
   __syncthreads();
-  for (uint32_t i = ty; i < 32; i += 8)
+  const uint32_t px = ta_perm(tx);
+  for (uint32_t i = ty; i < 32; i += 8) {
     if (co0 + i < c_out && ci0 + tx < c_in)
       Wt[base + (size_t)(co0 + i) * c_in + ci0 + tx] = from_f32<T>(tile[tx][i]);
+    if (Wtp != nullptr && co0 + i < c_out)      // c_in % 32 == 0: the tile is a full block
+      Wtp[base + (size_t)(co0 + i) * c_in + ci0 + tx] = from_f32<T>(tile[px][i]);
+    if (Wcp != nullptr && ci0 + i < c_in)       // c_out % 32 == 0
+      Wcp[base + (size_t)(ci0 + i) * c_out + co0 + tx] = from_f32<T>(tile[i][px]);
+  }
 }
 
 int conv_pack_weights(const float *W, uint32_t K, uint32_t c_in, uint32_t c_out, int dtype,
-                      void *w_cast, void *w_t, cudaStream_t stream) {
+                      void *w_cast, void *w_t, void *w_cp, void *w_tp, cudaStream_t stream) {
+  if (c_out % 32 != 0) w_cp = nullptr;
+  if (c_in % 32 != 0) w_tp = nullptr;
   dim3 grid(cdiv(c_out, 32), cdiv(c_in, 32), K);
   if (dtype == MEB200_BF16)
-    k_pack_w<__nv_bfloat16><<<grid, 256, 0, stream>>>(W, (__nv_bfloat16 *)w_cast,
-                                                      (__nv_bfloat16 *)w_t, c_in, c_out);
+    k_pack_w<__nv_bfloat16><<<grid, 256, 0, stream>>>(
+        W, (__nv_bfloat16 *)w_cast, (__nv_bfloat16 *)w_t, (__nv_bfloat16 *)w_cp,
+        (__nv_bfloat16 *)w_tp, c_in, c_out);
   else
-    k_pack_w<__half><<<grid, 256, 0, stream>>>(W, (__half *)w_cast, (__half *)w_t, c_in, c_out);
+    k_pack_w<__half><<<grid, 256, 0, stream>>>(W, (__half *)w_cast, (__half *)w_t, (__half *)w_cp,
+                                               (__half *)w_tp, c_in, c_out);
   MEB_LAUNCH_OK();
   return MEB200_OK;
 }
@@ -927,6 +943,15 @@ static int make_map_2d(CUtensorMap *m, int dtype, const void *base, uint64_t row
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
     return MEB200_ERR_UNSUPPORTED;
+  }
+  // cuTensorMapEncodeTiled is a DRIVER call: it needs a context current on the calling thread.
+  // Runtime calls bind the primary context implicitly, driver calls do not, and autograd's
+  // backward threads may reach this point before any runtime call (observed: error 201 from
+  // the first dgrad of a process).
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    MEB_CUDA(cudaFree(nullptr));
+    ctx_bound = true;
   }
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {cols * 2};
@@ -1159,6 +1184,606 @@ static int launch_tc_slice(const void *A, int dtype, uint32_t n_a, uint32_t c_re
   return launch_tc_bk_r<__half>(bk, R, tma, mA, mB, p, smem_bytes, grid, stream);
 }
 
+// =====================================================================================
+// Operand A in TENSOR MEMORY (k_conv_ta): the default forward/dgrad kernel for bf16/fp16 features
+// whose reduction width is a multiple of 32 channels.
+//
+// k_conv_rs stages the gathered rows in shared memory; per (tile, offset) stage that costs a
+// 24 KB zero fill, the valid rows, and the tensor core reading A and B back — ~82 KB of shared
+// memory traffic against 288 cycles of tensor time on the 96-channel layers (profiles/r1_notes.md).
+// Here the gathered rows never touch shared memory:
+//   producers : 3 groups x 4 warps.  A group owns every 3rd (tile, offset, channel chunk) stage;
+//               its four warps cover the four 32-lane quadrants of tensor memory.  Thread t of a
+//               warp handles rows {t/4, t/4+8, t/4+16, t/4+24} of the quadrant and the t%4-th
+//               16-byte piece of every 64-byte block of those rows: a warp-wide load touches 8
+//               rows x 64 contiguous bytes (the same sector efficiency as a cooperative row copy),
+//               missing neighbours stay zero registers, and `tcgen05.st.16x256b.x2` drops the
+//               registers straight into the A operand (TMEM lane = tile row).
+//   MMA warp  : tcgen05.mma with A from TMEM, B (the packed weights) from shared memory via TMA.
+//   epilogue  : unchanged (tcgen05.ld -> convert -> 16-byte stores).
+// Because four threads share a row, TMEM column c of a 32-channel block does not hold channels
+// (2c, 2c+1): position p = 16h + 4j + 2e + b of the reduction axis holds channel 8j + 4h + 2e + b
+// (h: 8-column group, j: piece/thread, e: word, b: half word).  The reduction order is free as
+// long as B agrees, so the weights are PACKED in that order once per optimizer step
+// (k_pack_w, ta_perm) instead of shuffling registers in the hot loop.
+// =====================================================================================
+constexpr int kTaGroups = 3;
+constexpr int kTaProducerWarps = 4 * kTaGroups;
+// warps [0,12) producers, [12,16) epilogue, 16 MMA, 17 release, 18 B loader
+constexpr int kTaThreads = (kTaProducerWarps + kEpilogueWarps + 3) * 32;
+
+struct TaParams {
+  const void *A;        // [n_a, c_red] gathered operand
+  const int32_t *nbr;   // [K, n_rows]
+  void *out;            // [n_rows, c_cols] (leading dimension out_ld)
+  uint32_t c_red, c_cols, K, n_rows;
+  uint32_t wb_row0, wb_rows_per_k;   // row of this launch's column slice inside one offset of Wb
+  uint32_t n_super, R, acc_sets, nA, nB;
+  uint32_t n_macro;                  // channel chunks (stages) per (tile, offset)
+  uint32_t b_stage_bytes, b_sub_bytes;
+  uint32_t a_col0;                   // first TMEM column of the A slots
+  uint32_t out_f32, out_ld;
+  uint32_t rs;                       // k_conv_ts: row slots of a producer thread's ring
+};
+
+__device__ __forceinline__ void tmem_st_16x256b_x2(uint32_t taddr, uint32_t r0, uint32_t r1,
+                                                   uint32_t r2, uint32_t r3, uint32_t r4,
+                                                   uint32_t r5, uint32_t r6, uint32_t r7) {
+  asm volatile("tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(r4), "r"(r5), "r"(r6), "r"(r7)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// ---- roles shared by the two A-in-TMEM kernels ------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void ta_epilogue(const TaParams &p, uint32_t bar0, uint32_t tmem_base,
+                                            uint32_t q, uint32_t lane) {
+  const uint32_t R = p.R;
+  uint32_t acc = 0, par = 0;
+  for (uint32_t st = blockIdx.x; st < p.n_super; st += gridDim.x) {
+    mbar_wait(bar_tfull(bar0, acc), par);
+    tc_fence_after();
+    for (uint32_t r = 0; r < R; ++r) {
+      const uint32_t row = (st * R + r) * kTileM + q * 32 + lane;
+      const uint32_t col0 = (acc * R + r) * p.c_cols;
+      for (uint32_t c = 0; c < p.c_cols; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((q * 32u) << 16) + col0 + c, v);
+        tmem_ld_wait();
+        if (row < p.n_rows) {
+          if (p.out_f32) {
+            float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) +
+                                                     (size_t)row * p.out_ld + c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                   __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+          } else {
+            uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<T *>(p.out) +
+                                                   (size_t)row * p.out_ld + c);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              uint4 w;
+              w.x = pack2<T>(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]));
+              w.y = pack2<T>(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
+              w.z = pack2<T>(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
+              w.w = pack2<T>(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
+              dst[i] = w;
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    mbar_arrive(bar_tempty(bar0, acc));
+    if (++acc == p.acc_sets) { acc = 0; par ^= 1u; }
+  }
+}
+
+// MMA issuer: the whole warp runs the loop, one elected lane issues (A from TMEM, B from smem)
+template <typename T, int NB, int BK>
+__device__ __forceinline__ void ta_mma(const TaParams &p, uint32_t sB, uint32_t bar0,
+                                       uint32_t tmem_base) {
+  using S = Swz<BK>;
+  constexpr uint32_t KC = 32u * NB, kACols = 16u * NB;
+  constexpr uint32_t kHi = umma_desc_hi(S::kSbo, S::kLayout);
+  const uint32_t R = p.R;
+  const uint32_t idesc = umma_idesc_f16(Fmt<T>::v, kTileM, p.c_cols, 0, 0);
+  const uint32_t b_lo0 = umma_desc_lo(sB, 16);
+  const uint32_t b_inc = p.b_stage_bytes >> 4, b_sub16 = p.b_sub_bytes >> 4;
+  uint32_t b_lo = b_lo0, sa = 0, pha = 0, sb = 0, phb = 0, acc = 0, par = 0;
+  const uint32_t n_groups = p.K * p.n_macro;
+  for (uint32_t st = blockIdx.x; st < p.n_super; st += gridDim.x) {
+    mbar_wait(bar_tempty(bar0, acc), par ^ 1u);
+    tc_fence_after();
+    const uint32_t d0 = tmem_base + acc * R * p.c_cols;
+    for (uint32_t grp = 0; grp < n_groups; ++grp) {
+      mbar_wait(bar_fullB(bar0, sb), phb);
+      for (uint32_t r = 0; r < R; ++r) {
+        mbar_wait(bar_fullA(bar0, sa), pha);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t d = d0 + r * p.c_cols;
+          const uint32_t a = tmem_base + p.a_col0 + sa * kACols;
+#pragma unroll
+          for (int s = 0; s < (int)(KC / 16); ++s) {
+            constexpr int kStepsPerSub = BK / 16;
+            const uint64_t db = pack_desc(b_lo + (s / kStepsPerSub) * b_sub16 + (s % kStepsPerSub) * 2, kHi);
+            umma_f16_ts(d, a + s * 8, db, idesc, s != 0 ? 1u : (grp != 0u));
+          }
+          umma_commit(bar_emptyA(bar0, sa));
+          if (r == R - 1) umma_commit(bar_emptyB(bar0, sb));
+        }
+        __syncwarp();
+        if (++sa == p.nA) { sa = 0; pha ^= 1u; }
+      }
+      b_lo += b_inc;
+      if (++sb == p.nB) { sb = 0; phb ^= 1u; b_lo = b_lo0; }
+    }
+    if (elect_one()) umma_commit(bar_tfull(bar0, acc));
+    __syncwarp();
+    if (++acc == p.acc_sets) { acc = 0; par ^= 1u; }
+  }
+}
+
+// consumes the A-slot "empty" completions strictly in order and publishes a monotonic count
+// (a producer group may run several ring revolutions ahead of a one-bit parity wait)
+__device__ __forceinline__ void ta_release(const TaParams &p, uint32_t bar0,
+                                           volatile uint32_t *consumed, uint32_t total) {
+  uint32_t sa = 0, pha = 0, done = 0;
+  for (uint32_t g = 0; g < total; ++g) {
+    mbar_wait(bar_emptyA(bar0, sa), pha);
+    __threadfence_block();
+    sts_volatile(consumed, ++done);
+    if (++sa == p.nA) { sa = 0; pha ^= 1u; }
+  }
+}
+
+template <int NB, int BK>
+__device__ __forceinline__ void ta_bload(const CUtensorMap *mapB, const TaParams &p, uint32_t sB,
+                                         uint32_t bar0) {
+  constexpr uint32_t KC = 32u * NB;
+  tma_prefetch_desc(mapB);
+  uint32_t sb = 0, phb = 0;
+  for (uint32_t st = blockIdx.x; st < p.n_super; st += gridDim.x) {
+    for (uint32_t k = 0; k < p.K; ++k) {
+      const int32_t brow = (int32_t)(k * p.wb_rows_per_k + p.wb_row0);
+      for (uint32_t mc = 0; mc < p.n_macro; ++mc) {
+        mbar_wait(bar_emptyB(bar0, sb), phb ^ 1u);
+        mbar_arrive_expect_tx(bar_fullB(bar0, sb), KC * p.c_cols * 2);
+        const uint32_t dstB = sB + sb * p.b_stage_bytes;
+#pragma unroll
+        for (int sub = 0; sub < (int)(KC / BK); ++sub)
+          tma_load_2d(dstB + sub * p.b_sub_bytes, mapB, (int32_t)(mc * KC + sub * BK), brow,
+                      bar_fullB(bar0, sb));
+        if (++sb == p.nB) { sb = 0; phb ^= 1u; }
+      }
+    }
+  }
+}
+
+// position of a producer in the stage sequence g -> (super tile, offset, channel chunk, row tile),
+// advanced without divisions
+struct TaPos {
+  uint32_t st, k, mc, r;
+  __device__ __forceinline__ void init(uint32_t g, uint32_t R, uint32_t n_macro, uint32_t K) {
+    const uint32_t SPK = n_macro * R, SPS = K * SPK;
+    const uint32_t t = g / SPS, rem = g - t * SPS;
+    st = blockIdx.x + t * gridDim.x;
+    k = rem / SPK;
+    const uint32_t rem2 = rem - k * SPK;
+    mc = rem2 / R;
+    r = rem2 - mc * R;
+  }
+  __device__ __forceinline__ void advance(uint32_t by, uint32_t R, uint32_t n_macro, uint32_t K) {
+    r += by;
+    while (r >= R) {
+      r -= R;
+      if (++mc == n_macro) {
+        mc = 0;
+        if (++k == K) { k = 0; st += gridDim.x; }
+      }
+    }
+  }
+};
+
+// ---- v1: gathered rows wait in REGISTERS (3 producer groups, one stage each) -------------------
+// NB = 32-channel blocks per stage (stage = 32 NB channels = 16 NB TMEM columns);
+// BK = channel width of one B sub-tile in shared memory (64 -> 128B swizzle, 32 -> 64B swizzle).
+template <typename T, int NB, int BK>
+__global__ void __launch_bounds__(kTaThreads, 1)
+k_conv_ta(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
+  constexpr uint32_t KC = 32u * NB;            // channels per stage
+  constexpr uint32_t kACols = 16u * NB;        // TMEM columns of one A slot
+  constexpr int NP = kTaProducerWarps;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sB = smem_u32(smem);
+  uint8_t *tail = smem + p.nB * p.b_stage_bytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(tail);
+  const uint32_t bar0 = smem_u32(bars);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * kMaxStages + 4);
+  volatile uint32_t *consumed = reinterpret_cast<volatile uint32_t *>(tail + tc::kBarBytes);
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t R = p.R;
+  const uint32_t SPS = p.K * p.n_macro * R;    // A stages per super tile
+  const uint32_t n_my = p.n_super > blockIdx.x
+                            ? (p.n_super - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const uint32_t total = n_my * SPS;
+
+  if (threadIdx.x == 0) {
+    for (uint32_t i = 0; i < p.nA; ++i) { mbar_init(bar_fullA(bar0, i), 4); mbar_init(bar_emptyA(bar0, i), 1); }
+    for (uint32_t i = 0; i < p.nB; ++i) { mbar_init(bar_fullB(bar0, i), 1); mbar_init(bar_emptyB(bar0, i), 1); }
+    for (uint32_t i = 0; i < 2; ++i) { mbar_init(bar_tfull(bar0, i), 1); mbar_init(bar_tempty(bar0, i), kEpilogueWarps * 32); }
+    mbar_fence_init();
+    consumed[0] = 0;
+  }
+  if (warp == NP + kEpilogueWarps) {
+    tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < NP) {
+    // =============================== PRODUCERS ======================================
+    const uint32_t grp = warp >> 2, quad = warp & 3u;
+    const uint32_t piece = lane & 3u, rsub = lane >> 2;
+    const T *A = reinterpret_cast<const T *>(p.A);
+    TaPos cur, nxt;
+    cur.init(grp, R, p.n_macro, p.K);
+    nxt = cur;
+    // lane l fetches the neighbour of row l of this warp's quadrant (one coalesced 128-byte read)
+    auto load_idx = [&](const TaPos &q) -> int32_t {
+      const uint32_t grow = (q.st * R + q.r) * kTileM + quad * 32 + lane;
+      return grow < p.n_rows ? __ldg(p.nbr + (size_t)q.k * p.n_rows + grow) : -1;
+    };
+    uint32_t g = grp, slot = grp % p.nA;
+    int32_t idx_cur = g < total ? load_idx(cur) : -1, idx_nxt = -1;
+    for (; g < total; g += kTaGroups) {
+      nxt.advance(kTaGroups, R, p.n_macro, p.K);
+      if (g + kTaGroups < total) idx_nxt = load_idx(nxt);
+      const T *src0 = A + cur.mc * KC + piece * 8;
+      // rows m = 2*half + hi  ->  quadrant row half*16 + hi*8 + rsub
+      uint4 v[4][NB];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int32_t srow = __shfl_sync(0xffffffffu, idx_cur, (m >> 1) * 16 + (m & 1) * 8 + (int)rsub);
+        if (srow >= 0) {
+          const T *src = src0 + (size_t)srow * p.c_red;
+#pragma unroll
+          for (int b = 0; b < NB; ++b) v[m][b] = ldg128(src + b * 32);
+        } else {
+#pragma unroll
+          for (int b = 0; b < NB; ++b) v[m][b] = make_uint4(0, 0, 0, 0);
+        }
+      }
+      wait_consumed(consumed, g, p.nA, lane);      // A slot recycled by the tensor core?
+      tc_fence_after();
+      const uint32_t ta = tmem_base + p.a_col0 + slot * kACols + ((quad * 32u) << 16);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          const uint4 lo = v[2 * half][b], hi = v[2 * half + 1][b];
+          tmem_st_16x256b_x2(ta + ((uint32_t)(half * 16) << 16) + b * 16,
+                             lo.x, lo.y, hi.x, hi.y, lo.z, lo.w, hi.z, hi.w);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_fullA(bar0, slot));
+      idx_cur = idx_nxt;
+      cur = nxt;
+      slot = (slot + kTaGroups) % p.nA;
+    }
+  } else if (warp < NP + kEpilogueWarps) {
+    ta_epilogue<T>(p, bar0, tmem_base, warp & 3u, lane);
+  } else if (warp == NP + kEpilogueWarps) {
+    ta_mma<T, NB, BK>(p, sB, bar0, tmem_base);
+  } else if (warp == NP + kEpilogueWarps + 1) {
+    if (lane == 0) ta_release(p, bar0, consumed, total);
+  } else {
+    if (lane == 0) ta_bload<NB, BK>(&mapB, p, sB, bar0);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == NP + kEpilogueWarps) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---- v2: gathered rows wait in SHARED MEMORY, one private ring per thread ----------------------
+// v1 keeps 3 stages x ~7.6 KB of useful loads in flight per SM; measured (profiles/r2_notes.md)
+// that leaves a stage at ~1200 cycles, the gather latency under load, against 288 cycles of
+// tensor time.  Here a producer thread copies its VALID rows with cp.async into a private ring
+// of RS row slots (layout [block][slot][lane] x 16 B: conflict free for the copies and for the
+// 128-bit reads back), runs up to kTsDepth stages ahead, and only then moves a landed stage
+// smem -> registers -> tensor memory.  Two groups of 4 warps alternate stages; missing rows take
+// no ring space, so the ring holds ~8 stages of useful bytes per group.
+constexpr int kTsGroups = 2;
+constexpr int kTsProducerWarps = 4 * kTsGroups;
+constexpr int kTsThreads = (kTsProducerWarps + kEpilogueWarps + 3) * 32;
+constexpr uint32_t kTsDepth = 8;             // stage descriptors / landing barriers per warp
+
+template <typename T, int NB, int BK>
+__global__ void __launch_bounds__(kTsThreads, 1)
+k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
+  constexpr uint32_t KC = 32u * NB;
+  constexpr uint32_t kACols = 16u * NB;
+  constexpr int NP = kTsProducerWarps;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sB = smem_u32(smem);
+  const uint32_t ring_bytes = NB * p.rs * 512u;                      // per producer warp
+  uint8_t *rings = smem + p.nB * p.b_stage_bytes;
+  uint8_t *tail = rings + NP * ring_bytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(tail);
+  const uint32_t bar0 = smem_u32(bars);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * kMaxStages + 4);
+  volatile uint32_t *consumed = reinterpret_cast<volatile uint32_t *>(tail + tc::kBarBytes);
+  uint64_t *landed_all = reinterpret_cast<uint64_t *>(tail + tc::kBarBytes + 64);   // [NP][kTsDepth]
+  uint32_t *desc_all = reinterpret_cast<uint32_t *>(landed_all + NP * kTsDepth);    // [NP][kTsDepth][32]
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t R = p.R;
+  const uint32_t SPS = p.K * p.n_macro * R;
+  const uint32_t n_my = p.n_super > blockIdx.x
+                            ? (p.n_super - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const uint32_t total = n_my * SPS;
+
+  if (threadIdx.x == 0) {
+    for (uint32_t i = 0; i < p.nA; ++i) { mbar_init(bar_fullA(bar0, i), 4); mbar_init(bar_emptyA(bar0, i), 1); }
+    for (uint32_t i = 0; i < p.nB; ++i) { mbar_init(bar_fullB(bar0, i), 1); mbar_init(bar_emptyB(bar0, i), 1); }
+    for (uint32_t i = 0; i < 2; ++i) { mbar_init(bar_tfull(bar0, i), 1); mbar_init(bar_tempty(bar0, i), kEpilogueWarps * 32); }
+    for (uint32_t i = 0; i < NP * kTsDepth; ++i) mbar_init(smem_u32(landed_all + i), 32);
+    mbar_fence_init();
+    consumed[0] = 0;
+  }
+  if (warp == NP + kEpilogueWarps) {
+    tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < NP) {
+    // =============================== PRODUCERS ======================================
+    const uint32_t grp = warp >> 2, quad = warp & 3u;
+    const uint32_t piece = lane & 3u, rsub = lane >> 2;
+    const T *A = reinterpret_cast<const T *>(p.A) + piece * 8;
+    const uint32_t ring = smem_u32(rings + warp * ring_bytes) + lane * 16;   // + (b*RS + slot)*512
+    const uint32_t landed = smem_u32(landed_all + warp * kTsDepth);
+    uint32_t *desc = desc_all + warp * kTsDepth * 32 + lane;                 // + d * 32
+    const uint32_t RS = p.rs;
+    // stages of this group: j = 0, 1, ...  <->  g = grp + kTsGroups * j
+    const uint32_t n_j = total > grp ? (total - grp + kTsGroups - 1) / kTsGroups : 0;
+    TaPos pis, ppf;                   // position of the next stage to issue / to prefetch indices for
+    pis.init(grp, R, p.n_macro, p.K);
+    ppf = pis;
+    auto load_idx = [&](const TaPos &q, uint32_t j) -> int32_t {
+      const uint32_t grow = (q.st * R + q.r) * kTileM + quad * 32 + lane;
+      return (j < n_j && grow < p.n_rows) ? __ldg(p.nbr + (size_t)q.k * p.n_rows + grow) : -1;
+    };
+    int32_t i0 = load_idx(ppf, 0);
+    ppf.advance(kTsGroups, R, p.n_macro, p.K);
+    int32_t i1 = load_idx(ppf, 1);
+    ppf.advance(kTsGroups, R, p.n_macro, p.K);
+    int32_t i2 = load_idx(ppf, 2);
+    uint32_t head = 0, tail_j = 0;           // consumed / issued stage counts of this group
+    uint32_t wr = 0, used = 0;               // this lane's ring: next slot, slots in use
+    uint32_t g_head = grp, slot_head = grp % p.nA;
+    while (head < n_j) {
+      // ---- run ahead: issue the copies of further stages while every lane has ring space ----
+      while (tail_j < n_j && tail_j - head < kTsDepth) {
+        int32_t srow[4];
+        uint32_t nv = 0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          srow[m] = __shfl_sync(0xffffffffu, i0, (m >> 1) * 16 + (m & 1) * 8 + (int)rsub);
+          nv += srow[m] >= 0;
+        }
+        if (!__all_sync(0xffffffffu, used + nv <= RS)) break;
+        const uint32_t d = tail_j % kTsDepth;
+        const T *src0 = A + pis.mc * KC;
+        uint32_t dw = 0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          uint32_t code = 0xffu;
+          if (srow[m] >= 0) {
+            code = wr;
+            const T *src = src0 + (size_t)srow[m] * p.c_red;
+            const uint32_t dst = ring + wr * 512u;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) cp_async16(dst + b * RS * 512u, src + b * 32, 16);
+            if (++wr == RS) wr = 0;
+          }
+          dw |= code << (8 * m);
+        }
+        used += nv;
+        desc[d * 32] = dw;
+        cp_async_mbar_arrive(landed + d * 8);
+        ++tail_j;
+        pis.advance(kTsGroups, R, p.n_macro, p.K);
+        ppf.advance(kTsGroups, R, p.n_macro, p.K);
+        i0 = i1; i1 = i2;
+        i2 = load_idx(ppf, tail_j + 2);
+      }
+      // ---- move the oldest landed stage: shared memory -> registers -> tensor memory ----------
+      {
+        const uint32_t d = head % kTsDepth;
+        mbar_wait(landed + d * 8, (head / kTsDepth) & 1u);
+        const uint32_t dw = desc[d * 32];
+        uint4 v[4][NB];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const uint32_t code = (dw >> (8 * m)) & 0xffu;
+          if (code != 0xffu) {
+            const uint32_t src = ring + code * 512u;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(v[m][b].x), "=r"(v[m][b].y), "=r"(v[m][b].z), "=r"(v[m][b].w)
+                           : "r"(src + b * RS * 512u));
+            }
+            --used;
+          } else {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) v[m][b] = make_uint4(0, 0, 0, 0);
+          }
+        }
+        wait_consumed(consumed, g_head, p.nA, lane);      // A slot recycled by the tensor core?
+        tc_fence_after();
+        const uint32_t ta = tmem_base + p.a_col0 + slot_head * kACols + ((quad * 32u) << 16);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            const uint4 lo = v[2 * half][b], hi = v[2 * half + 1][b];
+            tmem_st_16x256b_x2(ta + ((uint32_t)(half * 16) << 16) + b * 16,
+                               lo.x, lo.y, hi.x, hi.y, lo.z, lo.w, hi.z, hi.w);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_fullA(bar0, slot_head));
+        ++head;
+        g_head += kTsGroups;
+        slot_head = (slot_head + kTsGroups) % p.nA;
+      }
+    }
+    cp_async_wait<0>();
+  } else if (warp < NP + kEpilogueWarps) {
+    ta_epilogue<T>(p, bar0, tmem_base, warp & 3u, lane);
+  } else if (warp == NP + kEpilogueWarps) {
+    ta_mma<T, NB, BK>(p, sB, bar0, tmem_base);
+  } else if (warp == NP + kEpilogueWarps + 1) {
+    if (lane == 0) ta_release(p, bar0, consumed, total);
+  } else {
+    if (lane == 0) ta_bload<NB, BK>(&mapB, p, sB, bar0);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == NP + kEpilogueWarps) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <typename T, int NB, int BK>
+static int launch_ta(const CUtensorMap &mB, const TaParams &p, size_t smem_bytes, unsigned grid,
+                     cudaStream_t stream) {
+  auto kern = k_conv_ta<T, NB, BK>;
+  MEB_BIG_SMEM(kern);
+  kern<<<grid, kTaThreads, smem_bytes, stream>>>(mB, p);
+  count_tc_launch();
+  MEB_LAUNCH_OK();
+  return MEB200_OK;
+}
+template <typename T, int NB, int BK>
+static int launch_ts(const CUtensorMap &mB, const TaParams &p, size_t smem_bytes, unsigned grid,
+                     cudaStream_t stream) {
+  auto kern = k_conv_ts<T, NB, BK>;
+  MEB_BIG_SMEM(kern);
+  kern<<<grid, kTsThreads, smem_bytes, stream>>>(mB, p);
+  count_tc_launch();
+  MEB_LAUNCH_OK();
+  return MEB200_OK;
+}
+
+// forward/dgrad kernel family: 2 = k_conv_ts (A in TMEM, rows staged in shared-memory rings,
+// default), 1 = k_conv_ta (A in TMEM, rows staged in registers), 0 = k_conv_rs (A in shared memory)
+static int ta_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("MEB200_TC_KERNEL");     // "ts" (default) | "ta" | "rs"
+    v = (e && e[0] == 'r') ? 0 : ((e && e[0] == 't' && e[1] == 'a') ? 1 : 2);
+    if (encode_tiled_fn() == nullptr) v = 0;
+  }
+  return v;
+}
+
+// One launch of the A-in-TMEM kernels over output columns [n0, n0 + c_cols) (c_cols <= 256).
+// Wp = PERMUTED packed weights [K, c_cols_full, c_reduce] (reduction axis in ta_perm order).
+static int launch_ta_slice(const void *A, int dtype, uint32_t n_a, uint32_t c_reduce,
+                           const void *Wp_full, uint32_t c_cols_full, uint32_t n0, uint32_t K,
+                           uint32_t c_cols, const int32_t *nbr, uint32_t n_rows, void *out,
+                           uint32_t out_ld, int out_dtype, cudaStream_t stream) {
+  (void)n_a;
+  // MEB200_TA_R / MEB200_TA_ACC: tuning overrides (row tiles per weight stage, accumulator sets)
+  static int force_R = -1, force_acc = -1;
+  if (force_R < 0) {
+    const char *e = getenv("MEB200_TA_R");
+    force_R = e ? atoi(e) : 0;
+    e = getenv("MEB200_TA_ACC");
+    force_acc = e ? atoi(e) : 0;
+  }
+  bool staged = ta_mode() == 2;
+  tc::TaCfg cfg = tc::ta_config(c_reduce, c_cols, n_rows, staged, force_R, force_acc);
+  if (cfg.nb == 0 && (force_R || force_acc)) cfg = tc::ta_config(c_reduce, c_cols, n_rows, staged);
+  if (cfg.nb == 0 && staged) {
+    staged = false;
+    cfg = tc::ta_config(c_reduce, c_cols, n_rows, false);
+  }
+  if (cfg.nb == 0) return MEB200_ERR_UNSUPPORTED;
+  TaParams p{};
+  p.A = A; p.nbr = nbr; p.out = out;
+  p.c_red = c_reduce; p.c_cols = c_cols; p.K = K; p.n_rows = n_rows;
+  p.wb_row0 = n0; p.wb_rows_per_k = c_cols_full;
+  p.n_super = cfg.n_super; p.R = cfg.R; p.acc_sets = cfg.acc_sets; p.nA = cfg.nA; p.nB = cfg.nB;
+  p.n_macro = cfg.n_macro; p.b_stage_bytes = cfg.b_stage_bytes; p.b_sub_bytes = cfg.b_sub_bytes;
+  p.a_col0 = cfg.a_col0; p.out_f32 = out_dtype == MEB200_F32; p.out_ld = out_ld;
+  p.rs = cfg.rs;
+  CUtensorMap mB;
+  memset(&mB, 0, sizeof(mB));
+  int rc = make_map_2d(&mB, dtype, Wp_full, (uint64_t)K * c_cols_full, c_reduce, (uint32_t)cfg.bk, c_cols);
+  if (rc != MEB200_OK) return rc;
+  const unsigned grid = p.n_super < (uint32_t)num_sms() ? p.n_super : (unsigned)num_sms();
+#define MEB_TA(TT)                                                                        \
+  if (staged) {                                                                           \
+    switch (cfg.nb) {                                                                     \
+      case 1: return launch_ts<TT, 1, 32>(mB, p, cfg.smem_bytes, grid, stream);           \
+      case 2: return launch_ts<TT, 2, 64>(mB, p, cfg.smem_bytes, grid, stream);           \
+      case 3: return launch_ts<TT, 3, 32>(mB, p, cfg.smem_bytes, grid, stream);           \
+      case 4: return launch_ts<TT, 4, 64>(mB, p, cfg.smem_bytes, grid, stream);           \
+      default: break;                                                                     \
+    }                                                                                     \
+  } else {                                                                                \
+    switch (cfg.nb) {                                                                     \
+      case 1: return launch_ta<TT, 1, 32>(mB, p, cfg.smem_bytes, grid, stream);           \
+      case 2: return launch_ta<TT, 2, 64>(mB, p, cfg.smem_bytes, grid, stream);           \
+      case 3: return launch_ta<TT, 3, 32>(mB, p, cfg.smem_bytes, grid, stream);           \
+      default: break;                                                                     \
+    }                                                                                     \
+  }
+  if (dtype == MEB200_BF16) { MEB_TA(__nv_bfloat16) } else { MEB_TA(__half) }
+#undef MEB_TA
+  return MEB200_ERR_UNSUPPORTED;
+}
+
 bool conv_tc_supported(int dtype, uint32_t c_reduce, uint32_t c_cols) {
   if (dtype != MEB200_BF16 && dtype != MEB200_F16) return false;
   if (pick_bk(c_reduce) == 0) return false;
@@ -1168,7 +1793,7 @@ bool conv_tc_supported(int dtype, uint32_t c_reduce, uint32_t c_cols) {
 int conv_forward_tc(const void *A, int dtype, uint32_t n_a, uint32_t c_reduce, const void *W,
                     uint32_t K, uint32_t c_cols, bool dgrad, const int32_t *nbr, uint32_t n_rows,
                     void *out, int out_dtype, void *workspace, cudaStream_t stream,
-                    const int32_t *row_ids) {
+                    const int32_t *row_ids, const void *Wperm) {
   if (n_rows == 0) return MEB200_OK;
   MEB_CHECK_ARG(conv_tc_supported(dtype, c_reduce, c_cols), "shape not supported by tc path");
   const uint8_t *Wb = reinterpret_cast<const uint8_t *>(W);
@@ -1187,8 +1812,18 @@ int conv_forward_tc(const void *A, int dtype, uint32_t n_a, uint32_t c_reduce, c
   }
   // operand B is [K, c_cols, c_reduce]; split the column range in slices of <= 256
   const size_t out_esz = out_dtype == MEB200_F32 ? 4 : 2;
+  const bool aligned16 = (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
+                         (reinterpret_cast<uintptr_t>(Wperm) & 15) == 0;
   for (uint32_t n0 = 0; n0 < c_cols; n0 += 256) {
     uint32_t nc = c_cols - n0 < 256 ? c_cols - n0 : 256;
+    if (Wperm != nullptr && row_ids == nullptr && aligned16 && c_reduce % 32 == 0 && ta_mode() != 0) {
+      // operand A in tensor memory: needs the weights packed in ta_perm order
+      int rc = launch_ta_slice(A, dtype, n_a, c_reduce, Wperm, c_cols, n0, K, nc, nbr, n_rows,
+                               reinterpret_cast<uint8_t *>(out) + (size_t)n0 * out_esz, c_cols,
+                               out_dtype, stream);
+      if (rc == MEB200_OK) continue;
+      if (rc != MEB200_ERR_UNSUPPORTED) return rc;
+    }
     int rc = launch_tc_slice(A, dtype, n_a, c_reduce, Wb, c_cols, n0, K, nc, nbr, n_rows,
                              reinterpret_cast<uint8_t *>(out) + (size_t)n0 * out_esz, c_cols,
                              out_dtype, stream, row_ids);
@@ -1665,6 +2300,261 @@ k_wgrad_rs2(const __grid_constant__ CUtensorMap mapG, const Wg2Params p) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
+}
+
+// =====================================================================================
+// wgrad over COMPACTED PAIR LISTS (k_wgrad_pairs, default when the caller provides the lists).
+//
+// The dense kernel above spends 69 % of its stages' rows on zero rows (8.5 of 27 neighbours
+// exist on the bench clouds) and its four producer warps are issue bound (profiles/r2_notes.md).
+// Here the reduction runs over the valid (input row, output row) pairs of one offset at a time
+// (meb200_kernel_map_pairs: per-offset segments padded to whole stages), both operands gathered
+// row by row with cp.async:
+//   stage    = 64 pairs: A = 64 gathered input rows (this CTA's <= 256-channel slice),
+//              B = the 64 matching dOut rows; MN-major 128B-swizzled blocks as above
+//   CTA      = (channel slice, contiguous range of the global stage list); when the range
+//              crosses an offset boundary the accumulator is flushed (red.global.add into
+//              dW[k]) and the next offset starts on the other accumulator set
+//   warps    = 8 producers (8 rows of every stage each; per-thread copy slots are fixed, so a
+//              stage costs one shuffle + one address + one cp.async per 16 bytes), 4 epilogue
+//              warps, 1 MMA warp
+// No zero fill (channels past c_in in the last A block feed accumulator rows nobody reads),
+// no wasted MMAs except the <= 63 pad pairs at the end of each offset.
+// =====================================================================================
+constexpr int kWpRows = 64;
+constexpr int kWpProducerWarps = 8;
+constexpr int kWpThreads = (kWpProducerWarps + kEpilogueWarps + 1) * 32;
+constexpr int kWpMaxSlots = 8;              // 16-byte copies per thread per operand per stage
+constexpr uint32_t kWpMaxK = 1023;
+
+struct WpParams {
+  const void *in;        // [n_in, c_in]
+  const void *gout;      // [n_out, c_out]
+  const int32_t *pin, *pout, *seg_start;   // padded pair lists, seg_start[K+1]
+  float *dW;             // [K, c_in, c_out]
+  uint32_t c_in, c_out, K;
+  uint32_t mt_cta, n_mtgroups, n_splits;
+  uint32_t blkB, n_stage, a_bytes, stage_bytes, acc_sets;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t s0 = smem_u32(smem);
+  uint8_t *tail = smem + p.n_stage * p.stage_bytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(tail);
+  const uint32_t bar0 = smem_u32(bars);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * kMaxStages + 4);
+  int32_t *seg = reinterpret_cast<int32_t *>(tail + tc::kBarBytes);     // [K + 1], in STAGES
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t mtg = blockIdx.x % p.n_mtgroups, split = blockIdx.x / p.n_mtgroups;
+  const uint32_t ch0 = mtg * p.mt_cta * 128;
+  const uint32_t ch_n = min(p.c_in - ch0, p.mt_cta * 128);        // channels of this CTA's slice
+  const uint32_t mt = (ch_n + 127) / 128;
+
+  for (uint32_t i = threadIdx.x; i <= p.K; i += kWpThreads) seg[i] = __ldg(p.seg_start + i) / kWpRows;
+  if (threadIdx.x == 0) {
+    for (uint32_t i = 0; i < p.n_stage; ++i) {
+      mbar_init(bar_fullA(bar0, i), kWpProducerWarps * 32);
+      mbar_init(bar_emptyA(bar0, i), 1);
+    }
+    for (uint32_t i = 0; i < 2; ++i) { mbar_init(bar_tfull(bar0, i), 1); mbar_init(bar_tempty(bar0, i), kEpilogueWarps * 32); }
+    mbar_fence_init();
+  }
+  if (warp == kWpProducerWarps + kEpilogueWarps) {
+    tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // this CTA's range of the global stage list, walked offset by offset (identically by every role)
+  const uint32_t n_total = (uint32_t)seg[p.K];
+  const uint32_t s_begin = (uint32_t)((uint64_t)n_total * split / p.n_splits);
+  const uint32_t s_end = (uint32_t)((uint64_t)n_total * (split + 1) / p.n_splits);
+  uint32_t k_first = 0;
+  while (k_first < p.K && (uint32_t)seg[k_first + 1] <= s_begin) ++k_first;
+
+  if (warp < kWpProducerWarps) {
+    // =============================== PRODUCERS ======================================
+    const T *in = reinterpret_cast<const T *>(p.in) + ch0;
+    const T *gout = reinterpret_cast<const T *>(p.gout);
+    const uint32_t cprA = ch_n / 8, cprB = p.c_out / 8;      // 16-byte chunks per row
+    const uint32_t nA = (8 * cprA + 31) / 32, nB = (8 * cprB + 31) / 32;   // slots per thread
+    // fixed copy slots: slot s of this lane copies chunk `c % cpr` of row `c / cpr` (of the
+    // warp's 8 rows), c = lane + 32 s; destination offsets never change
+    uint32_t a_dst[kWpMaxSlots], b_dst[kWpMaxSlots], a_meta[kWpMaxSlots], b_meta[kWpMaxSlots];
+#pragma unroll
+    for (int sl = 0; sl < kWpMaxSlots; ++sl) {
+      const uint32_t c = lane + 32u * sl;
+      {
+        const uint32_t rl = c / cprA, chunk = c - rl * cprA;
+        const bool ok = (uint32_t)sl < nA && rl < 8;
+        a_meta[sl] = ok ? (rl | (chunk << 3)) : 0xffffffffu;
+        a_dst[sl] = (chunk >> 3) * kBlkBytes + (warp * 8 + rl) * 128 + (((chunk & 7u) ^ rl) << 4);
+      }
+      {
+        const uint32_t rl = c / cprB, chunk = c - rl * cprB;
+        const bool ok = (uint32_t)sl < nB && rl < 8;
+        b_meta[sl] = ok ? (rl | (chunk << 3)) : 0xffffffffu;
+        b_dst[sl] = p.a_bytes + (chunk >> 3) * kBlkBytes + (warp * 8 + rl) * 128 +
+                    (((chunk & 7u) ^ rl) << 4);
+      }
+    }
+    // lanes 0-7 hold the input rows, lanes 8-15 the output rows of the warp's 8 pairs
+    const int32_t *list = (lane & 8u) ? p.pout : p.pin;
+    const uint32_t li = warp * 8 + (lane & 7u);
+    auto load_idx = [&](uint32_t stage) -> int32_t {
+      return (lane < 16 && stage < s_end) ? __ldg(list + (size_t)stage * kWpRows + li) : -1;
+    };
+    int32_t i0 = load_idx(s_begin), i1 = load_idx(s_begin + 1), i2 = load_idx(s_begin + 2);
+    uint32_t slot = 0, ph = 0;
+    for (uint32_t s = s_begin; s < s_end; ++s) {
+      const int32_t i3 = load_idx(s + 3);
+      if (lane == 0) mbar_wait(bar_emptyA(bar0, slot), ph ^ 1u);
+      __syncwarp();
+      const uint32_t base = s0 + slot * p.stage_bytes;
+#pragma unroll
+      for (int sl = 0; sl < kWpMaxSlots; ++sl) {
+        if ((uint32_t)sl < nA) {
+          const uint32_t m = a_meta[sl];
+          const int32_t row = __shfl_sync(0xffffffffu, i0, (int)(m & 7u));
+          if (m != 0xffffffffu) {
+            const T *src = in + (row < 0 ? 0 : (size_t)row * p.c_in + (m >> 3) * 8);
+            cp_async16(base + a_dst[sl], src, row < 0 ? 0u : 16u);
+          }
+        }
+      }
+#pragma unroll
+      for (int sl = 0; sl < kWpMaxSlots; ++sl) {
+        if ((uint32_t)sl < nB) {
+          const uint32_t m = b_meta[sl];
+          const int32_t row = __shfl_sync(0xffffffffu, i0, (int)(8u + (m & 7u)));
+          if (m != 0xffffffffu) {
+            const T *src = gout + (row < 0 ? 0 : (size_t)row * p.c_out + (m >> 3) * 8);
+            cp_async16(base + b_dst[sl], src, row < 0 ? 0u : 16u);
+          }
+        }
+      }
+      cp_async_mbar_arrive(bar_fullA(bar0, slot));
+      if (++slot == p.n_stage) { slot = 0; ph ^= 1u; }
+      i0 = i1; i1 = i2; i2 = i3;
+    }
+    cp_async_wait<0>();
+  } else if (warp < kWpProducerWarps + kEpilogueWarps) {
+    // =============================== EPILOGUE =======================================
+    const uint32_t q = warp & 3u;
+    uint32_t acc = 0, par = 0, k = k_first;
+    for (uint32_t s = s_begin; s < s_end;) {
+      const uint32_t e = min(s_end, (uint32_t)seg[k + 1]);
+      if (e > s) {
+        mbar_wait_sleep(bar_tfull(bar0, acc), par, 200);
+        tc_fence_after();
+        for (uint32_t t = 0; t < mt; ++t) {
+          const uint32_t ci = ch0 + t * 128 + q * 32 + lane;
+          const uint32_t col0 = (acc * p.mt_cta + t) * p.c_out;
+          float *dst_row = p.dW + ((size_t)k * p.c_in + ci) * p.c_out;
+          for (uint32_t c = 0; c < p.c_out; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem_base + ((q * 32u) << 16) + col0 + c, v);
+            tmem_ld_wait();
+            if (ci < p.c_in) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) atomicAdd(dst_row + c + i, __uint_as_float(v[i]));
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(bar_tempty(bar0, acc));
+        if (++acc == p.acc_sets) { acc = 0; par ^= 1u; }
+        s = e;
+      }
+      if (s >= (uint32_t)seg[k + 1]) ++k;
+    }
+  } else {
+    // =============================== MMA ISSUER =====================================
+    const uint32_t idesc = umma_idesc_f16(Fmt<T>::v, kTileM, p.c_out, 1, 1);
+    uint32_t slot = 0, ph = 0, acc = 0, par = 0, k = k_first;
+    for (uint32_t s = s_begin; s < s_end;) {
+      const uint32_t e = min(s_end, (uint32_t)seg[k + 1]);
+      if (e > s) {
+        mbar_wait(bar_tempty(bar0, acc), par ^ 1u);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + acc * p.mt_cta * p.c_out;
+        for (uint32_t st = s; st < e; ++st) {
+          mbar_wait(bar_fullA(bar0, slot), ph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t abase = s0 + slot * p.stage_bytes, bbase = abase + p.a_bytes;
+            for (uint32_t t = 0; t < mt; ++t) {
+#pragma unroll
+              for (int j = 0; j < kWpRows / 16; ++j) {
+                const uint64_t da = umma_desc(abase + t * 2 * kBlkBytes + j * 2048, kBlkBytes, 1024, 2);
+                const uint64_t db = umma_desc(bbase + j * 2048, kBlkBytes, 1024, 2);
+                umma_f16(d0 + t * p.c_out, da, db, idesc, (st != s || j != 0) ? 1u : 0u);
+              }
+            }
+            umma_commit(bar_emptyA(bar0, slot));
+          }
+          __syncwarp();
+          if (++slot == p.n_stage) { slot = 0; ph ^= 1u; }
+        }
+        if (elect_one()) umma_commit(bar_tfull(bar0, acc));
+        __syncwarp();
+        if (++acc == p.acc_sets) { acc = 0; par ^= 1u; }
+        s = e;
+      }
+      if (s >= (uint32_t)seg[k + 1]) ++k;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWpProducerWarps + kEpilogueWarps) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+bool conv_wgrad_pairs_supported(int dtype, uint32_t c_in, uint32_t K, uint32_t c_out) {
+  if (dtype != MEB200_BF16 && dtype != MEB200_F16) return false;
+  return c_in % 8 == 0 && c_in >= 16 && c_out % 16 == 0 && c_out >= 16 && c_out <= 256 &&
+         K <= kWpMaxK;
+}
+
+int conv_wgrad_pairs(const void *in, const void *grad_out, int dtype, uint32_t c_in, uint32_t K,
+                     uint32_t c_out, const int32_t *pairs_in, const int32_t *pairs_out,
+                     const int32_t *seg_start, uint32_t n_out, float *grad_weight,
+                     cudaStream_t stream) {
+  MEB_CUDA(cudaMemsetAsync(grad_weight, 0, (size_t)K * c_in * c_out * sizeof(float), stream));
+  if (n_out == 0 || K == 0) return MEB200_OK;
+  const tc::WpCfg cfg = tc::wgrad_pairs_config(c_in, c_out, K, n_out, (uint32_t)num_sms());
+  if (cfg.mt_cta == 0) {
+    set_error("wgrad pairs: no configuration fits (c_in=%u c_out=%u K=%u)", c_in, c_out, K);
+    return MEB200_ERR_UNSUPPORTED;
+  }
+  WpParams p{};
+  p.in = in; p.gout = grad_out; p.pin = pairs_in; p.pout = pairs_out; p.seg_start = seg_start;
+  p.dW = grad_weight; p.c_in = c_in; p.c_out = c_out; p.K = K;
+  p.mt_cta = cfg.mt_cta; p.n_mtgroups = cfg.n_mtgroups; p.n_splits = cfg.n_splits;
+  p.blkB = cfg.blkB; p.n_stage = cfg.n_stage; p.a_bytes = cfg.a_bytes;
+  p.stage_bytes = cfg.stage_bytes; p.acc_sets = cfg.acc_sets;
+  const unsigned grid = cfg.n_mtgroups * cfg.n_splits;
+  if (dtype == MEB200_BF16) {
+    MEB_BIG_SMEM(k_wgrad_pairs<__nv_bfloat16>);
+    k_wgrad_pairs<__nv_bfloat16><<<grid, kWpThreads, cfg.smem_bytes, stream>>>(p);
+  } else {
+    MEB_BIG_SMEM(k_wgrad_pairs<__half>);
+    k_wgrad_pairs<__half><<<grid, kWpThreads, cfg.smem_bytes, stream>>>(p);
+  }
+  count_tc_launch();
+  MEB_LAUNCH_OK();
+  return MEB200_OK;
 }
 
 bool conv_wgrad_tc_supported(int dtype, uint32_t c_in, uint32_t c_out) {

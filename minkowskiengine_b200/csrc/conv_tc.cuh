@@ -14,14 +14,23 @@ bool conv_wgrad_tc_supported(int dtype, uint32_t c_in, uint32_t c_out);
 int conv_forward_tc(const void *A, int dtype, uint32_t n_a, uint32_t c_reduce, const void *W,
                     uint32_t K, uint32_t c_cols, bool dgrad, const int32_t *nbr, uint32_t n_rows,
                     void *out, int out_dtype, void *workspace, cudaStream_t stream,
-                    const int32_t *row_ids = nullptr);   // ordered tiles: see TcParams::row_ids
+                    const int32_t *row_ids = nullptr,    // ordered tiles: see TcParams::row_ids
+                    const void *Wperm = nullptr);        // operand B in ta_perm order (k_conv_ta)
 
-// fp32 W[K,c_in,c_out] -> (w_cast [K,c_in,c_out], w_t [K,c_out,c_in]) in `dtype` (bf16/fp16).
+// fp32 W[K,c_in,c_out] -> w_cast [K,c_in,c_out], w_t [K,c_out,c_in] and their k_conv_ta twins
+// w_cp / w_tp (reduction axis permuted within 32-channel blocks; may be NULL) in bf16/fp16.
 int conv_pack_weights(const float *W, uint32_t K, uint32_t c_in, uint32_t c_out, int dtype,
-                      void *w_cast, void *w_t, cudaStream_t stream);
+                      void *w_cast, void *w_t, void *w_cp, void *w_tp, cudaStream_t stream);
 
 int conv_wgrad_tc(const void *in, const void *grad_out, int dtype, uint32_t c_in, uint32_t K,
                   uint32_t c_out, const int32_t *out_nbr, uint32_t n_out, float *grad_weight,
                   cudaStream_t stream);
+
+// wgrad over the compacted pair lists of meb200_kernel_map_pairs (stage = 64 pairs).
+bool conv_wgrad_pairs_supported(int dtype, uint32_t c_in, uint32_t K, uint32_t c_out);
+int conv_wgrad_pairs(const void *in, const void *grad_out, int dtype, uint32_t c_in, uint32_t K,
+                     uint32_t c_out, const int32_t *pairs_in, const int32_t *pairs_out,
+                     const int32_t *seg_start, uint32_t n_out, float *grad_weight,
+                     cudaStream_t stream);
 
 }  // namespace meb200

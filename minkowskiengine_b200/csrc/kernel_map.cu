@@ -40,6 +40,129 @@ k_kernel_map(const int32_t *__restrict__ x_coords, uint32_t nx,
   }
 }
 
+// ---- compacted per-offset pair lists (the reference's own kernel-map representation:
+//      gpu_kernel_map in_maps / out_maps, src/kernel_map.cuh:48-429) --------------------------
+// The dense neighbour table is what the output-stationary forward/dgrad kernels want; the wgrad
+// kernel reduces over PAIRS, so it wants them compacted: for every offset k the valid
+// (other row, table row) pairs in table-row order, each offset's segment padded with (-1, -1)
+// to a multiple of `stage` entries.  Three small deterministic passes (count, scan, fill), no
+// atomics, no host synchronisation; capacity is the caller's upper bound K*n + K*stage.
+constexpr uint32_t kPairChunk = 2048;   // table entries per block: 256 threads x 8 consecutive
+
+__device__ __forceinline__ void load8(const int32_t *__restrict__ row_k, uint32_t r0, uint32_t n,
+                                      int32_t (&v)[8]) {
+  if (r0 + 8 <= n && ((reinterpret_cast<uintptr_t>(row_k + r0) & 15) == 0)) {
+    const int4 a = __ldg(reinterpret_cast<const int4 *>(row_k + r0));
+    const int4 b = __ldg(reinterpret_cast<const int4 *>(row_k + r0) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (r0 + j < n) ? __ldg(row_k + r0 + j) : -1;
+  }
+}
+
+// exclusive prefix of `c` over the 256 threads of the block; *total = block sum
+__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t c, uint32_t *total) {
+  __shared__ uint32_t warp_sums[8];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= (uint32_t)d) incl += t;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  uint32_t base = 0, sum = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    const uint32_t ws = warp_sums[w];
+    if ((uint32_t)w < warp) base += ws;
+    sum += ws;
+  }
+  *total = sum;
+  return base + incl - c;
+}
+
+__global__ void __launch_bounds__(256)
+k_pair_count(const int32_t *__restrict__ nbr, uint32_t n, uint32_t nchunks,
+             uint32_t *__restrict__ cnt) {
+  const uint32_t chunk = blockIdx.x, k = blockIdx.y;
+  int32_t v[8];
+  load8(nbr + (size_t)k * n, chunk * kPairChunk + threadIdx.x * 8, n, v);
+  uint32_t c = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) c += v[j] >= 0;
+  uint32_t total;
+  block_excl_scan_256(c, &total);
+  if (threadIdx.x == 0) cnt[(size_t)k * nchunks + chunk] = total;
+}
+
+// one block: per-offset exclusive scan of the chunk counts (a warp per offset), then the padded
+// segment starts (seg_start[k+1] - seg_start[k] = roundup(count_k, stage))
+__global__ void __launch_bounds__(1024)
+k_pair_scan(uint32_t *__restrict__ cnt /* in: counts, out: exclusive offsets within the offset */,
+            uint32_t K, uint32_t nchunks, uint32_t stage, int32_t *__restrict__ seg_start,
+            uint32_t *__restrict__ seg_count) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t k = warp; k < K; k += 32) {
+    uint32_t running = 0;
+    for (uint32_t base = 0; base < nchunks; base += 32) {
+      const uint32_t i = base + lane;
+      const uint32_t c = i < nchunks ? cnt[(size_t)k * nchunks + i] : 0u;
+      uint32_t incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += t;
+      }
+      if (i < nchunks) cnt[(size_t)k * nchunks + i] = running + incl - c;
+      running += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) seg_count[k] = running;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t pos = 0;
+    for (uint32_t k = 0; k < K; ++k) {
+      seg_start[k] = (int32_t)pos;
+      pos += (seg_count[k] + stage - 1) / stage * stage;
+    }
+    seg_start[K] = (int32_t)pos;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_pair_fill(const int32_t *__restrict__ nbr, uint32_t n, uint32_t nchunks,
+            const uint32_t *__restrict__ chunk_off, const int32_t *__restrict__ seg_start,
+            const uint32_t *__restrict__ seg_count, int32_t *__restrict__ pairs_other,
+            int32_t *__restrict__ pairs_row) {
+  const uint32_t chunk = blockIdx.x, k = blockIdx.y;
+  const uint32_t r0 = chunk * kPairChunk + threadIdx.x * 8;
+  int32_t v[8];
+  load8(nbr + (size_t)k * n, r0, n, v);
+  uint32_t c = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) c += v[j] >= 0;
+  uint32_t total;
+  uint32_t pos = (uint32_t)seg_start[k] + chunk_off[(size_t)k * nchunks + chunk] +
+                 block_excl_scan_256(c, &total);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (v[j] >= 0) {
+      pairs_other[pos] = v[j];
+      pairs_row[pos] = (int32_t)(r0 + j);
+      ++pos;
+    }
+  if (chunk == nchunks - 1) {   // pad the offset's segment to a whole number of stages
+    const uint32_t beg = (uint32_t)seg_start[k] + seg_count[k], end = (uint32_t)seg_start[k + 1];
+    for (uint32_t i = beg + threadIdx.x; i < end; i += 256) {
+      pairs_other[i] = -1;
+      pairs_row[i] = -1;
+    }
+  }
+}
+
 }  // namespace meb200
 
 using namespace meb200;
@@ -60,6 +183,42 @@ extern "C" int meb200_kernel_map(const int32_t *x_coords, uint32_t nx, const int
   MEB_DISPATCH_NCOLS(ncols, k_kernel_map<NC><<<cdiv(total, 256), 256, 0, stream>>>(
                                 x_coords, nx, y_coords, ny, y_table, y_capacity - 1, offsets, K,
                                 x_nbr, y_nbr, d_num_pairs));
+  MEB_LAUNCH_OK();
+  return MEB200_OK;
+}
+
+
+extern "C" uint64_t meb200_pair_list_scratch_bytes(uint32_t K, uint32_t n_rows) {
+  const uint64_t nchunks = (n_rows + kPairChunk - 1) / kPairChunk;
+  return (K * nchunks + K) * sizeof(uint32_t) + 256;
+}
+
+extern "C" uint64_t meb200_pair_list_capacity(uint32_t K, uint32_t n_rows, uint32_t stage) {
+  return (uint64_t)K * n_rows + (uint64_t)K * stage;
+}
+
+extern "C" int meb200_kernel_map_pairs(const int32_t *nbr, uint32_t K, uint32_t n_rows,
+                                       uint32_t stage, int32_t *pairs_other, int32_t *pairs_row,
+                                       int32_t *seg_start, void *scratch, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MEB_CHECK_ARG(K > 0 && K <= 65535 && stage > 0, "K=%u stage=%u", K, stage);
+  MEB_CHECK_ARG(seg_start != nullptr, "seg_start");
+  MEB_CHECK_ARG((uint64_t)K * n_rows + (uint64_t)K * stage < (1ull << 31), "pair list too long");
+  if (n_rows == 0) {
+    MEB_CUDA(cudaMemsetAsync(seg_start, 0, (K + 1) * sizeof(int32_t), stream));
+    return MEB200_OK;
+  }
+  MEB_CHECK_ARG(nbr && pairs_other && pairs_row && scratch, "null buffer");
+  const uint32_t nchunks = (n_rows + kPairChunk - 1) / kPairChunk;
+  uint32_t *cnt = reinterpret_cast<uint32_t *>(scratch);
+  uint32_t *seg_count = cnt + (size_t)K * nchunks;
+  dim3 grid(nchunks, K);
+  k_pair_count<<<grid, 256, 0, stream>>>(nbr, n_rows, nchunks, cnt);
+  MEB_LAUNCH_OK();
+  k_pair_scan<<<1, 1024, 0, stream>>>(cnt, K, nchunks, stage, seg_start, seg_count);
+  MEB_LAUNCH_OK();
+  k_pair_fill<<<grid, 256, 0, stream>>>(nbr, n_rows, nchunks, cnt, seg_start, seg_count,
+                                        pairs_other, pairs_row);
   MEB_LAUNCH_OK();
   return MEB200_OK;
 }

@@ -87,6 +87,77 @@ inline FwdCfg fwd_config(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, uint3
   return c;
 }
 
+// ---- forward / dgrad with operand A in tensor memory (k_conv_ta) --------------------------
+// TMEM (512 columns): acc_sets x R accumulators of c_cols columns, then nA operand-A slots of
+// 16*nb columns (one stage = nb 32-channel blocks of a 128-row tile).  Shared memory holds only
+// the ring of packed-weight stages (nB x [c_cols x 32*nb channels]).
+struct TaCfg {
+  uint32_t nb;            // 32-channel blocks per stage (1..4); 0 = unsupported
+  int bk;                 // channel width of a B sub-tile (64 or 32)
+  uint32_t n_macro;       // stages per (tile, offset) = c_red / (32 nb)
+  uint32_t R, acc_sets, n_super, nA, nB;
+  uint32_t a_col0, b_sub_bytes, b_stage_bytes, smem_bytes;
+  uint32_t rs;            // staged kernel: row slots per producer thread (0 = register kernel)
+};
+constexpr uint32_t kTsProducerWarpsCfg = 8;     // k_conv_ts: 2 groups x 4 warps
+constexpr uint32_t kTsTailBytes = 64 + 8 * 8 * 8 + 8 * 8 * 32 * 4;   // counters, landing barriers, descriptors
+// staged = true : k_conv_ts (gathered rows wait in per-thread shared-memory rings, up to 4
+//                 blocks = 128 channels per stage)
+// staged = false: k_conv_ta (rows wait in registers, up to 3 blocks per stage)
+inline TaCfg ta_config(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, bool staged = true,
+                       int force_R = 0, int force_acc = 0) {
+  TaCfg c{};
+  if (c_red % 32 != 0 || c_cols % 16 != 0 || c_cols < 16 || c_cols > 256) return c;
+  uint32_t nb = c_red % 96 == 0 ? 3 : (c_red % 64 == 0 ? 2 : 1);
+  if (staged && c_red % 128 == 0) nb = 4;
+  c.bk = (nb == 2 || nb == 4) ? 64 : 32;
+  c.n_macro = c_red / (32 * nb);
+  const uint32_t a_cols = 16 * nb;
+  const uint32_t tiles = cdiv_u(n_rows, kTileM);
+  uint32_t bestR = 0, bestAcc = 0;
+  for (uint32_t acc = 2; acc >= 1 && bestR == 0; --acc) {
+    if (force_acc && (int)acc != force_acc) continue;
+    for (uint32_t R = 4; R >= 1; R >>= 1) {
+      if (force_R && (int)R != force_R) continue;
+      if (R > 1 && R > tiles) continue;
+      if (acc * R * c_cols + 2 * a_cols <= kTmemCols) { bestR = R; bestAcc = acc; break; }
+    }
+  }
+  if (bestR == 0) return c;
+  c.R = bestR; c.acc_sets = bestAcc;
+  c.n_super = cdiv_u(tiles, c.R);
+  c.a_col0 = c.acc_sets * c.R * c_cols;
+  c.nA = (kTmemCols - c.a_col0) / a_cols;
+  if (c.nA > 8) c.nA = 8;
+  if (c.nA < 2) return c;
+  c.b_sub_bytes = ((c_cols * (uint32_t)c.bk * 2 + 1023) / 1024) * 1024;
+  c.b_stage_bytes = (32 * nb / (uint32_t)c.bk) * c.b_sub_bytes;
+  if (!staged) {
+    const uint32_t budget = kSmemBudget - kBarBytes - 1024 - 64;
+    c.nB = budget / c.b_stage_bytes;
+    if (c.nB > 8) c.nB = 8;
+    if (c.nB < 2) return c;
+    c.smem_bytes = 1024 + c.nB * c.b_stage_bytes + kBarBytes + 64;
+    c.nb = nb;
+    return c;
+  }
+  // staged: weights ring of 3 (2 if tight) stages, the rest of shared memory goes to the rings
+  const uint32_t budget = kSmemBudget - kBarBytes - 1024 - kTsTailBytes;
+  const uint32_t per_slot = kTsProducerWarpsCfg * nb * 512;     // bytes one more row slot costs
+  for (uint32_t nB = 3; nB >= 2; --nB) {
+    if (nB * c.b_stage_bytes >= budget) continue;
+    uint32_t rs = (budget - nB * c.b_stage_bytes) / per_slot;
+    if (rs > 8) rs = 8;
+    if (rs >= 4) {
+      c.nB = nB; c.rs = rs;
+      c.smem_bytes = 1024 + nB * c.b_stage_bytes + rs * per_slot + kBarBytes + kTsTailBytes;
+      c.nb = nb;
+      return c;
+    }
+  }
+  return c;   // nb = 0: the caller falls back to the register kernel
+}
+
 // ---- wgrad: dW[K, c_in, c_out] reduced over n_out rows --------------------------------------
 struct WgCfg {
   uint32_t mt_cta;        // 128-channel m-tiles of c_in per CTA (1 or 2); 0 = unsupported
@@ -139,6 +210,44 @@ inline WgCfg wgrad_config(uint32_t c_in, uint32_t c_out, uint32_t K, uint32_t n_
   best.n_splits = cdiv_u(n_out, best.rows_per_split);
   best.smem_bytes = 1024 + best.pipe.nA * best.a_stage_bytes + best.pipe.nB * best.b_stage_bytes + kBarBytes;
   return best;
+}
+
+// ---- wgrad over compacted pair lists (k_wgrad_pairs) --------------------------------------
+// stage = 64 pairs: A = mt_cta*2 blocks of [64 rows][128 B] (this CTA's channel slice of the
+// gathered input rows), B = ceil(c_out/64) blocks (the matching dOut rows).
+struct WpCfg {
+  uint32_t mt_cta;        // 128-channel m-tiles per CTA (1 or 2); 0 = unsupported
+  uint32_t n_mtgroups, n_splits, blkB, n_stage, a_bytes, stage_bytes, acc_sets, smem_bytes;
+};
+inline WpCfg wgrad_pairs_config(uint32_t c_in, uint32_t c_out, uint32_t K, uint32_t n_out,
+                                uint32_t n_sms) {
+  WpCfg c{};
+  if (c_out > 256 || c_out == 0 || K > 1023) return c;
+  const uint32_t mt_total = cdiv_u(c_in, 128);
+  uint32_t mt = kTmemCols / c_out;
+  if (mt > 2) mt = 2;
+  if (mt > mt_total) mt = mt_total;
+  if (mt == 0) return c;
+  c.n_mtgroups = cdiv_u(mt_total, mt);
+  c.blkB = cdiv_u(c_out, 64);
+  c.a_bytes = mt * 2 * kBlkBytes;
+  c.stage_bytes = c.a_bytes + c.blkB * kBlkBytes;
+  c.acc_sets = 2 * mt * c_out <= kTmemCols ? 2 : 1;
+  const uint32_t tail = kBarBytes + (K + 1) * 4 + 64;
+  c.n_stage = (kSmemBudget - 1024 - tail) / c.stage_bytes;
+  if (c.n_stage > 16) c.n_stage = 16;
+  if (c.n_stage < 2) return c;
+  // row-range splits: two waves of CTAs at most, and at least ~8 stages of work per CTA on the
+  // estimate "a third of the K*n_out table entries are pairs"
+  const uint64_t est_stages = (uint64_t)K * n_out / (3 * 64) + 1;
+  uint32_t want = (2u * n_sms) / c.n_mtgroups;
+  if (want < 1) want = 1;
+  uint64_t by_work = est_stages / 8;
+  if (by_work < 1) by_work = 1;
+  c.n_splits = (uint32_t)(by_work < want ? by_work : want);
+  c.smem_bytes = 1024 + c.n_stage * c.stage_bytes + tail;
+  c.mt_cta = mt;
+  return c;
 }
 
 // ---- wgrad, register-staged producers over dense 128-row windows (opt-in variant) ----

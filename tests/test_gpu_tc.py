@@ -121,3 +121,78 @@ def test_tc_wgrad_matches_fp32_reference(ME, cuda, dtype, cin, cout, n_in, n_out
         valid = (idx >= 0).unsqueeze(1)
         ref[k] = (f32[idx.clamp(min=0)] * valid).t() @ g32
     assert (gw.float() - ref).abs().max().item() / ref.abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("cin,cout,n_in,n_out,K", [
+    (32, 32, 3000, 3001, 27),        # one 32-channel block per stage, R = 4, ragged tail
+    (32, 16, 500, 100, 27),          # single partial tile
+    (64, 128, 5000, 2000, 27),       # two blocks per stage (128B-swizzled weights)
+    (96, 96, 4000, 4000, 27),        # three blocks per stage: the MinkUNet34C stride-1 blocks
+    (128, 96, 4000, 1000, 8),        # two stages per (tile, offset)
+    (192, 128, 1000, 1000, 27),
+    (384, 256, 700, 300, 27),        # four stages per offset, N = 256 (single accumulator set)
+    (256, 384, 300, 129, 27),        # output columns split in two launches
+    (160, 64, 2000, 1500, 5),        # 160 = 5 blocks of 32 (one block per stage)
+    (32, 64, 90000, 90000, 8),       # more super tiles than SMs: persistent loop + phases
+    (96, 96, 50000, 50000, 27),
+])
+def test_ta_forward_and_dgrad_packed_weights(ME, cuda, dtype, cin, cout, n_in, n_out, K):
+    """fp32 master weights -> packed operand copies -> k_conv_ta (operand A in tensor memory):
+    forward over out_nbr and dgrad over in_nbr against the fp32 torch restatement."""
+    from minkowskiengine_b200 import _lib, backend
+    g = torch.Generator().manual_seed(cin * 1000 + cout + 7)
+    feats = (torch.rand(n_in, cin, generator=g) - 0.5).to(dtype).to(cuda)
+    w = ((torch.rand(K, cin, cout, generator=g) - 0.5) / (cin ** 0.5)).to(cuda)   # fp32 master
+    wl = w.to(dtype)
+    out_nbr = _random_table(K, n_out, n_in, 0.35, seed=K + n_out, device=cuda)
+    in_nbr = _random_table(K, n_in, n_out, 0.3, seed=K + n_in + 3, device=cuda)
+    km = backend._KernelMap(out_nbr, in_nbr)
+    before = _lib.tc_launch_count()
+    out32 = backend._conv_forward(feats, w, km, out_dtype=torch.float32)
+    assert _lib.tc_launch_count() > before
+    ref = _torch_ref_forward(feats, wl, out_nbr)
+    scale = ref.abs().max().item()
+    assert (out32 - ref).abs().max().item() / scale < 2e-5
+    out_lp = backend._conv_forward(feats, w, km)
+    assert out_lp.dtype == dtype
+    assert (out_lp.float() - ref).abs().max().item() / scale < 6e-3
+    # weights modified in place -> the packed copies must be rebuilt
+    with torch.no_grad():
+        w.mul_(0.5)
+    out_half = backend._conv_forward(feats, w, km, out_dtype=torch.float32)
+    ref_half = _torch_ref_forward(feats, w.to(dtype), out_nbr)
+    assert (out_half - ref_half).abs().max().item() / scale < 2e-5
+    # dgrad: rows = input rows, reduction over c_out, W_k^T
+    gout = (torch.rand(n_out, cout, generator=g) - 0.5).to(dtype).to(cuda)
+    gi, _ = backend._conv_backward(feats, gout, w, km, need_in=True, need_w=False)
+    ref_gi = _torch_ref_forward(gout, w.to(dtype).transpose(1, 2).contiguous(), in_nbr)
+    assert gi.dtype == dtype
+    assert (gi.float() - ref_gi).abs().max().item() / ref_gi.abs().max().item() < 6e-3
+
+
+@pytest.mark.parametrize("K,n,density", [(27, 5000, 0.3), (8, 70000, 0.125), (1, 100, 1.0),
+                                         (125, 3001, 0.05), (27, 2048, 0.0), (81, 40000, 0.4)])
+def test_pair_lists_match_table(ME, cuda, K, n, density):
+    """meb200_kernel_map_pairs: per-offset compacted (other row, table row) lists in table-row
+    order, every offset padded with -1 to a multiple of the stage, against torch.nonzero."""
+    from minkowskiengine_b200 import backend
+    nbr = _random_table(K, n, 12345, density, seed=K + n, device=cuda)
+    km = backend._KernelMap(nbr, torch.empty((K, 1), dtype=torch.int32, device=cuda))
+    pin, pout, seg = km.pair_lists()
+    S = km.PAIR_STAGE
+    seg_h = seg.cpu().tolist()
+    assert seg_h[0] == 0 and len(seg_h) == K + 1
+    for k in range(K):
+        rows = torch.nonzero(nbr[k] >= 0).flatten()
+        c = len(rows)
+        a, b = seg_h[k], seg_h[k + 1]
+        assert b - a == (c + S - 1) // S * S
+        assert torch.equal(pout[a:a + c].long(), rows)
+        assert torch.equal(pin[a:a + c], nbr[k][rows])
+        assert bool((pin[a + c:b] == -1).all()) and bool((pout[a + c:b] == -1).all())
+    # the swapped view exchanges the two sides and shares the storage
+    sw = km.swapped()
+    sin, sout, sseg = sw.pair_lists()
+    assert sin.data_ptr() == pout.data_ptr() and sout.data_ptr() == pin.data_ptr()
+    assert sseg.data_ptr() == seg.data_ptr()
