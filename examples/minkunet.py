@@ -29,7 +29,24 @@ _PLANES_34 = {
 }
 
 
+def _bn_relu(ME):
+    """relu(norm(x) [+ residual]): one fused pass on module handles that provide it
+    (minkowskiengine_b200.fused_bn_relu), the reference's three separate ops otherwise."""
+    fused = getattr(ME, "fused_bn_relu", None)
+
+    def bn_relu(norm, relu, x, residual=None):
+        if fused is not None:
+            return fused(norm, x, residual)
+        out = norm(x)
+        if residual is not None:
+            out += residual
+        return relu(out)
+    return bn_relu
+
+
 def _basic_block(ME):
+    bn_relu = _bn_relu(ME)
+
     class BasicBlock(nn.Module):
         expansion = 1
 
@@ -47,12 +64,11 @@ def _basic_block(ME):
 
         def forward(self, x):
             residual = x
-            out = self.relu(self.norm1(self.conv1(x)))
-            out = self.norm2(self.conv2(out))
+            out = bn_relu(self.norm1, self.relu, self.conv1(x))
+            out = self.conv2(out)
             if self.downsample is not None:
                 residual = self.downsample(x)
-            out += residual
-            return self.relu(out)
+            return bn_relu(self.norm2, self.relu, out, residual)
 
     return BasicBlock
 
@@ -64,6 +80,7 @@ def minkunet(name, ME, in_channels=3, out_channels=20, D=3):
     layers = _LAYERS[base]
     planes = (_PLANES_34 if base == "MinkUNet34" else _PLANES)[variant]
     block = _basic_block(ME)
+    bn_relu = _bn_relu(ME)
     init_dim = 32
 
     class MinkUNet(nn.Module):
@@ -131,26 +148,27 @@ def minkunet(name, ME, in_channels=3, out_channels=20, D=3):
             return nn.Sequential(*mods)
 
         def forward(self, x):
-            out = self.relu(self.bn0(self.conv0p1s1(x)))
+            relu = self.relu
+            out = bn_relu(self.bn0, relu, self.conv0p1s1(x))
             out_p1 = out
-            out = self.relu(self.bn1(self.conv1p1s2(out_p1)))
+            out = bn_relu(self.bn1, relu, self.conv1p1s2(out_p1))
             out_b1p2 = self.block1(out)
-            out = self.relu(self.bn2(self.conv2p2s2(out_b1p2)))
+            out = bn_relu(self.bn2, relu, self.conv2p2s2(out_b1p2))
             out_b2p4 = self.block2(out)
-            out = self.relu(self.bn3(self.conv3p4s2(out_b2p4)))
+            out = bn_relu(self.bn3, relu, self.conv3p4s2(out_b2p4))
             out_b3p8 = self.block3(out)
-            out = self.relu(self.bn4(self.conv4p8s2(out_b3p8)))
+            out = bn_relu(self.bn4, relu, self.conv4p8s2(out_b3p8))
             out = self.block4(out)
-            out = self.relu(self.bntr4(self.convtr4p16s2(out)))
+            out = bn_relu(self.bntr4, relu, self.convtr4p16s2(out))
             out = ME.cat(out, out_b3p8)
             out = self.block5(out)
-            out = self.relu(self.bntr5(self.convtr5p8s2(out)))
+            out = bn_relu(self.bntr5, relu, self.convtr5p8s2(out))
             out = ME.cat(out, out_b2p4)
             out = self.block6(out)
-            out = self.relu(self.bntr6(self.convtr6p4s2(out)))
+            out = bn_relu(self.bntr6, relu, self.convtr6p4s2(out))
             out = ME.cat(out, out_b1p2)
             out = self.block7(out)
-            out = self.relu(self.bntr7(self.convtr7p2s2(out)))
+            out = bn_relu(self.bntr7, relu, self.convtr7p2s2(out))
             out = ME.cat(out, out_p1)
             out = self.block8(out)
             return self.final(out)

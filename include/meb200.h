@@ -232,6 +232,24 @@ int meb200_bn_backward_apply(const void *dy, const void *x, int dtype, uint32_t 
                              const double *sums, double count, const double *d_count, void *dx,
                              void *stream);
 
+/* Fused forms (the BasicBlock tail of modules/resnet_block.py:52-68):
+ *   apply_fused           y = relu?( bn(x) + residual? )
+ *   backward_reduce_fused sums over dy' = relu ? dy * (y > 0) : dy   (y_mask = the fused output y)
+ *   backward_apply_fused  dx from dy' as above; d_residual (may be NULL) = dy'
+ * residual / y_mask / d_residual may be NULL; the unfused entry points above are these with
+ * NULLs. */
+int meb200_bn_apply_fused(const void *x, int dtype, uint32_t n, uint32_t C, const float *mean,
+                          const float *invstd, const float *weight, const float *bias,
+                          const void *residual, int relu, void *y, void *stream);
+int meb200_bn_backward_reduce_fused(const void *dy, const void *x, const void *y_mask, int dtype,
+                                    uint32_t n, uint32_t C, const float *mean,
+                                    const float *invstd, double *sums, void *stream);
+int meb200_bn_backward_apply_fused(const void *dy, const void *x, const void *y_mask, int dtype,
+                                   uint32_t n, uint32_t C, const float *mean, const float *invstd,
+                                   const float *weight, const double *sums, double count,
+                                   const double *d_count, void *dx, void *d_residual,
+                                   void *stream);
+
 /* ---- experimental: forward convolution over spatially ordered row tiles -------------------
  * Same result as meb200_conv_forward (reference: ConvolutionForwardKernelGPU
  * src/convolution_kernel.cu:320-496), but the 128-row tiles of the kernel walk the output rows

@@ -30,7 +30,7 @@ from .convolution import (MinkowskiConvolution, MinkowskiConvolutionFunction,
                           MinkowskiGenerativeConvolutionTranspose)
 from .pooling import (MinkowskiAvgPooling, MinkowskiLocalPoolingFunction, MinkowskiMaxPooling,
                       MinkowskiSumPooling)
-from .normalization import MinkowskiBatchNorm, MinkowskiSyncBatchNorm
+from .normalization import MinkowskiBatchNorm, MinkowskiSyncBatchNorm, fused_bn_relu
 from .nonlinearity import *  # noqa: F401,F403
 from .ops import MinkowskiLinear, cat
 from . import modules, utils  # noqa: F401

@@ -74,9 +74,9 @@ __device__ __forceinline__ BnGeom bn_geom(uint32_t C) {
 // TWO per-channel sums: MODE 0: (x, x^2); MODE 1: (dy, dy * xhat)
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kBnThreads)
-k_bn_reduce(const T *__restrict__ a, const T *__restrict__ x, const float *__restrict__ mean,
-            const float *__restrict__ invstd, uint32_t n, uint32_t C, uint32_t rows_per_cta,
-            double *__restrict__ sums) {
+k_bn_reduce(const T *__restrict__ a, const T *__restrict__ x, const T *__restrict__ ymask,
+            const float *__restrict__ mean, const float *__restrict__ invstd, uint32_t n,
+            uint32_t C, uint32_t rows_per_cta, double *__restrict__ sums) {
   extern __shared__ float s_acc[];   // [2C]
   for (uint32_t i = threadIdx.x; i < 2 * C; i += kBnThreads) s_acc[i] = 0.f;
   __syncthreads();
@@ -101,6 +101,12 @@ k_bn_reduce(const T *__restrict__ a, const T *__restrict__ x, const float *__res
       } else {
         float vx[8];
         Vec8<T>::load(x + (size_t)r * C + cg * 8, vx);
+        if (ymask != nullptr) {      // ReLU folded into the layer: dy passes where y > 0
+          float vy[8];
+          Vec8<T>::load(ymask + (size_t)r * C + cg * 8, vy);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) va[i] = vy[i] > 0.f ? va[i] : 0.f;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) { s1[i] += va[i]; s2[i] = fmaf(va[i], (vx[i] - m[i]) * is[i], s2[i]); }
       }
@@ -138,11 +144,15 @@ __global__ void k_bn_finalize(const double *__restrict__ sums, double count,
 // MODE 0: y = (x - mean) * invstd * w + b (+ ReLU);  MODE 1: dx from dy (see file header)
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kBnThreads)
-k_bn_apply(const T *__restrict__ a, const T *__restrict__ x, const float *__restrict__ mean,
-           const float *__restrict__ invstd, const float *__restrict__ weight,
-           const float *__restrict__ bias, const double *__restrict__ gsums, double count,
-           const double *__restrict__ d_count, uint32_t n, uint32_t C, uint32_t rows_per_cta,
-           int relu, T *__restrict__ out) {
+k_bn_apply(const T *__restrict__ a, const T *__restrict__ x, const T *__restrict__ aux,
+           const float *__restrict__ mean, const float *__restrict__ invstd,
+           const float *__restrict__ weight, const float *__restrict__ bias,
+           const double *__restrict__ gsums, double count, const double *__restrict__ d_count,
+           uint32_t n, uint32_t C, uint32_t rows_per_cta, int relu, T *__restrict__ out,
+           T *__restrict__ out2) {
+  // aux: MODE 0 = residual added before the ReLU (may be NULL); MODE 1 = the layer's fused output
+  // y whose sign is the ReLU mask (may be NULL).  out2 (MODE 1, may be NULL) = masked dy, the
+  // gradient of the residual branch.
   const BnGeom g = bn_geom(C);
   if (threadIdx.x >= g.active) return;
   if (d_count != nullptr) count = *d_count;
@@ -169,14 +179,25 @@ k_bn_apply(const T *__restrict__ a, const T *__restrict__ x, const float *__rest
     float va[8], vo[8];
     Vec8<T>::load(a + (size_t)r * C + cg * 8, va);
     if (MODE == 0) {
+      float vr[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) vr[i] = 0.f;
+      if (aux != nullptr) Vec8<T>::load(aux + (size_t)r * C + cg * 8, vr);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        float y = fmaf(va[i], sc[i], sh[i]);
+        float y = fmaf(va[i], sc[i], sh[i]) + vr[i];
         vo[i] = relu ? fmaxf(y, 0.f) : y;
       }
     } else {
       float vx[8];
       Vec8<T>::load(x + (size_t)r * C + cg * 8, vx);
+      if (aux != nullptr) {
+        float vy[8];
+        Vec8<T>::load(aux + (size_t)r * C + cg * 8, vy);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) va[i] = vy[i] > 0.f ? va[i] : 0.f;
+      }
+      if (out2 != nullptr) Vec8<T>::store(out2 + (size_t)r * C + cg * 8, va);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float xhat = (vx[i] - m[i]) * is[i];
@@ -218,9 +239,9 @@ int meb200_bn_stats(const void *x, int dtype, uint32_t n, uint32_t C, double *su
   uint32_t rows = bn_rows_per_cta(n, C, &grid);
   size_t smem = 2 * (size_t)C * sizeof(float);
   switch (dtype) {
-    case MEB200_F32: k_bn_reduce<float, 0><<<grid, kBnThreads, smem, s>>>((const float *)x, nullptr, nullptr, nullptr, n, C, rows, sums); break;
-    case MEB200_BF16: k_bn_reduce<__nv_bfloat16, 0><<<grid, kBnThreads, smem, s>>>((const __nv_bfloat16 *)x, nullptr, nullptr, nullptr, n, C, rows, sums); break;
-    case MEB200_F16: k_bn_reduce<__half, 0><<<grid, kBnThreads, smem, s>>>((const __half *)x, nullptr, nullptr, nullptr, n, C, rows, sums); break;
+    case MEB200_F32: k_bn_reduce<float, 0><<<grid, kBnThreads, smem, s>>>((const float *)x, nullptr, nullptr, nullptr, nullptr, n, C, rows, sums); break;
+    case MEB200_BF16: k_bn_reduce<__nv_bfloat16, 0><<<grid, kBnThreads, smem, s>>>((const __nv_bfloat16 *)x, nullptr, nullptr, nullptr, nullptr, n, C, rows, sums); break;
+    case MEB200_F16: k_bn_reduce<__half, 0><<<grid, kBnThreads, smem, s>>>((const __half *)x, nullptr, nullptr, nullptr, nullptr, n, C, rows, sums); break;
     default: set_error("batch norm: unsupported dtype %d", dtype); return MEB200_ERR_UNSUPPORTED;
   }
   MEB_LAUNCH_OK();
@@ -237,26 +258,33 @@ int meb200_bn_finalize(const double *sums, double count, const double *d_count, 
   return MEB200_OK;
 }
 
-int meb200_bn_apply(const void *x, int dtype, uint32_t n, uint32_t C, const float *mean,
-                    const float *invstd, const float *weight, const float *bias, int relu,
-                    void *y, void *stream_) {
+int meb200_bn_apply_fused(const void *x, int dtype, uint32_t n, uint32_t C, const float *mean,
+                          const float *invstd, const float *weight, const float *bias,
+                          const void *residual, int relu, void *y, void *stream_) {
   cudaStream_t s = (cudaStream_t)stream_;
   MEB_BN_CHECK(C);
   if (n == 0) return MEB200_OK;
   unsigned grid;
   uint32_t rows = bn_rows_per_cta(n, C, &grid);
   switch (dtype) {
-    case MEB200_F32: k_bn_apply<float, 0><<<grid, kBnThreads, 0, s>>>((const float *)x, nullptr, mean, invstd, weight, bias, nullptr, 1.0, nullptr, n, C, rows, relu, (float *)y); break;
-    case MEB200_BF16: k_bn_apply<__nv_bfloat16, 0><<<grid, kBnThreads, 0, s>>>((const __nv_bfloat16 *)x, nullptr, mean, invstd, weight, bias, nullptr, 1.0, nullptr, n, C, rows, relu, (__nv_bfloat16 *)y); break;
-    case MEB200_F16: k_bn_apply<__half, 0><<<grid, kBnThreads, 0, s>>>((const __half *)x, nullptr, mean, invstd, weight, bias, nullptr, 1.0, nullptr, n, C, rows, relu, (__half *)y); break;
+    case MEB200_F32: k_bn_apply<float, 0><<<grid, kBnThreads, 0, s>>>((const float *)x, nullptr, (const float *)residual, mean, invstd, weight, bias, nullptr, 1.0, nullptr, n, C, rows, relu, (float *)y, nullptr); break;
+    case MEB200_BF16: k_bn_apply<__nv_bfloat16, 0><<<grid, kBnThreads, 0, s>>>((const __nv_bfloat16 *)x, nullptr, (const __nv_bfloat16 *)residual, mean, invstd, weight, bias, nullptr, 1.0, nullptr, n, C, rows, relu, (__nv_bfloat16 *)y, nullptr); break;
+    case MEB200_F16: k_bn_apply<__half, 0><<<grid, kBnThreads, 0, s>>>((const __half *)x, nullptr, (const __half *)residual, mean, invstd, weight, bias, nullptr, 1.0, nullptr, n, C, rows, relu, (__half *)y, nullptr); break;
     default: set_error("batch norm: unsupported dtype %d", dtype); return MEB200_ERR_UNSUPPORTED;
   }
   MEB_LAUNCH_OK();
   return MEB200_OK;
 }
 
-int meb200_bn_backward_reduce(const void *dy, const void *x, int dtype, uint32_t n, uint32_t C,
-                              const float *mean, const float *invstd, double *sums, void *stream_) {
+int meb200_bn_apply(const void *x, int dtype, uint32_t n, uint32_t C, const float *mean,
+                    const float *invstd, const float *weight, const float *bias, int relu,
+                    void *y, void *stream_) {
+  return meb200_bn_apply_fused(x, dtype, n, C, mean, invstd, weight, bias, nullptr, relu, y, stream_);
+}
+
+int meb200_bn_backward_reduce_fused(const void *dy, const void *x, const void *y_mask, int dtype,
+                                    uint32_t n, uint32_t C, const float *mean,
+                                    const float *invstd, double *sums, void *stream_) {
   cudaStream_t s = (cudaStream_t)stream_;
   MEB_BN_CHECK(C);
   MEB_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(double), s));
@@ -265,9 +293,35 @@ int meb200_bn_backward_reduce(const void *dy, const void *x, int dtype, uint32_t
   uint32_t rows = bn_rows_per_cta(n, C, &grid);
   size_t smem = 2 * (size_t)C * sizeof(float);
   switch (dtype) {
-    case MEB200_F32: k_bn_reduce<float, 1><<<grid, kBnThreads, smem, s>>>((const float *)dy, (const float *)x, mean, invstd, n, C, rows, sums); break;
-    case MEB200_BF16: k_bn_reduce<__nv_bfloat16, 1><<<grid, kBnThreads, smem, s>>>((const __nv_bfloat16 *)dy, (const __nv_bfloat16 *)x, mean, invstd, n, C, rows, sums); break;
-    case MEB200_F16: k_bn_reduce<__half, 1><<<grid, kBnThreads, smem, s>>>((const __half *)dy, (const __half *)x, mean, invstd, n, C, rows, sums); break;
+    case MEB200_F32: k_bn_reduce<float, 1><<<grid, kBnThreads, smem, s>>>((const float *)dy, (const float *)x, (const float *)y_mask, mean, invstd, n, C, rows, sums); break;
+    case MEB200_BF16: k_bn_reduce<__nv_bfloat16, 1><<<grid, kBnThreads, smem, s>>>((const __nv_bfloat16 *)dy, (const __nv_bfloat16 *)x, (const __nv_bfloat16 *)y_mask, mean, invstd, n, C, rows, sums); break;
+    case MEB200_F16: k_bn_reduce<__half, 1><<<grid, kBnThreads, smem, s>>>((const __half *)dy, (const __half *)x, (const __half *)y_mask, mean, invstd, n, C, rows, sums); break;
+    default: set_error("batch norm: unsupported dtype %d", dtype); return MEB200_ERR_UNSUPPORTED;
+  }
+  MEB_LAUNCH_OK();
+  return MEB200_OK;
+}
+
+int meb200_bn_backward_reduce(const void *dy, const void *x, int dtype, uint32_t n, uint32_t C,
+                              const float *mean, const float *invstd, double *sums, void *stream_) {
+  return meb200_bn_backward_reduce_fused(dy, x, nullptr, dtype, n, C, mean, invstd, sums, stream_);
+}
+
+int meb200_bn_backward_apply_fused(const void *dy, const void *x, const void *y_mask, int dtype,
+                                   uint32_t n, uint32_t C, const float *mean, const float *invstd,
+                                   const float *weight, const double *sums, double count,
+                                   const double *d_count, void *dx, void *d_residual,
+                                   void *stream_) {
+  cudaStream_t s = (cudaStream_t)stream_;
+  MEB_BN_CHECK(C);
+  if (n == 0) return MEB200_OK;
+  MEB_CHECK_ARG(count > 0 || d_count != nullptr, "count");
+  unsigned grid;
+  uint32_t rows = bn_rows_per_cta(n, C, &grid);
+  switch (dtype) {
+    case MEB200_F32: k_bn_apply<float, 1><<<grid, kBnThreads, 0, s>>>((const float *)dy, (const float *)x, (const float *)y_mask, mean, invstd, weight, nullptr, sums, count, d_count, n, C, rows, 0, (float *)dx, (float *)d_residual); break;
+    case MEB200_BF16: k_bn_apply<__nv_bfloat16, 1><<<grid, kBnThreads, 0, s>>>((const __nv_bfloat16 *)dy, (const __nv_bfloat16 *)x, (const __nv_bfloat16 *)y_mask, mean, invstd, weight, nullptr, sums, count, d_count, n, C, rows, 0, (__nv_bfloat16 *)dx, (__nv_bfloat16 *)d_residual); break;
+    case MEB200_F16: k_bn_apply<__half, 1><<<grid, kBnThreads, 0, s>>>((const __half *)dy, (const __half *)x, (const __half *)y_mask, mean, invstd, weight, nullptr, sums, count, d_count, n, C, rows, 0, (__half *)dx, (__half *)d_residual); break;
     default: set_error("batch norm: unsupported dtype %d", dtype); return MEB200_ERR_UNSUPPORTED;
   }
   MEB_LAUNCH_OK();
@@ -278,20 +332,8 @@ int meb200_bn_backward_apply(const void *dy, const void *x, int dtype, uint32_t 
                              const float *mean, const float *invstd, const float *weight,
                              const double *sums, double count, const double *d_count, void *dx,
                              void *stream_) {
-  cudaStream_t s = (cudaStream_t)stream_;
-  MEB_BN_CHECK(C);
-  if (n == 0) return MEB200_OK;
-  MEB_CHECK_ARG(count > 0 || d_count != nullptr, "count");
-  unsigned grid;
-  uint32_t rows = bn_rows_per_cta(n, C, &grid);
-  switch (dtype) {
-    case MEB200_F32: k_bn_apply<float, 1><<<grid, kBnThreads, 0, s>>>((const float *)dy, (const float *)x, mean, invstd, weight, nullptr, sums, count, d_count, n, C, rows, 0, (float *)dx); break;
-    case MEB200_BF16: k_bn_apply<__nv_bfloat16, 1><<<grid, kBnThreads, 0, s>>>((const __nv_bfloat16 *)dy, (const __nv_bfloat16 *)x, mean, invstd, weight, nullptr, sums, count, d_count, n, C, rows, 0, (__nv_bfloat16 *)dx); break;
-    case MEB200_F16: k_bn_apply<__half, 1><<<grid, kBnThreads, 0, s>>>((const __half *)dy, (const __half *)x, mean, invstd, weight, nullptr, sums, count, d_count, n, C, rows, 0, (__half *)dx); break;
-    default: set_error("batch norm: unsupported dtype %d", dtype); return MEB200_ERR_UNSUPPORTED;
-  }
-  MEB_LAUNCH_OK();
-  return MEB200_OK;
+  return meb200_bn_backward_apply_fused(dy, x, nullptr, dtype, n, C, mean, invstd, weight, sums,
+                                        count, d_count, dx, nullptr, stream_);
 }
 
 }

@@ -14,6 +14,7 @@ replaces the two NCCL all-reduces per layer by libmeb200's one-shot exchange ove
 memory (`meb200_peer_allreduce_f64`, csrc/peer.cu): one single-CTA kernel on the compute stream,
 no NCCL launch and no cross-stream hand-off.
 """
+import contextlib
 import os
 
 import torch
@@ -68,113 +69,157 @@ class _PeerExchange:
                                                  self.world, _lib.ptr(out), _lib.current_stream()))
 
 
+def _device_guard(dev):
+    """Native launches go to the CURRENT device's stream: make the tensor's device current."""
+    return torch.cuda.device(dev) if dev.type == "cuda" else contextlib.nullcontext()
+
+
 class _BatchNormFunction(torch.autograd.Function):
+    """y = relu?( bn(x) + residual? ) with batch statistics (training) or the running statistics
+    (`use_running`, inference under autograd: frozen-BN fine-tuning, attribution)."""
+
     @staticmethod
-    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, group):
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, group, relu,
+                residual, use_running):
         lib = _lib.load()
         x = x.contiguous()
         n, C = x.shape
         code = _lib.dtype_code(x.dtype)
-        stream = _lib.current_stream()
         dev = x.device
-        w32 = None if weight is None else weight.detach().float().contiguous()
-        b32 = None if bias is None else bias.detach().float().contiguous()
-        peer = _PeerExchange.get(group, dev) if (group is not None and _USE_PEER) else None
-        if peer is not None:
-            off, sums = peer.next_slot(2 * C + 1)      # statistics land in symmetric memory
-        else:
-            sums = torch.empty(2 * C + 1, dtype=torch.float64, device=dev)
-        _lib.check(lib.meb200_bn_stats(_lib.ptr(x), code, n, C, _lib.ptr(sums), stream))
-        d_count = None
-        if group is not None:
-            sums[2 * C] = float(n)
-            if peer is not None:
-                total = torch.empty(2 * C + 1, dtype=torch.float64, device=dev)
-                peer.allreduce(off, 2 * C + 1, total)
-                sums = total
+        with _device_guard(dev):
+            stream = _lib.current_stream()
+            w32 = None if weight is None else weight.detach().float().contiguous()
+            b32 = None if bias is None else bias.detach().float().contiguous()
+            d_count = None
+            if use_running:
+                mean = running_mean.detach().float().contiguous()
+                invstd = torch.rsqrt(running_var.detach().float() + eps)
             else:
-                torch.distributed.all_reduce(sums, group=group)
-            d_count = sums[2 * C:]
-        mean = torch.empty(C, dtype=torch.float32, device=dev)
-        invstd = torch.empty(C, dtype=torch.float32, device=dev)
-        _lib.check(lib.meb200_bn_finalize(
-            _lib.ptr(sums), float(n), _lib.ptr(d_count), C, float(eps), float(momentum),
-            _lib.ptr(running_mean), _lib.ptr(running_var), _lib.ptr(mean), _lib.ptr(invstd), stream))
-        y = torch.empty_like(x)
-        _lib.check(lib.meb200_bn_apply(_lib.ptr(x), code, n, C, _lib.ptr(mean), _lib.ptr(invstd),
-                                       _lib.ptr(w32), _lib.ptr(b32), 0, _lib.ptr(y), stream))
+                peer = _PeerExchange.get(group, dev) if (group is not None and _USE_PEER) else None
+                if peer is not None:
+                    off, sums = peer.next_slot(2 * C + 1)   # statistics land in symmetric memory
+                else:
+                    sums = torch.empty(2 * C + 1, dtype=torch.float64, device=dev)
+                _lib.check(lib.meb200_bn_stats(_lib.ptr(x), code, n, C, _lib.ptr(sums), stream))
+                if group is not None:
+                    sums[2 * C] = float(n)
+                    if peer is not None:
+                        total = torch.empty(2 * C + 1, dtype=torch.float64, device=dev)
+                        peer.allreduce(off, 2 * C + 1, total)
+                        sums = total
+                    else:
+                        torch.distributed.all_reduce(sums, group=group)
+                    d_count = sums[2 * C:]
+                mean = torch.empty(C, dtype=torch.float32, device=dev)
+                invstd = torch.empty(C, dtype=torch.float32, device=dev)
+                _lib.check(lib.meb200_bn_finalize(
+                    _lib.ptr(sums), float(max(n, 1)), _lib.ptr(d_count), C, float(eps),
+                    float(momentum), _lib.ptr(running_mean), _lib.ptr(running_var),
+                    _lib.ptr(mean), _lib.ptr(invstd), stream))
+            if residual is not None:
+                residual = residual.contiguous()
+            y = torch.empty_like(x)
+            _lib.check(lib.meb200_bn_apply_fused(
+                _lib.ptr(x), code, n, C, _lib.ptr(mean), _lib.ptr(invstd), _lib.ptr(w32),
+                _lib.ptr(b32), _lib.ptr(residual), 1 if relu else 0, _lib.ptr(y), stream))
         ctx.save_for_backward(x, mean, invstd, w32 if w32 is not None else mean.new_empty(0),
-                              d_count if d_count is not None else sums.new_empty(0))
+                              d_count if d_count is not None else mean.new_empty(0, dtype=torch.float64),
+                              y if relu else x.new_empty(0))
         ctx.group = group
         ctx.has_affine = weight is not None
         ctx.param_dtype = None if weight is None else weight.dtype
+        ctx.relu, ctx.has_residual, ctx.use_running = bool(relu), residual is not None, use_running
         return y
 
     @staticmethod
     def backward(ctx, dy):
         lib = _lib.load()
-        x, mean, invstd, w32, d_count = ctx.saved_tensors
+        x, mean, invstd, w32, d_count, y = ctx.saved_tensors
         dy = dy.contiguous()
         if dy.dtype != x.dtype:
             dy = dy.to(x.dtype)
         n, C = x.shape
         code = _lib.dtype_code(x.dtype)
-        stream = _lib.current_stream()
-        peer = _PeerExchange.get(ctx.group, x.device) if (ctx.group is not None and _USE_PEER) \
-            else None
-        if peer is not None:
-            off, gs = peer.next_slot(2 * C)
-        else:
-            gs = torch.empty(2 * C, dtype=torch.float64, device=x.device)
-        _lib.check(lib.meb200_bn_backward_reduce(_lib.ptr(dy), _lib.ptr(x), code, n, C,
-                                                 _lib.ptr(mean), _lib.ptr(invstd), _lib.ptr(gs),
-                                                 stream))
-        grad_w = grad_b = None
-        if ctx.has_affine:   # local sums; DDP averages parameter gradients across ranks
-            grad_b = gs[:C].to(ctx.param_dtype, copy=True)
-            grad_w = gs[C:].to(ctx.param_dtype, copy=True)
-        if peer is not None:
-            total = torch.empty(2 * C, dtype=torch.float64, device=x.device)
-            peer.allreduce(off, 2 * C, total)
-            gs = total
-        elif ctx.group is not None:
-            torch.distributed.all_reduce(gs, group=ctx.group)
-        dx = torch.empty_like(x)
-        _lib.check(lib.meb200_bn_backward_apply(
-            _lib.ptr(dy), _lib.ptr(x), code, n, C, _lib.ptr(mean), _lib.ptr(invstd),
-            _lib.ptr(w32) if w32.numel() else None, _lib.ptr(gs), float(n),
-            _lib.ptr(d_count) if d_count.numel() else None, _lib.ptr(dx), stream))
-        return dx, grad_w, grad_b, None, None, None, None, None
+        ymask = y if ctx.relu else None
+        with _device_guard(x.device):
+            stream = _lib.current_stream()
+            group = None if ctx.use_running else ctx.group
+            peer = _PeerExchange.get(group, x.device) if (group is not None and _USE_PEER) else None
+            if peer is not None:
+                off, gs = peer.next_slot(2 * C)
+            else:
+                gs = torch.empty(2 * C, dtype=torch.float64, device=x.device)
+            _lib.check(lib.meb200_bn_backward_reduce_fused(
+                _lib.ptr(dy), _lib.ptr(x), _lib.ptr(ymask), code, n, C, _lib.ptr(mean),
+                _lib.ptr(invstd), _lib.ptr(gs), stream))
+            grad_w = grad_b = None
+            if ctx.has_affine:   # local sums; DDP averages parameter gradients across ranks
+                grad_b = gs[:C].to(ctx.param_dtype, copy=True)
+                grad_w = gs[C:].to(ctx.param_dtype, copy=True)
+            if ctx.use_running:
+                gs = torch.zeros_like(gs)      # statistics are constants: dx = dy' * invstd * w
+            elif peer is not None:
+                total = torch.empty(2 * C, dtype=torch.float64, device=x.device)
+                peer.allreduce(off, 2 * C, total)
+                gs = total
+            elif group is not None:
+                torch.distributed.all_reduce(gs, group=group)
+            dx = torch.empty_like(x)
+            dres = torch.empty_like(x) if ctx.has_residual else None
+            _lib.check(lib.meb200_bn_backward_apply_fused(
+                _lib.ptr(dy), _lib.ptr(x), _lib.ptr(ymask), code, n, C, _lib.ptr(mean),
+                _lib.ptr(invstd), _lib.ptr(w32) if w32.numel() else None, _lib.ptr(gs),
+                float(max(n, 1)), _lib.ptr(d_count) if d_count.numel() else None, _lib.ptr(dx),
+                _lib.ptr(dres), stream))
+        return dx, grad_w, grad_b, None, None, None, None, None, None, dres, None
 
 
 def _native_ok(bn, x):
+    """Shape/dtype/configuration only (never the row count or per-rank state): every rank of a
+    process group must take the same path, or their collectives would not match."""
+    def buf_ok(t):
+        return (t is not None and t.dtype == torch.float32 and t.is_contiguous()
+                and t.device == x.device)
     return (not _USE_TORCH and x.is_cuda and x.dim() == 2 and x.shape[1] % 8 == 0
-            and x.shape[1] <= 2048 and x.dtype in (torch.float32, torch.bfloat16, torch.float16)
-            and bn.track_running_stats and bn.momentum is not None and x.shape[0] > 0)
+            and 8 <= x.shape[1] <= 2048
+            and x.dtype in (torch.float32, torch.bfloat16, torch.float16)
+            and bn.track_running_stats and bn.momentum is not None
+            and buf_ok(bn.running_mean) and buf_ok(bn.running_var))
 
 
-def _batch_norm(bn, x, group=None):
-    """Functional core shared by the two modules."""
-    if not _native_ok(bn, x):
-        return bn(x)
+def _batch_norm(bn, x, group=None, relu=False, residual=None):
+    """Functional core shared by the modules and fused_bn_relu."""
+    if not _native_ok(bn, x) or (residual is not None and (residual.shape != x.shape
+                                                           or residual.dtype != x.dtype)):
+        y = bn(x)
+        if residual is not None:
+            y = y + residual
+        return torch.relu(y) if relu else y
     if bn.training:
+        if x.shape[0] == 0 and group is None:      # nothing to normalise, statistics untouched
+            return x.clone() if residual is None else x + residual
         if bn.num_batches_tracked is not None:
             bn.num_batches_tracked.add_(1)
         return _BatchNormFunction.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                                        bn.momentum, bn.eps, group)
-    # inference: normalise with the running statistics
-    lib = _lib.load()
-    x = x.contiguous()
-    n, C = x.shape
-    invstd = torch.rsqrt(bn.running_var.float() + bn.eps)
-    y = torch.empty_like(x)
-    w = None if bn.weight is None else bn.weight.detach().float().contiguous()
-    b = None if bn.bias is None else bn.bias.detach().float().contiguous()
-    _lib.check(lib.meb200_bn_apply(_lib.ptr(x), _lib.dtype_code(x.dtype), n, C,
-                                   _lib.ptr(bn.running_mean.float().contiguous()),
-                                   _lib.ptr(invstd), _lib.ptr(w), _lib.ptr(b), 0, _lib.ptr(y),
-                                   _lib.current_stream()))
-    return y
+                                        bn.momentum, bn.eps, group, relu, residual, False)
+    return _BatchNormFunction.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                    bn.momentum, bn.eps, None, relu, residual, True)
+
+
+def fused_bn_relu(norm, input, residual=None):
+    """relu(norm(input) [+ residual]) in one pass over the features — the tail of a residual
+    block (reference: MinkowskiEngine/modules/resnet_block.py:52-68 runs norm, `+=` and ReLU as
+    three passes).  `norm` is a MinkowskiBatchNorm / MinkowskiSyncBatchNorm module."""
+    bn = norm.bn
+    group = norm._group() if isinstance(norm, MinkowskiSyncBatchNorm) else None
+    res = None
+    if residual is not None:
+        assert residual.coordinate_map_key == input.coordinate_map_key, \
+            "residual and input must live on the same coordinate map"
+        res = residual.F
+    out = _batch_norm(bn, input.F, group, relu=True, residual=res)
+    return SparseTensor(out, coordinate_map_key=input.coordinate_map_key,
+                        coordinate_manager=input.coordinate_manager)
 
 
 class MinkowskiBatchNorm(nn.Module):
@@ -205,14 +250,16 @@ class MinkowskiSyncBatchNorm(MinkowskiBatchNorm):
                                          track_running_stats=track_running_stats,
                                          process_group=process_group)
 
-    def forward(self, input):
+    def _group(self):
         bn = self.bn
-        group = None
         if bn.training and torch.distributed.is_available() and torch.distributed.is_initialized():
             group = getattr(bn, "process_group", None) or torch.distributed.group.WORLD
-            if torch.distributed.get_world_size(group) == 1:
-                group = None
-        output = _batch_norm(bn, input.F, group) if _native_ok(bn, input.F) else bn(input.F)
+            if torch.distributed.get_world_size(group) > 1:
+                return group
+        return None
+
+    def forward(self, input):
+        output = _batch_norm(self.bn, input.F, self._group())
         return SparseTensor(output, coordinate_map_key=input.coordinate_map_key,
                             coordinate_manager=input.coordinate_manager)
 
