@@ -1523,6 +1523,7 @@ constexpr int kTsGroups = 2;
 constexpr int kTsProducerWarps = 4 * kTsGroups;
 constexpr int kTsThreads = (kTsProducerWarps + kEpilogueWarps + 3) * 32;
 constexpr uint32_t kTsDepth = 8;             // stage descriptors / landing barriers per warp
+constexpr int kTsPf = 12;                    // neighbour indices are fetched this many stages ahead
 
 template <typename T, int NB, int BK>
 __global__ void __launch_bounds__(kTsThreads, 1)
@@ -1586,11 +1587,15 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
       const uint32_t grow = (q.st * R + q.r) * kTileM + quad * 32 + lane;
       return (j < n_j && grow < p.n_rows) ? __ldg(p.nbr + (size_t)q.k * p.n_rows + grow) : -1;
     };
-    int32_t i0 = load_idx(ppf, 0);
-    ppf.advance(kTsGroups, R, p.n_macro, p.K);
-    int32_t i1 = load_idx(ppf, 1);
-    ppf.advance(kTsGroups, R, p.n_macro, p.K);
-    int32_t i2 = load_idx(ppf, 2);
+    // the neighbour table streams from HBM (no reuse): its latency (~2 us under load) must be
+    // covered by the prefetch distance, or every stage costs latency / distance (measured: a
+    // distance of 3 held a stage at ~1500 cycles).  One register per stage per lane.
+    int32_t ip[kTsPf];
+#pragma unroll
+    for (int d = 0; d < kTsPf; ++d) {
+      ip[d] = load_idx(ppf, (uint32_t)d);
+      if (d + 1 < kTsPf) ppf.advance(kTsGroups, R, p.n_macro, p.K);
+    }
     uint32_t head = 0, tail_j = 0;           // consumed / issued stage counts of this group
     uint32_t wr = 0, used = 0;               // this lane's ring: next slot, slots in use
     uint32_t g_head = grp, slot_head = grp % p.nA;
@@ -1601,7 +1606,7 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
         uint32_t nv = 0;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-          srow[m] = __shfl_sync(0xffffffffu, i0, (m >> 1) * 16 + (m & 1) * 8 + (int)rsub);
+          srow[m] = __shfl_sync(0xffffffffu, ip[0], (m >> 1) * 16 + (m & 1) * 8 + (int)rsub);
           nv += srow[m] >= 0;
         }
         if (!__all_sync(0xffffffffu, used + nv <= RS)) break;
@@ -1627,8 +1632,9 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
         ++tail_j;
         pis.advance(kTsGroups, R, p.n_macro, p.K);
         ppf.advance(kTsGroups, R, p.n_macro, p.K);
-        i0 = i1; i1 = i2;
-        i2 = load_idx(ppf, tail_j + 2);
+#pragma unroll
+        for (int d = 0; d + 1 < kTsPf; ++d) ip[d] = ip[d + 1];
+        ip[kTsPf - 1] = load_idx(ppf, tail_j + kTsPf - 1);
       }
       // ---- move the oldest landed stage: shared memory -> registers -> tensor memory ----------
       {
@@ -2325,6 +2331,7 @@ constexpr int kWpRows = 64;
 constexpr int kWpProducerWarps = 8;
 constexpr int kWpThreads = (kWpProducerWarps + kEpilogueWarps + 1) * 32;
 constexpr int kWpMaxSlots = 8;              // 16-byte copies per thread per operand per stage
+constexpr int kWpPf = 12;                   // pair indices are fetched this many stages ahead
 constexpr uint32_t kWpMaxK = 1023;
 
 struct WpParams {
@@ -2412,10 +2419,16 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
     auto load_idx = [&](uint32_t stage) -> int32_t {
       return (lane < 16 && stage < s_end) ? __ldg(list + (size_t)stage * kWpRows + li) : -1;
     };
-    int32_t i0 = load_idx(s_begin), i1 = load_idx(s_begin + 1), i2 = load_idx(s_begin + 2);
+    // the pair lists stream from HBM: fetch them kWpPf stages ahead (one register per stage)
+    int32_t ip[kWpPf];
+#pragma unroll
+    for (int d = 0; d < kWpPf; ++d) ip[d] = load_idx(s_begin + d);
     uint32_t slot = 0, ph = 0;
     for (uint32_t s = s_begin; s < s_end; ++s) {
-      const int32_t i3 = load_idx(s + 3);
+      const int32_t i0 = ip[0];
+#pragma unroll
+      for (int d = 0; d + 1 < kWpPf; ++d) ip[d] = ip[d + 1];
+      ip[kWpPf - 1] = load_idx(s + kWpPf);
       if (lane == 0) mbar_wait(bar_emptyA(bar0, slot), ph ^ 1u);
       __syncwarp();
       const uint32_t base = s0 + slot * p.stage_bytes;
@@ -2443,7 +2456,6 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
       }
       cp_async_mbar_arrive(bar_fullA(bar0, slot));
       if (++slot == p.n_stage) { slot = 0; ph ^= 1u; }
-      i0 = i1; i1 = i2; i2 = i3;
     }
     cp_async_wait<0>();
   } else if (warp < kWpProducerWarps + kEpilogueWarps) {
