@@ -125,17 +125,19 @@ int meb200_kernel_map(const int32_t *x_coords, uint32_t nx, const int32_t *y_coo
 
 /* Compacted pair lists of a neighbour table — the reference's own kernel-map representation
  * (gpu_kernel_map::in_maps / out_maps per offset, src/kernel_map.cuh:48-429; what
- * CoordinateMapManager::kernel_map returns, coordinate_map_manager.cpp:662-823).  For every offset
- * k, in table-row order: pairs_other[i] = nbr[k][r], pairs_row[i] = r for the rows r with
- * nbr[k][r] >= 0; offset k occupies [seg_start[k], seg_start[k+1]), padded with (-1, -1) to a
- * multiple of `stage` entries.  Deterministic, no atomics, no host synchronisation.
- * Buffers: pairs_* hold meb200_pair_list_capacity(K, n_rows, stage) int32 each, seg_start K+1
- * int32, scratch meb200_pair_list_scratch_bytes(K, n_rows) bytes. */
-uint64_t meb200_pair_list_scratch_bytes(uint32_t K, uint32_t n_rows);
-uint64_t meb200_pair_list_capacity(uint32_t K, uint32_t n_rows, uint32_t stage);
+ * CoordinateMapManager::kernel_map returns, coordinate_map_manager.cpp:662-823).  The table rows
+ * are cut into chunks of `chunk_rows` rows (rounded up to a multiple of 2048; 0 = one chunk);
+ * segment s = chunk * K + k holds, in table-row order, pairs_other[i] = nbr[k][r], pairs_row[i] = r
+ * for the rows r of the chunk with nbr[k][r] >= 0 and occupies [seg_start[s], seg_start[s+1]),
+ * padded with (-1, -1) to a multiple of `stage` entries.  Deterministic, no atomics, no host
+ * synchronisation.  Buffers: pairs_* hold meb200_pair_list_capacity(...) int32 each, seg_start
+ * meb200_pair_list_chunks(...) * K + 1 int32, scratch meb200_pair_list_scratch_bytes(...) bytes. */
+uint32_t meb200_pair_list_chunks(uint32_t n_rows, uint32_t chunk_rows);
+uint64_t meb200_pair_list_scratch_bytes(uint32_t K, uint32_t n_rows, uint32_t chunk_rows);
+uint64_t meb200_pair_list_capacity(uint32_t K, uint32_t n_rows, uint32_t stage, uint32_t chunk_rows);
 int meb200_kernel_map_pairs(const int32_t *nbr, uint32_t K, uint32_t n_rows, uint32_t stage,
-                            int32_t *pairs_other, int32_t *pairs_row, int32_t *seg_start,
-                            void *scratch, void *stream);
+                            uint32_t chunk_rows, int32_t *pairs_other, int32_t *pairs_row,
+                            int32_t *seg_start, void *scratch, void *stream);
 
 /* ---- sparse convolution (reference a8/a9/a10: ConvolutionForwardKernelCPU /
  *      ConvolutionBackwardKernelCPU src/convolution_kernel.hpp:33-144, GPU
@@ -182,14 +184,16 @@ int meb200_conv_forward_packed(const void *in, int in_dtype, uint32_t n_in, uint
 
 /* meb200_conv_backward on packed weights (w_cast, and w_cp or NULL), tensor-core path only;
  * grad_in / grad_weight may be NULL to skip dgrad / wgrad.  pairs_in / pairs_out / seg_start
- * (all three or NULL): the compacted pair lists of out_nbr from meb200_kernel_map_pairs with
- * stage = 64; with them wgrad reduces over valid pairs only instead of the dense table. */
+ * (all three or NULL) + n_chunks: the compacted pair lists of out_nbr from
+ * meb200_kernel_map_pairs with stage = 64 and their chunk count; with them wgrad reduces over
+ * valid pairs only instead of the dense table. */
 int meb200_conv_backward_packed(const void *in, const void *grad_out, int dtype, uint32_t n_in,
                                 uint32_t c_in, const void *w_cast, const void *w_cp, uint32_t K,
                                 uint32_t c_out, const int32_t *out_nbr, const int32_t *in_nbr,
                                 uint32_t n_out, void *grad_in, int grad_in_dtype,
                                 float *grad_weight, const int32_t *pairs_in,
-                                const int32_t *pairs_out, const int32_t *seg_start, void *stream);
+                                const int32_t *pairs_out, const int32_t *seg_start,
+                                uint32_t n_chunks, void *stream);
 
 /* Workspace the two calls above may use (0 is legal: slower fallbacks are chosen). */
 uint64_t meb200_conv_workspace_bytes(uint32_t n_in, uint32_t n_out, uint32_t c_in,

@@ -162,6 +162,7 @@ class _KernelMap:
 
     __slots__ = ("out_nbr", "in_nbr", "stride_pairs", "_n_pairs", "_pairs", "_pair_src")
     PAIR_STAGE = 64   # pairs per pipeline stage of the wgrad kernel (k_wgrad_pairs)
+    PAIR_CHUNK_ROWS = 65536   # table rows per chunk of the pair lists (multiple of 2048)
 
     def __init__(self, out_nbr, in_nbr, stride_pairs=None):
         self.out_nbr, self.in_nbr = out_nbr, in_nbr
@@ -171,27 +172,32 @@ class _KernelMap:
         self._pair_src = None   # the map this one is the swapped view of
 
     def pair_lists(self):
-        """(pairs_in, pairs_out, seg_start): per-offset compacted (input row, output row) lists
-        padded to PAIR_STAGE entries per offset (meb200_kernel_map_pairs) — the reference's own
-        kernel-map representation.  Built on first use; a swapped view shares its source's lists
-        with the two sides exchanged."""
+        """(pairs_in, pairs_out, seg_start, n_chunks): compacted (input row, output row) lists in
+        (row chunk, offset) order, every segment padded to PAIR_STAGE entries
+        (meb200_kernel_map_pairs) — the reference's own kernel-map representation, chunked so
+        that a consumer keeps one chunk's feature rows L2-resident across the offsets.  Built on
+        first use; a swapped view shares its source's lists with the two sides exchanged."""
         if self._pairs is None:
             if self._pair_src is not None:
-                pin, pout, seg = self._pair_src.pair_lists()
-                self._pairs = (pout, pin, seg)
+                pin, pout, seg, nch = self._pair_src.pair_lists()
+                self._pairs = (pout, pin, seg, nch)
                 return self._pairs
             lib = _lib.load()
             K, n = self.out_nbr.shape
             dev = self.out_nbr.device
-            cap = int(lib.meb200_pair_list_capacity(K, n, self.PAIR_STAGE))
+            chunk_rows = self.PAIR_CHUNK_ROWS
+            while K * int(lib.meb200_pair_list_chunks(n, chunk_rows)) > 2047:
+                chunk_rows *= 2
+            nch = int(lib.meb200_pair_list_chunks(n, chunk_rows))
+            cap = int(lib.meb200_pair_list_capacity(K, n, self.PAIR_STAGE, chunk_rows))
             pairs = torch.empty((2, cap), dtype=torch.int32, device=dev)
-            seg = torch.empty(K + 1, dtype=torch.int32, device=dev)
-            scratch = torch.empty(int(lib.meb200_pair_list_scratch_bytes(K, n)), dtype=torch.uint8,
-                                  device=dev)
+            seg = torch.empty(nch * K + 1, dtype=torch.int32, device=dev)
+            scratch = torch.empty(int(lib.meb200_pair_list_scratch_bytes(K, n, chunk_rows)),
+                                  dtype=torch.uint8, device=dev)
             _lib.check(lib.meb200_kernel_map_pairs(
-                _lib.ptr(self.out_nbr), K, n, self.PAIR_STAGE, _lib.ptr(pairs[0]),
+                _lib.ptr(self.out_nbr), K, n, self.PAIR_STAGE, chunk_rows, _lib.ptr(pairs[0]),
                 _lib.ptr(pairs[1]), _lib.ptr(seg), _lib.ptr(scratch), _lib.current_stream()))
-            self._pairs = (pairs[0], pairs[1], seg)   # other side = input rows, row = output rows
+            self._pairs = (pairs[0], pairs[1], seg, nch)   # other side = input rows, row = output rows
         return self._pairs
 
     @property
@@ -677,12 +683,14 @@ def _conv_backward_impl(in_feat, grad_out, kernel, km, need_in=True, need_w=True
     if _can_pack(kernel, in_feat.dtype):
         w, _, w_cp, _ = _packed_weights(kernel, in_feat.dtype)
         pin = pout = seg = None
+        nch = 0
         if need_w and c_in % 8 == 0 and c_in >= 16 and K <= 1023:
-            pin, pout, seg = km.pair_lists()
+            pin, pout, seg, nch = km.pair_lists()
         rc = lib.meb200_conv_backward_packed(
             _lib.ptr(in_feat), _lib.ptr(grad_out), code, n_in, c_in, _lib.ptr(w), _lib.ptr(w_cp),
             K, c_out, _lib.ptr(km.out_nbr), _lib.ptr(km.in_nbr), n_out, _lib.ptr(grad_in), code,
-            _lib.ptr(grad_w), _lib.ptr(pin), _lib.ptr(pout), _lib.ptr(seg), _lib.current_stream())
+            _lib.ptr(grad_w), _lib.ptr(pin), _lib.ptr(pout), _lib.ptr(seg), nch,
+            _lib.current_stream())
         if rc != _ERR_UNSUPPORTED:
             _lib.check(rc)
             return grad_in, grad_w

@@ -90,7 +90,7 @@ int meb200_conv_backward_packed(const void *in, const void *grad_out, int dtype,
                                 uint32_t n_out, void *grad_in, int grad_in_dtype,
                                 float *grad_weight, const int32_t *pairs_in,
                                 const int32_t *pairs_out, const int32_t *seg_start,
-                                void *stream_) {
+                                uint32_t n_chunks, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   MEB_CHECK_ARG(dtype == MEB200_BF16 || dtype == MEB200_F16, "packed backward is bf16 or fp16");
   MEB_CHECK_ARG(grad_in_dtype == MEB200_F32 || grad_in_dtype == dtype,
@@ -117,10 +117,10 @@ int meb200_conv_backward_packed(const void *in, const void *grad_out, int dtype,
       const char *e = getenv("MEB200_TC_WGRAD");
       use_pairs = (e && e[0] == 'd') ? 0 : 1;
     }
-    if (use_pairs && pairs_in && pairs_out && seg_start &&
+    if (use_pairs && pairs_in && pairs_out && seg_start && n_chunks > 0 &&
         conv_wgrad_pairs_supported(dtype, c_in, K, c_out)) {
       int rc = conv_wgrad_pairs(in, grad_out, dtype, c_in, K, c_out, pairs_in, pairs_out,
-                                seg_start, n_out, grad_weight, stream);
+                                seg_start, n_chunks, n_out, grad_weight, stream);
       if (rc != MEB200_ERR_UNSUPPORTED) return rc;
     }
     return conv_wgrad_tc(in, grad_out, dtype, c_in, K, c_out, out_nbr, n_out, grad_weight, stream);

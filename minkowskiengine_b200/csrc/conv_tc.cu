@@ -1252,7 +1252,9 @@ __device__ __forceinline__ void ta_epilogue(const TaParams &p, uint32_t bar0, ui
   const uint32_t R = p.R;
   uint32_t acc = 0, par = 0;
   for (uint32_t st = blockIdx.x; st < p.n_super; st += gridDim.x) {
-    mbar_wait(bar_tfull(bar0, acc), par);
+    // a super tile takes tens of microseconds: poll rarely, the producers need the issue slots
+    // (the busy wait was 19 % of all issued instructions in the first capture)
+    mbar_wait_sleep(bar_tfull(bar0, acc), par, 256);
     tc_fence_after();
     for (uint32_t r = 0; r < R; ++r) {
       const uint32_t row = (st * R + r) * kTileM + q * 32 + lane;
@@ -1523,7 +1525,7 @@ constexpr int kTsGroups = 2;
 constexpr int kTsProducerWarps = 4 * kTsGroups;
 constexpr int kTsThreads = (kTsProducerWarps + kEpilogueWarps + 3) * 32;
 constexpr uint32_t kTsDepth = 8;             // stage descriptors / landing barriers per warp
-constexpr int kTsPf = 12;                    // neighbour indices are fetched this many stages ahead
+constexpr int kTsPf = 8;                     // neighbour indices are copied this many stages ahead
 
 template <typename T, int NB, int BK>
 __global__ void __launch_bounds__(kTsThreads, 1)
@@ -1544,6 +1546,7 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
   volatile uint32_t *consumed = reinterpret_cast<volatile uint32_t *>(tail + tc::kBarBytes);
   uint64_t *landed_all = reinterpret_cast<uint64_t *>(tail + tc::kBarBytes + 64);   // [NP][kTsDepth]
   uint32_t *desc_all = reinterpret_cast<uint32_t *>(landed_all + NP * kTsDepth);    // [NP][kTsDepth][32]
+  int32_t *idx_all = reinterpret_cast<int32_t *>(desc_all + NP * kTsDepth * 32);     // [NP][kTsPf][32]
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t R = p.R;
@@ -1583,17 +1586,25 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
     TaPos pis, ppf;                   // position of the next stage to issue / to prefetch indices for
     pis.init(grp, R, p.n_macro, p.K);
     ppf = pis;
-    auto load_idx = [&](const TaPos &q, uint32_t j) -> int32_t {
-      const uint32_t grow = (q.st * R + q.r) * kTileM + quad * 32 + lane;
-      return (j < n_j && grow < p.n_rows) ? __ldg(p.nbr + (size_t)q.k * p.n_rows + grow) : -1;
+    // The neighbour table streams from HBM (no reuse): its latency (~2 us under load) must be
+    // covered by the prefetch distance.  Registers cannot do it — rotating a register ring makes
+    // every iteration wait for the newest load (measured: 12 % of all stall samples on the first
+    // use, r2_run4) — so the indices of stage j + kTsPf are copied by cp.async (4 bytes per lane,
+    // one coalesced 128-byte row of the table per warp) into a per-warp ring in shared memory,
+    // one commit group per issued stage.
+    const uint32_t iring = smem_u32(idx_all + warp * kTsPf * 32);
+    auto copy_idx = [&](const TaPos &q, uint32_t j) {
+      if (j < n_j) {
+        const uint32_t grow = (q.st * R + q.r) * kTileM + quad * 32 + lane;
+        const bool ok = grow < p.n_rows;
+        cp_async4(iring + ((j % kTsPf) * 32 + lane) * 4,
+                  p.nbr + (ok ? (size_t)q.k * p.n_rows + grow : 0), ok ? 4u : 0u);
+      }
+      cp_async_commit();
     };
-    // the neighbour table streams from HBM (no reuse): its latency (~2 us under load) must be
-    // covered by the prefetch distance, or every stage costs latency / distance (measured: a
-    // distance of 3 held a stage at ~1500 cycles).  One register per stage per lane.
-    int32_t ip[kTsPf];
-#pragma unroll
+#pragma unroll 1
     for (int d = 0; d < kTsPf; ++d) {
-      ip[d] = load_idx(ppf, (uint32_t)d);
+      copy_idx(ppf, (uint32_t)d);
       if (d + 1 < kTsPf) ppf.advance(kTsGroups, R, p.n_macro, p.K);
     }
     uint32_t head = 0, tail_j = 0;           // consumed / issued stage counts of this group
@@ -1602,11 +1613,19 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
     while (head < n_j) {
       // ---- run ahead: issue the copies of further stages while every lane has ring space ----
       while (tail_j < n_j && tail_j - head < kTsDepth) {
+        // indices of stage tail_j: copied kTsPf issued stages ago (or in the prologue)
+        cp_async_wait<kTsPf - 1>();
+        __syncwarp();
         int32_t srow[4];
         uint32_t nv = 0;
+        const uint32_t grow0 = (pis.st * R + pis.r) * kTileM + quad * 32 + rsub;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-          srow[m] = __shfl_sync(0xffffffffu, ip[0], (m >> 1) * 16 + (m & 1) * 8 + (int)rsub);
+          const uint32_t rq = (m >> 1) * 16 + (m & 1) * 8;
+          int32_t v;
+          asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v)
+                       : "r"(iring + ((tail_j % kTsPf) * 32 + rq + rsub) * 4));
+          srow[m] = (grow0 + rq < p.n_rows) ? v : -1;     // rows past the end were zero-filled
           nv += srow[m] >= 0;
         }
         if (!__all_sync(0xffffffffu, used + nv <= RS)) break;
@@ -1632,9 +1651,8 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
         ++tail_j;
         pis.advance(kTsGroups, R, p.n_macro, p.K);
         ppf.advance(kTsGroups, R, p.n_macro, p.K);
-#pragma unroll
-        for (int d = 0; d + 1 < kTsPf; ++d) ip[d] = ip[d + 1];
-        ip[kTsPf - 1] = load_idx(ppf, tail_j + kTsPf - 1);
+        __syncwarp();                 // every lane has read stage tail_j - 1's ring row: reuse it
+        copy_idx(ppf, tail_j + kTsPf - 1);
       }
       // ---- move the oldest landed stage: shared memory -> registers -> tensor memory ----------
       {
@@ -2331,17 +2349,62 @@ constexpr int kWpRows = 64;
 constexpr int kWpProducerWarps = 8;
 constexpr int kWpThreads = (kWpProducerWarps + kEpilogueWarps + 1) * 32;
 constexpr int kWpMaxSlots = 8;              // 16-byte copies per thread per operand per stage
-constexpr int kWpPf = 12;                   // pair indices are fetched this many stages ahead
-constexpr uint32_t kWpMaxK = 1023;
+constexpr int kWpPf = 8;                    // pair indices are copied this many stages ahead
+constexpr uint32_t kWpMaxSeg = 2047;        // (row chunks) x K segments a launch can walk
 
 struct WpParams {
   const void *in;        // [n_in, c_in]
   const void *gout;      // [n_out, c_out]
-  const int32_t *pin, *pout, *seg_start;   // padded pair lists, seg_start[K+1]
+  const int32_t *pin, *pout, *seg_start;   // padded pair lists, seg_start[n_chunks*K + 1]
   float *dW;             // [K, c_in, c_out]
-  uint32_t c_in, c_out, K;
+  uint32_t c_in, c_out, K, n_chunks;
   uint32_t mt_cta, n_mtgroups, n_splits;
   uint32_t blkB, n_stage, a_bytes, stage_bytes, acc_sets;
+};
+
+// This CTA's share of the stage list: for every row chunk c the `split`-th of n_splits equal
+// slices of the chunk's stages — all CTAs sweep the chunks together, so one chunk's rows of both
+// feature matrices stay L2-resident across the K offsets.  Within a chunk the slice is walked
+// segment by segment (segment = one offset of the chunk); every role iterates identically.
+struct WpWalk {
+  const int32_t *seg;      // [n_chunks*K + 1], in stages (shared memory)
+  uint32_t K, n_chunks, split, n_splits;
+  uint32_t c, sgm, s, s_end;             // current chunk, segment, stage, end of this chunk's slice
+  __device__ __forceinline__ void open_chunk() {
+    while (c < n_chunks) {
+      const uint32_t lo = (uint32_t)seg[c * K], hi = (uint32_t)seg[(c + 1) * K];
+      s = lo + (uint32_t)((uint64_t)(hi - lo) * split / n_splits);
+      s_end = lo + (uint32_t)((uint64_t)(hi - lo) * (split + 1) / n_splits);
+      if (s < s_end) {
+        sgm = c * K;
+        while ((uint32_t)seg[sgm + 1] <= s) ++sgm;
+        return;
+      }
+      ++c;
+    }
+  }
+  __device__ __forceinline__ void init(const int32_t *seg_, uint32_t K_, uint32_t n_chunks_,
+                                       uint32_t split_, uint32_t n_splits_) {
+    seg = seg_; K = K_; n_chunks = n_chunks_; split = split_; n_splits = n_splits_;
+    c = 0; sgm = 0; s = 0; s_end = 0;
+    open_chunk();
+  }
+  __device__ __forceinline__ bool done() const { return c >= n_chunks; }
+  // next run of stages inside one segment: [s, e) of offset k; advances past it
+  __device__ __forceinline__ void next_run(uint32_t &run_begin, uint32_t &run_end, uint32_t &k) {
+    run_begin = s;
+    run_end = min(s_end, (uint32_t)seg[sgm + 1]);
+    k = sgm - c * K;
+    s = run_end;
+    if (s >= s_end) { ++c; open_chunk(); }
+    else { while ((uint32_t)seg[sgm + 1] <= s) ++sgm; }
+  }
+  // single-stage stepping for the producers
+  __device__ __forceinline__ uint32_t next_stage() {
+    const uint32_t cur = s;
+    if (++s >= s_end) { ++c; open_chunk(); }
+    return cur;
+  }
 };
 
 template <typename T>
@@ -2354,15 +2417,17 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
   uint64_t *bars = reinterpret_cast<uint64_t *>(tail);
   const uint32_t bar0 = smem_u32(bars);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * kMaxStages + 4);
-  int32_t *seg = reinterpret_cast<int32_t *>(tail + tc::kBarBytes);     // [K + 1], in STAGES
+  int32_t *iring_all = reinterpret_cast<int32_t *>(tail + tc::kBarBytes);         // [8 warps][kWpPf][16]
+  int32_t *seg = iring_all + kWpProducerWarps * kWpPf * 16;                        // [n_seg + 1], in STAGES
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t mtg = blockIdx.x % p.n_mtgroups, split = blockIdx.x / p.n_mtgroups;
   const uint32_t ch0 = mtg * p.mt_cta * 128;
   const uint32_t ch_n = min(p.c_in - ch0, p.mt_cta * 128);        // channels of this CTA's slice
   const uint32_t mt = (ch_n + 127) / 128;
+  const uint32_t n_seg = p.n_chunks * p.K;
 
-  for (uint32_t i = threadIdx.x; i <= p.K; i += kWpThreads) seg[i] = __ldg(p.seg_start + i) / kWpRows;
+  for (uint32_t i = threadIdx.x; i <= n_seg; i += kWpThreads) seg[i] = __ldg(p.seg_start + i) / kWpRows;
   if (threadIdx.x == 0) {
     for (uint32_t i = 0; i < p.n_stage; ++i) {
       mbar_init(bar_fullA(bar0, i), kWpProducerWarps * 32);
@@ -2379,13 +2444,6 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
-  // this CTA's range of the global stage list, walked offset by offset (identically by every role)
-  const uint32_t n_total = (uint32_t)seg[p.K];
-  const uint32_t s_begin = (uint32_t)((uint64_t)n_total * split / p.n_splits);
-  const uint32_t s_end = (uint32_t)((uint64_t)n_total * (split + 1) / p.n_splits);
-  uint32_t k_first = 0;
-  while (k_first < p.K && (uint32_t)seg[k_first + 1] <= s_begin) ++k_first;
 
   if (warp < kWpProducerWarps) {
     // =============================== PRODUCERS ======================================
@@ -2413,31 +2471,41 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
                     (((chunk & 7u) ^ rl) << 4);
       }
     }
-    // lanes 0-7 hold the input rows, lanes 8-15 the output rows of the warp's 8 pairs
+    // The pair lists stream from HBM: the 8 + 8 row indices of the warp's pairs of a stage are
+    // copied kWpPf stages ahead by cp.async (lanes 0-7 input rows, 8-15 output rows) into a
+    // per-warp ring in shared memory, one commit group per stage (a register ring would make
+    // every stage wait for its newest load).
     const int32_t *list = (lane & 8u) ? p.pout : p.pin;
     const uint32_t li = warp * 8 + (lane & 7u);
-    auto load_idx = [&](uint32_t stage) -> int32_t {
-      return (lane < 16 && stage < s_end) ? __ldg(list + (size_t)stage * kWpRows + li) : -1;
+    const uint32_t iring = smem_u32(iring_all + warp * kWpPf * 16);
+    WpWalk wk, wpf;
+    wk.init(seg, p.K, p.n_chunks, split, p.n_splits);
+    wpf = wk;
+    auto copy_idx = [&](uint32_t n) {
+      if (!wpf.done()) {
+        const uint32_t stage = wpf.next_stage();
+        if (lane < 16)
+          cp_async4(iring + ((n % kWpPf) * 16 + lane) * 4, list + (size_t)stage * kWpRows + li, 4u);
+      }
+      cp_async_commit();
     };
-    // the pair lists stream from HBM: fetch them kWpPf stages ahead (one register per stage)
-    int32_t ip[kWpPf];
-#pragma unroll
-    for (int d = 0; d < kWpPf; ++d) ip[d] = load_idx(s_begin + d);
-    uint32_t slot = 0, ph = 0;
-    for (uint32_t s = s_begin; s < s_end; ++s) {
-      const int32_t i0 = ip[0];
-#pragma unroll
-      for (int d = 0; d + 1 < kWpPf; ++d) ip[d] = ip[d + 1];
-      ip[kWpPf - 1] = load_idx(s + kWpPf);
+#pragma unroll 1
+    for (uint32_t d = 0; d < (uint32_t)kWpPf; ++d) copy_idx(d);
+    uint32_t slot = 0, ph = 0, n = 0;
+    while (!wk.done()) {
+      wk.next_stage();
+      cp_async_wait<kWpPf - 1>();      // this stage's indices (copied kWpPf stages ago) landed
       if (lane == 0) mbar_wait(bar_emptyA(bar0, slot), ph ^ 1u);
       __syncwarp();
       const uint32_t base = s0 + slot * p.stage_bytes;
+      const uint32_t irow = iring + (n % kWpPf) * 64;
 #pragma unroll
       for (int sl = 0; sl < kWpMaxSlots; ++sl) {
         if ((uint32_t)sl < nA) {
           const uint32_t m = a_meta[sl];
-          const int32_t row = __shfl_sync(0xffffffffu, i0, (int)(m & 7u));
           if (m != 0xffffffffu) {
+            int32_t row;
+            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(row) : "r"(irow + (m & 7u) * 4));
             const T *src = in + (row < 0 ? 0 : (size_t)row * p.c_in + (m >> 3) * 8);
             cp_async16(base + a_dst[sl], src, row < 0 ? 0u : 16u);
           }
@@ -2447,8 +2515,9 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
       for (int sl = 0; sl < kWpMaxSlots; ++sl) {
         if ((uint32_t)sl < nB) {
           const uint32_t m = b_meta[sl];
-          const int32_t row = __shfl_sync(0xffffffffu, i0, (int)(8u + (m & 7u)));
           if (m != 0xffffffffu) {
+            int32_t row;
+            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(row) : "r"(irow + (8u + (m & 7u)) * 4));
             const T *src = gout + (row < 0 ? 0 : (size_t)row * p.c_out + (m >> 3) * 8);
             cp_async16(base + b_dst[sl], src, row < 0 ? 0u : 16u);
           }
@@ -2456,72 +2525,77 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
       }
       cp_async_mbar_arrive(bar_fullA(bar0, slot));
       if (++slot == p.n_stage) { slot = 0; ph ^= 1u; }
+      __syncwarp();                    // ring row n % kWpPf fully read: reuse it
+      copy_idx(n + kWpPf);
+      ++n;
     }
     cp_async_wait<0>();
   } else if (warp < kWpProducerWarps + kEpilogueWarps) {
     // =============================== EPILOGUE =======================================
     const uint32_t q = warp & 3u;
-    uint32_t acc = 0, par = 0, k = k_first;
-    for (uint32_t s = s_begin; s < s_end;) {
-      const uint32_t e = min(s_end, (uint32_t)seg[k + 1]);
-      if (e > s) {
-        mbar_wait_sleep(bar_tfull(bar0, acc), par, 200);
-        tc_fence_after();
-        for (uint32_t t = 0; t < mt; ++t) {
-          const uint32_t ci = ch0 + t * 128 + q * 32 + lane;
-          const uint32_t col0 = (acc * p.mt_cta + t) * p.c_out;
-          float *dst_row = p.dW + ((size_t)k * p.c_in + ci) * p.c_out;
-          for (uint32_t c = 0; c < p.c_out; c += 16) {
-            uint32_t v[16];
-            tmem_ld16(tmem_base + ((q * 32u) << 16) + col0 + c, v);
-            tmem_ld_wait();
-            if (ci < p.c_in) {
+    uint32_t acc = 0, par = 0;
+    WpWalk wk;
+    wk.init(seg, p.K, p.n_chunks, split, p.n_splits);
+    while (!wk.done()) {
+      uint32_t rb, re, k;
+      wk.next_run(rb, re, k);
+      mbar_wait_sleep(bar_tfull(bar0, acc), par, 200);
+      tc_fence_after();
+      for (uint32_t t = 0; t < mt; ++t) {
+        const uint32_t ci = ch0 + t * 128 + q * 32 + lane;
+        const uint32_t col0 = (acc * p.mt_cta + t) * p.c_out;
+        float *dst_row = p.dW + ((size_t)k * p.c_in + ci) * p.c_out;
+        for (uint32_t c = 0; c < p.c_out; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((q * 32u) << 16) + col0 + c, v);
+          tmem_ld_wait();
+          if (ci < p.c_in) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) atomicAdd(dst_row + c + i, __uint_as_float(v[i]));
-            }
+            for (int i = 0; i < 16; i += 4)       // 16-byte vector reductions (sm_90+)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst_row + c + i),
+                           "f"(__uint_as_float(v[i])), "f"(__uint_as_float(v[i + 1])),
+                           "f"(__uint_as_float(v[i + 2])), "f"(__uint_as_float(v[i + 3]))
+                           : "memory");
           }
         }
-        tc_fence_before();
-        mbar_arrive(bar_tempty(bar0, acc));
-        if (++acc == p.acc_sets) { acc = 0; par ^= 1u; }
-        s = e;
       }
-      if (s >= (uint32_t)seg[k + 1]) ++k;
+      tc_fence_before();
+      mbar_arrive(bar_tempty(bar0, acc));
+      if (++acc == p.acc_sets) { acc = 0; par ^= 1u; }
     }
   } else {
     // =============================== MMA ISSUER =====================================
     const uint32_t idesc = umma_idesc_f16(Fmt<T>::v, kTileM, p.c_out, 1, 1);
-    uint32_t slot = 0, ph = 0, acc = 0, par = 0, k = k_first;
-    for (uint32_t s = s_begin; s < s_end;) {
-      const uint32_t e = min(s_end, (uint32_t)seg[k + 1]);
-      if (e > s) {
-        mbar_wait(bar_tempty(bar0, acc), par ^ 1u);
+    uint32_t slot = 0, ph = 0, acc = 0, par = 0;
+    WpWalk wk;
+    wk.init(seg, p.K, p.n_chunks, split, p.n_splits);
+    while (!wk.done()) {
+      uint32_t rb, re, k;
+      wk.next_run(rb, re, k);
+      mbar_wait(bar_tempty(bar0, acc), par ^ 1u);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + acc * p.mt_cta * p.c_out;
+      for (uint32_t st = rb; st < re; ++st) {
+        mbar_wait(bar_fullA(bar0, slot), ph);
         tc_fence_after();
-        const uint32_t d0 = tmem_base + acc * p.mt_cta * p.c_out;
-        for (uint32_t st = s; st < e; ++st) {
-          mbar_wait(bar_fullA(bar0, slot), ph);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t abase = s0 + slot * p.stage_bytes, bbase = abase + p.a_bytes;
-            for (uint32_t t = 0; t < mt; ++t) {
+        if (elect_one()) {
+          const uint32_t abase = s0 + slot * p.stage_bytes, bbase = abase + p.a_bytes;
+          for (uint32_t t = 0; t < mt; ++t) {
 #pragma unroll
-              for (int j = 0; j < kWpRows / 16; ++j) {
-                const uint64_t da = umma_desc(abase + t * 2 * kBlkBytes + j * 2048, kBlkBytes, 1024, 2);
-                const uint64_t db = umma_desc(bbase + j * 2048, kBlkBytes, 1024, 2);
-                umma_f16(d0 + t * p.c_out, da, db, idesc, (st != s || j != 0) ? 1u : 0u);
-              }
+            for (int j = 0; j < kWpRows / 16; ++j) {
+              const uint64_t da = umma_desc(abase + t * 2 * kBlkBytes + j * 2048, kBlkBytes, 1024, 2);
+              const uint64_t db = umma_desc(bbase + j * 2048, kBlkBytes, 1024, 2);
+              umma_f16(d0 + t * p.c_out, da, db, idesc, (st != rb || j != 0) ? 1u : 0u);
             }
-            umma_commit(bar_emptyA(bar0, slot));
           }
-          __syncwarp();
-          if (++slot == p.n_stage) { slot = 0; ph ^= 1u; }
+          umma_commit(bar_emptyA(bar0, slot));
         }
-        if (elect_one()) umma_commit(bar_tfull(bar0, acc));
         __syncwarp();
-        if (++acc == p.acc_sets) { acc = 0; par ^= 1u; }
-        s = e;
+        if (++slot == p.n_stage) { slot = 0; ph ^= 1u; }
       }
-      if (s >= (uint32_t)seg[k + 1]) ++k;
+      if (elect_one()) umma_commit(bar_tfull(bar0, acc));
+      __syncwarp();
+      if (++acc == p.acc_sets) { acc = 0; par ^= 1u; }
     }
   }
 
@@ -2536,23 +2610,23 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
 bool conv_wgrad_pairs_supported(int dtype, uint32_t c_in, uint32_t K, uint32_t c_out) {
   if (dtype != MEB200_BF16 && dtype != MEB200_F16) return false;
   return c_in % 8 == 0 && c_in >= 16 && c_out % 16 == 0 && c_out >= 16 && c_out <= 256 &&
-         K <= kWpMaxK;
+         K <= kWpMaxSeg;
 }
 
 int conv_wgrad_pairs(const void *in, const void *grad_out, int dtype, uint32_t c_in, uint32_t K,
                      uint32_t c_out, const int32_t *pairs_in, const int32_t *pairs_out,
-                     const int32_t *seg_start, uint32_t n_out, float *grad_weight,
-                     cudaStream_t stream) {
+                     const int32_t *seg_start, uint32_t n_chunks, uint32_t n_out,
+                     float *grad_weight, cudaStream_t stream) {
   MEB_CUDA(cudaMemsetAsync(grad_weight, 0, (size_t)K * c_in * c_out * sizeof(float), stream));
   if (n_out == 0 || K == 0) return MEB200_OK;
-  const tc::WpCfg cfg = tc::wgrad_pairs_config(c_in, c_out, K, n_out, (uint32_t)num_sms());
+  const tc::WpCfg cfg = tc::wgrad_pairs_config(c_in, c_out, K, n_chunks, n_out, (uint32_t)num_sms());
   if (cfg.mt_cta == 0) {
     set_error("wgrad pairs: no configuration fits (c_in=%u c_out=%u K=%u)", c_in, c_out, K);
     return MEB200_ERR_UNSUPPORTED;
   }
   WpParams p{};
   p.in = in; p.gout = grad_out; p.pin = pairs_in; p.pout = pairs_out; p.seg_start = seg_start;
-  p.dW = grad_weight; p.c_in = c_in; p.c_out = c_out; p.K = K;
+  p.dW = grad_weight; p.c_in = c_in; p.c_out = c_out; p.K = K; p.n_chunks = n_chunks;
   p.mt_cta = cfg.mt_cta; p.n_mtgroups = cfg.n_mtgroups; p.n_splits = cfg.n_splits;
   p.blkB = cfg.blkB; p.n_stage = cfg.n_stage; p.a_bytes = cfg.a_bytes;
   p.stage_bytes = cfg.stage_bytes; p.acc_sets = cfg.acc_sets;

@@ -30,7 +30,7 @@ int conv_wgrad_tc(const void *in, const void *grad_out, int dtype, uint32_t c_in
 bool conv_wgrad_pairs_supported(int dtype, uint32_t c_in, uint32_t K, uint32_t c_out);
 int conv_wgrad_pairs(const void *in, const void *grad_out, int dtype, uint32_t c_in, uint32_t K,
                      uint32_t c_out, const int32_t *pairs_in, const int32_t *pairs_out,
-                     const int32_t *seg_start, uint32_t n_out, float *grad_weight,
-                     cudaStream_t stream);
+                     const int32_t *seg_start, uint32_t n_chunks, uint32_t n_out,
+                     float *grad_weight, cudaStream_t stream);
 
 }  // namespace meb200

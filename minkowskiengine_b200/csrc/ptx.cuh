@@ -48,6 +48,11 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32
                "r"(src_bytes)
                : "memory");
 }
+// 4-byte variant (neighbour indices); src_bytes = 0 zero-fills
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
+               : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() {
   asm volatile("cp.async.commit_group;" ::: "memory");
 }

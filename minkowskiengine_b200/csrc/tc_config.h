@@ -100,7 +100,7 @@ struct TaCfg {
   uint32_t rs;            // staged kernel: row slots per producer thread (0 = register kernel)
 };
 constexpr uint32_t kTsProducerWarpsCfg = 8;     // k_conv_ts: 2 groups x 4 warps
-constexpr uint32_t kTsTailBytes = 64 + 8 * 8 * 8 + 8 * 8 * 32 * 4;   // counters, landing barriers, descriptors
+constexpr uint32_t kTsTailBytes = 64 + 8 * 8 * 8 + 8 * 8 * 32 * 4 + 8 * 8 * 32 * 4;   // counters, landing barriers, descriptors, index rings
 // staged = true : k_conv_ts (gathered rows wait in per-thread shared-memory rings, up to 4
 //                 blocks = 128 channels per stage)
 // staged = false: k_conv_ta (rows wait in registers, up to 3 blocks per stage)
@@ -219,10 +219,10 @@ struct WpCfg {
   uint32_t mt_cta;        // 128-channel m-tiles per CTA (1 or 2); 0 = unsupported
   uint32_t n_mtgroups, n_splits, blkB, n_stage, a_bytes, stage_bytes, acc_sets, smem_bytes;
 };
-inline WpCfg wgrad_pairs_config(uint32_t c_in, uint32_t c_out, uint32_t K, uint32_t n_out,
-                                uint32_t n_sms) {
+inline WpCfg wgrad_pairs_config(uint32_t c_in, uint32_t c_out, uint32_t K, uint32_t n_chunks,
+                                uint32_t n_out, uint32_t n_sms) {
   WpCfg c{};
-  if (c_out > 256 || c_out == 0 || K > 1023) return c;
+  if (c_out > 256 || c_out == 0 || n_chunks == 0 || (uint64_t)K * n_chunks > 2047) return c;
   const uint32_t mt_total = cdiv_u(c_in, 128);
   uint32_t mt = kTmemCols / c_out;
   if (mt > 2) mt = 2;
@@ -233,16 +233,19 @@ inline WpCfg wgrad_pairs_config(uint32_t c_in, uint32_t c_out, uint32_t K, uint3
   c.a_bytes = mt * 2 * kBlkBytes;
   c.stage_bytes = c.a_bytes + c.blkB * kBlkBytes;
   c.acc_sets = 2 * mt * c_out <= kTmemCols ? 2 : 1;
-  const uint32_t tail = kBarBytes + (K + 1) * 4 + 64;
+  const uint32_t tail = kBarBytes + 8 * 8 * 16 * 4 + (K * n_chunks + 1) * 4 + 64;   // barriers, index rings, segment table
   c.n_stage = (kSmemBudget - 1024 - tail) / c.stage_bytes;
   if (c.n_stage > 16) c.n_stage = 16;
   if (c.n_stage < 2) return c;
-  // row-range splits: two waves of CTAs at most, and at least ~8 stages of work per CTA on the
-  // estimate "a third of the K*n_out table entries are pairs"
+  // row-range splits: two waves of CTAs at most, and enough stages per CTA to amortise its
+  // accumulator flush (mt*128 x c_out reductions into dW; ~one stage's time per 16 columns) on
+  // the estimate "a third of the K*n_out table entries are pairs"
   const uint64_t est_stages = (uint64_t)K * n_out / (3 * 64) + 1;
   uint32_t want = (2u * n_sms) / c.n_mtgroups;
   if (want < 1) want = 1;
-  uint64_t by_work = est_stages / 8;
+  // (per CHUNK: a CTA flushes at least once per chunk it has stages in)
+  const uint32_t min_stages = 8 + mt * c_out / 8;
+  uint64_t by_work = est_stages / n_chunks / min_stages;
   if (by_work < 1) by_work = 1;
   c.n_splits = (uint32_t)(by_work < want ? by_work : want);
   c.smem_bytes = 1024 + c.n_stage * c.stage_bytes + tail;

@@ -36,13 +36,19 @@ def sparse_collate(coords, feats, labels=None, dtype=torch.int32, device=None):
 
 def sparse_quantize(coordinates, features=None, labels=None, ignore_label=-100,
                     return_index=False, return_inverse=False, return_maps_only=False,
-                    quantization_size=None, device="cuda"):
+                    quantization_size=None, device="cuda", label_mode="reference"):
     """Voxelisation on the GPU (reference: utils/quantization.py:136-333 + src/quantization.cpp):
     floor(coordinates / quantization_size) -> int32, deduplicated by the device hash map
     (meb200_insert_and_map: the FIRST point of every voxel is kept and voxels are numbered by
     first occurrence, as the reference CPU path does).  Same arguments and return values as the
-    reference; unlike it, labels are resolved on the device too: a voxel keeps the label of its
-    first point if all its points agree, `ignore_label` otherwise (quantization.cpp:140-196)."""
+    reference; unlike it, labels are resolved on the device too (quantization.cpp:140-196).
+    label_mode="reference" (default) reproduces the reference bit for bit, INCLUDING its indexing
+    slip: when the points of voxel u disagree it writes `ignore_label` to
+    colabels[inverse_mapping[u]] — the voxel that contains point number u — instead of
+    colabels[u] (quantization.cpp:188-191; `val.first` is a voxel id used as a point id).
+    label_mode="consistent" applies the documented intent: a voxel keeps the label of its first
+    point if all its points agree and gets `ignore_label` otherwise."""
+    assert label_mode in ("reference", "consistent")
     from ..backend import CoordinateMapManagerGPU_c10
     assert isinstance(coordinates, (np.ndarray, torch.Tensor)), \
         "Coords must be either np.array or torch.Tensor."
@@ -88,7 +94,14 @@ def sparse_quantize(coordinates, features=None, labels=None, ignore_label=-100,
         differs = (lab != first[inverse_map]).to(torch.int32)
         mixed = torch.zeros(unique_map.shape[0], dtype=torch.int32, device=dev)
         mixed.index_add_(0, inverse_map, differs)
-        colabels = torch.where(mixed > 0, torch.full_like(first, ignore_label), first)
+        # a voxel whose first label already is ignore_label never "conflicts" in the reference
+        conflict = (mixed > 0) & (first != ignore_label)
+        if label_mode == "consistent":
+            colabels = torch.where(conflict, torch.full_like(first, ignore_label), first)
+        else:
+            colabels = first.clone()
+            target = inverse_map[torch.nonzero(conflict).flatten()]   # voxel of point number u
+            colabels[target] = ignore_label
         ret = [back(discrete[unique_map])]
         if f is not None:
             ret.append(back(f[unique_map]))

@@ -61,6 +61,14 @@ def test_sparse_quantize_labels_match_reference(ME, cuda):
     assert torch.equal(ginv.cpu().long(), torch.as_tensor(np.asarray(rinv)).long())
     assert torch.equal(gl.cpu().int(), torch.as_tensor(np.asarray(rl)).int())
     assert int((gl == -100).sum()) > 0
+    # documented intent (label_mode="consistent"): first label if the voxel's points agree
+    gl2 = ME.utils.sparse_quantize(pts, feats, labels, ignore_label=-100, device="cuda",
+                                   label_mode="consistent")[2].cpu()
+    inv, first = torch.as_tensor(np.asarray(rinv)).long(), labels[torch.as_tensor(np.asarray(ri)).long()]
+    for u in range(0, len(first), 97):
+        ls = labels[inv == u]
+        want = int(first[u]) if bool((ls == first[u]).all()) or int(first[u]) == -100 else -100
+        assert int(gl2[u]) == want
 
 
 def test_collate_then_quantize_on_device(ME, cuda):

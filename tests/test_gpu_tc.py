@@ -171,28 +171,61 @@ def test_ta_forward_and_dgrad_packed_weights(ME, cuda, dtype, cin, cout, n_in, n
     assert (gi.float() - ref_gi).abs().max().item() / ref_gi.abs().max().item() < 6e-3
 
 
-@pytest.mark.parametrize("K,n,density", [(27, 5000, 0.3), (8, 70000, 0.125), (1, 100, 1.0),
-                                         (125, 3001, 0.05), (27, 2048, 0.0), (81, 40000, 0.4)])
-def test_pair_lists_match_table(ME, cuda, K, n, density):
-    """meb200_kernel_map_pairs: per-offset compacted (other row, table row) lists in table-row
-    order, every offset padded with -1 to a multiple of the stage, against torch.nonzero."""
+@pytest.mark.parametrize("K,n,density,chunk", [(27, 5000, 0.3, 2048), (8, 70000, 0.125, 65536),
+                                               (1, 100, 1.0, 65536), (125, 3001, 0.05, 2048),
+                                               (27, 2048, 0.0, 2048), (81, 40000, 0.4, 4096),
+                                               (27, 150000, 0.3, 65536)])
+def test_pair_lists_match_table(ME, cuda, K, n, density, chunk, monkeypatch):
+    """meb200_kernel_map_pairs: compacted (other row, table row) lists in (row chunk, offset)
+    order, table-row order inside a segment, every segment padded with -1 to a multiple of the
+    stage — against torch.nonzero."""
     from minkowskiengine_b200 import backend
+    monkeypatch.setattr(backend._KernelMap, "PAIR_CHUNK_ROWS", chunk)
     nbr = _random_table(K, n, 12345, density, seed=K + n, device=cuda)
     km = backend._KernelMap(nbr, torch.empty((K, 1), dtype=torch.int32, device=cuda))
-    pin, pout, seg = km.pair_lists()
+    pin, pout, seg, nch = km.pair_lists()
     S = km.PAIR_STAGE
     seg_h = seg.cpu().tolist()
-    assert seg_h[0] == 0 and len(seg_h) == K + 1
-    for k in range(K):
-        rows = torch.nonzero(nbr[k] >= 0).flatten()
-        c = len(rows)
-        a, b = seg_h[k], seg_h[k + 1]
-        assert b - a == (c + S - 1) // S * S
-        assert torch.equal(pout[a:a + c].long(), rows)
-        assert torch.equal(pin[a:a + c], nbr[k][rows])
-        assert bool((pin[a + c:b] == -1).all()) and bool((pout[a + c:b] == -1).all())
+    assert seg_h[0] == 0 and len(seg_h) == nch * K + 1
+    bpc = -(-chunk // 2048)                   # table blocks (2048 rows) per chunk
+    assert nch == -(-(-(-n // 2048)) // bpc)
+    covered = 0
+    for c in range(nch):
+        r0, r1 = c * bpc * 2048, min((c + 1) * bpc * 2048, n)
+        for k in range(K):
+            rows = torch.nonzero(nbr[k, r0:r1] >= 0).flatten() + r0
+            cnum = len(rows)
+            a, b = seg_h[c * K + k], seg_h[c * K + k + 1]
+            assert b - a == (cnum + S - 1) // S * S
+            assert torch.equal(pout[a:a + cnum].long(), rows)
+            assert torch.equal(pin[a:a + cnum], nbr[k][rows])
+            assert bool((pin[a + cnum:b] == -1).all()) and bool((pout[a + cnum:b] == -1).all())
+            covered += cnum
+    assert covered == int((nbr >= 0).sum())
     # the swapped view exchanges the two sides and shares the storage
     sw = km.swapped()
-    sin, sout, sseg = sw.pair_lists()
+    sin, sout, sseg, snch = sw.pair_lists()
     assert sin.data_ptr() == pout.data_ptr() and sout.data_ptr() == pin.data_ptr()
-    assert sseg.data_ptr() == seg.data_ptr()
+    assert sseg.data_ptr() == seg.data_ptr() and snch == nch
+
+
+def test_wgrad_pairs_many_chunks(ME, cuda, monkeypatch):
+    """k_wgrad_pairs walking several row chunks (small chunks forced) against the fp32 reference."""
+    from minkowskiengine_b200 import backend
+    monkeypatch.setattr(backend._KernelMap, "PAIR_CHUNK_ROWS", 4096)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    K, n_in, n_out, cin, cout = 27, 30000, 33000, 96, 96
+    g = torch.Generator().manual_seed(5)
+    feats = (torch.rand(n_in, cin, generator=g) - 0.5).bfloat16().to(cuda)
+    gout = (torch.rand(n_out, cout, generator=g) - 0.5).bfloat16().to(cuda)
+    w = torch.zeros(K, cin, cout, device=cuda)
+    nbr = _random_table(K, n_out, n_in, 0.3, seed=11, device=cuda)
+    km = backend._KernelMap(nbr, torch.full((K, n_in), -1, dtype=torch.int32, device=cuda))
+    _, gw = backend._conv_backward(feats, gout, w, km, need_in=False, need_w=True)
+    assert km.pair_lists()[3] == 9
+    ref = torch.zeros(K, cin, cout, device=cuda)
+    f32, g32 = feats.float(), gout.float()
+    for k in range(K):
+        idx = nbr[k].long()
+        ref[k] = (f32[idx.clamp(min=0)] * (idx >= 0).unsqueeze(1)).t() @ g32
+    assert (gw - ref).abs().max().item() / ref.abs().max().item() < 2e-5
