@@ -554,10 +554,15 @@ def run_ours(args):
     # launches on).  achieved = ALGORITHMIC flops (2*P*Cin*Cout per launch) or bytes (SURVEY.md
     # 8d formulas) / summed durations.  Every rank runs the extra steps (DDP all-reduce inside).
     prof = ME.backend.profile_conv_kernels(step_resident if is_net else step_e2e, steps=2)
+    if flush_l2:
+        # cfg1: the convolution kernels from the cached-map step (what `value` times), the
+        # kernel-map construction from the e2e step (the only one that builds maps)
+        prof_res = ME.backend.profile_conv_kernels(step_resident, steps=2)
+        prof["conv_fwd_dgrad"], prof["conv_wgrad"] = prof_res["conv_fwd_dgrad"], prof_res["conv_wgrad"]
     roof = None
     if rank == 0:
         peaks = load_peaks()
-        step_ms = (ms_e2e if not is_net else ms) / args.steps
+        step_ms = (ms if (is_net or flush_l2) else ms_e2e) / args.steps
         peak = peaks["bf16_tflops_sustained"]   # kernels timed inside a long step
 
         def tf(d):
@@ -575,8 +580,9 @@ def run_ours(args):
                     "hbm": {"achieved_gbs": gb(d), "peak_gbs": peaks["hbm_gbs"],
                             "frac": gb(d) / peaks["hbm_gbs"],
                             "note": "compulsory bytes (SURVEY.md 8d) / same durations"}}
-        fam = {"conv_fwd_dgrad": "k_conv_rs (tcgen05 sparse-conv forward/dgrad)",
-               "conv_wgrad": "k_wgrad_tc (tcgen05 wgrad)"}
+        fam = {"conv_fwd_dgrad": "k_conv_ts (tcgen05 sparse-conv forward/dgrad, operand A in tensor memory)",
+               "conv_wgrad": "k_wgrad_pairs (tcgen05 wgrad over compacted pair lists; its time "
+                             "includes building the lists when the map is new)"}
         km = prof["kernel_map"]
         km_entry = {"kernel": "k_kernel_map (hash probes -> neighbour tables)", "bound": "hbm",
                     "achieved": gb(km), "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -602,7 +608,7 @@ def run_ours(args):
                 roof = {"bound": "tensor", "achieved": e["achieved"], "peak": peak,
                         "unit": "TFLOP/s", "frac": e["frac"],
                         "peak_source": f"{peaks['source']} (MEASURED_PEAKS.json bf16_tflops_sustained)"}
-                roof.update(load_traffic("k_wgrad_tc" if top == "conv_wgrad" else "k_conv_rs"))
+                roof.update(load_traffic("k_wgrad_pairs" if top == "conv_wgrad" else "k_conv_ts"))
                 roof.update({k: v for k, v in e.items() if k not in ("achieved", "frac")})
                 roof["other"] = [entry(k, fam[k]) for k in live[1:]]
                 if km["launches"]:

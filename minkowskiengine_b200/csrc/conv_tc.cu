@@ -1224,6 +1224,7 @@ struct TaParams {
   uint32_t a_col0;                   // first TMEM column of the A slots
   uint32_t out_f32, out_ld;
   uint32_t rs;                       // k_conv_ts: row slots of a producer thread's ring
+  uint32_t Kg;                       // offset groups: K, or ceil(K / G) when a stage spans G offsets
 };
 
 __device__ __forceinline__ void tmem_st_16x256b_x2(uint32_t taddr, uint32_t r0, uint32_t r1,
@@ -1254,7 +1255,7 @@ __device__ __forceinline__ void ta_epilogue(const TaParams &p, uint32_t bar0, ui
   for (uint32_t st = blockIdx.x; st < p.n_super; st += gridDim.x) {
     // a super tile takes tens of microseconds: poll rarely, the producers need the issue slots
     // (the busy wait was 19 % of all issued instructions in the first capture)
-    mbar_wait_sleep(bar_tfull(bar0, acc), par, 256);
+    mbar_wait_park(bar_tfull(bar0, acc), par);
     tc_fence_after();
     for (uint32_t r = 0; r < R; ++r) {
       const uint32_t row = (st * R + r) * kTileM + q * 32 + lane;
@@ -1305,15 +1306,15 @@ __device__ __forceinline__ void ta_mma(const TaParams &p, uint32_t sB, uint32_t 
   const uint32_t b_lo0 = umma_desc_lo(sB, 16);
   const uint32_t b_inc = p.b_stage_bytes >> 4, b_sub16 = p.b_sub_bytes >> 4;
   uint32_t b_lo = b_lo0, sa = 0, pha = 0, sb = 0, phb = 0, acc = 0, par = 0;
-  const uint32_t n_groups = p.K * p.n_macro;
+  const uint32_t n_groups = p.Kg * p.n_macro;
   for (uint32_t st = blockIdx.x; st < p.n_super; st += gridDim.x) {
-    mbar_wait(bar_tempty(bar0, acc), par ^ 1u);
+    mbar_wait_park(bar_tempty(bar0, acc), par ^ 1u);
     tc_fence_after();
     const uint32_t d0 = tmem_base + acc * R * p.c_cols;
     for (uint32_t grp = 0; grp < n_groups; ++grp) {
-      mbar_wait(bar_fullB(bar0, sb), phb);
+      mbar_wait_park(bar_fullB(bar0, sb), phb);
       for (uint32_t r = 0; r < R; ++r) {
-        mbar_wait(bar_fullA(bar0, sa), pha);
+        mbar_wait_park(bar_fullA(bar0, sa), pha);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t d = d0 + r * p.c_cols;
@@ -1345,30 +1346,39 @@ __device__ __forceinline__ void ta_release(const TaParams &p, uint32_t bar0,
                                            volatile uint32_t *consumed, uint32_t total) {
   uint32_t sa = 0, pha = 0, done = 0;
   for (uint32_t g = 0; g < total; ++g) {
-    mbar_wait(bar_emptyA(bar0, sa), pha);
+    mbar_wait_park(bar_emptyA(bar0, sa), pha);
     __threadfence_block();
     sts_volatile(consumed, ++done);
     if (++sa == p.nA) { sa = 0; pha ^= 1u; }
   }
 }
 
-template <int NB, int BK>
+// G > 1: a stage spans G consecutive offsets (narrow layers: c_red = 32 NB / G channels each),
+// its B sub-tiles come from G different offsets; offsets past K repeat the last one (their A
+// blocks are zero).
+template <int NB, int BK, int G = 1>
 __device__ __forceinline__ void ta_bload(const CUtensorMap *mapB, const TaParams &p, uint32_t sB,
                                          uint32_t bar0) {
   constexpr uint32_t KC = 32u * NB;
+  constexpr int kSubs = (int)(KC / BK), kSubsPerOffset = kSubs / G;
   tma_prefetch_desc(mapB);
   uint32_t sb = 0, phb = 0;
   for (uint32_t st = blockIdx.x; st < p.n_super; st += gridDim.x) {
-    for (uint32_t k = 0; k < p.K; ++k) {
-      const int32_t brow = (int32_t)(k * p.wb_rows_per_k + p.wb_row0);
+    for (uint32_t kg = 0; kg < p.Kg; ++kg) {
       for (uint32_t mc = 0; mc < p.n_macro; ++mc) {
-        mbar_wait(bar_emptyB(bar0, sb), phb ^ 1u);
+        mbar_wait_park(bar_emptyB(bar0, sb), phb ^ 1u);
         mbar_arrive_expect_tx(bar_fullB(bar0, sb), KC * p.c_cols * 2);
         const uint32_t dstB = sB + sb * p.b_stage_bytes;
 #pragma unroll
-        for (int sub = 0; sub < (int)(KC / BK); ++sub)
-          tma_load_2d(dstB + sub * p.b_sub_bytes, mapB, (int32_t)(mc * KC + sub * BK), brow,
-                      bar_fullB(bar0, sb));
+        for (int sub = 0; sub < kSubs; ++sub) {
+          uint32_t k = kg, c0 = mc * KC + sub * BK;
+          if constexpr (G > 1) {
+            k = min(kg * G + sub / kSubsPerOffset, p.K - 1);
+            c0 = (sub % kSubsPerOffset) * BK;
+          }
+          tma_load_2d(dstB + sub * p.b_sub_bytes, mapB, (int32_t)c0,
+                      (int32_t)(k * p.wb_rows_per_k + p.wb_row0), bar_fullB(bar0, sb));
+        }
         if (++sb == p.nB) { sb = 0; phb ^= 1u; }
       }
     }
@@ -1421,7 +1431,7 @@ k_conv_ta(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t R = p.R;
-  const uint32_t SPS = p.K * p.n_macro * R;    // A stages per super tile
+  const uint32_t SPS = p.Kg * p.n_macro * R;   // A stages per super tile
   const uint32_t n_my = p.n_super > blockIdx.x
                             ? (p.n_super - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const uint32_t total = n_my * SPS;
@@ -1448,7 +1458,7 @@ k_conv_ta(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
     const uint32_t piece = lane & 3u, rsub = lane >> 2;
     const T *A = reinterpret_cast<const T *>(p.A);
     TaPos cur, nxt;
-    cur.init(grp, R, p.n_macro, p.K);
+    cur.init(grp, R, p.n_macro, p.Kg);
     nxt = cur;
     // lane l fetches the neighbour of row l of this warp's quadrant (one coalesced 128-byte read)
     auto load_idx = [&](const TaPos &q) -> int32_t {
@@ -1458,7 +1468,7 @@ k_conv_ta(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
     uint32_t g = grp, slot = grp % p.nA;
     int32_t idx_cur = g < total ? load_idx(cur) : -1, idx_nxt = -1;
     for (; g < total; g += kTaGroups) {
-      nxt.advance(kTaGroups, R, p.n_macro, p.K);
+      nxt.advance(kTaGroups, R, p.n_macro, p.Kg);
       if (g + kTaGroups < total) idx_nxt = load_idx(nxt);
       const T *src0 = A + cur.mc * KC + piece * 8;
       // rows m = 2*half + hi  ->  quadrant row half*16 + hi*8 + rsub
@@ -1527,11 +1537,16 @@ constexpr int kTsThreads = (kTsProducerWarps + kEpilogueWarps + 3) * 32;
 constexpr uint32_t kTsDepth = 8;             // stage descriptors / landing barriers per warp
 constexpr int kTsPf = 8;                     // neighbour indices are copied this many stages ahead
 
-template <typename T, int NB, int BK>
+template <typename T, int NB, int BK, int G>
 __global__ void __launch_bounds__(kTsThreads, 1)
 k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
+  // G = offsets per stage.  G = 1: a stage is NB 32-channel blocks of ONE offset's rows (chunk
+  // mc of c_red).  G > 1 (c_red = 32 NB / G): the stage concatenates the rows of G consecutive
+  // offsets along the reduction axis — out = sum_k A_k W_k = [A_k0 .. A_k(G-1)] [W_k0; ..] — so
+  // the narrow layers get stages as fat as the wide ones instead of G times as many thin ones.
   constexpr uint32_t KC = 32u * NB;
   constexpr uint32_t kACols = 16u * NB;
+  constexpr int NBo = NB / G;                  // 32-channel blocks per offset
   constexpr int NP = kTsProducerWarps;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>(
@@ -1546,11 +1561,11 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
   volatile uint32_t *consumed = reinterpret_cast<volatile uint32_t *>(tail + tc::kBarBytes);
   uint64_t *landed_all = reinterpret_cast<uint64_t *>(tail + tc::kBarBytes + 64);   // [NP][kTsDepth]
   uint32_t *desc_all = reinterpret_cast<uint32_t *>(landed_all + NP * kTsDepth);    // [NP][kTsDepth][32]
-  int32_t *idx_all = reinterpret_cast<int32_t *>(desc_all + NP * kTsDepth * 32);     // [NP][kTsPf][32]
+  int32_t *idx_all = reinterpret_cast<int32_t *>(desc_all + NP * kTsDepth * 32);     // [NP][kTsPf][G][32]
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t R = p.R;
-  const uint32_t SPS = p.K * p.n_macro * R;
+  const uint32_t SPS = p.Kg * p.n_macro * R;
   const uint32_t n_my = p.n_super > blockIdx.x
                             ? (p.n_super - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const uint32_t total = n_my * SPS;
@@ -1584,49 +1599,61 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
     // stages of this group: j = 0, 1, ...  <->  g = grp + kTsGroups * j
     const uint32_t n_j = total > grp ? (total - grp + kTsGroups - 1) / kTsGroups : 0;
     TaPos pis, ppf;                   // position of the next stage to issue / to prefetch indices for
-    pis.init(grp, R, p.n_macro, p.K);
+    pis.init(grp, R, p.n_macro, p.Kg);
     ppf = pis;
     // The neighbour table streams from HBM (no reuse): its latency (~2 us under load) must be
     // covered by the prefetch distance.  Registers cannot do it — rotating a register ring makes
     // every iteration wait for the newest load (measured: 12 % of all stall samples on the first
     // use, r2_run4) — so the indices of stage j + kTsPf are copied by cp.async (4 bytes per lane,
-    // one coalesced 128-byte row of the table per warp) into a per-warp ring in shared memory,
-    // one commit group per issued stage.
-    const uint32_t iring = smem_u32(idx_all + warp * kTsPf * 32);
+    // one coalesced 128-byte row of the table per warp and offset) into a per-warp ring in shared
+    // memory, one commit group per issued stage.
+    const uint32_t iring = smem_u32(idx_all + warp * kTsPf * G * 32);
     auto copy_idx = [&](const TaPos &q, uint32_t j) {
       if (j < n_j) {
         const uint32_t grow = (q.st * R + q.r) * kTileM + quad * 32 + lane;
-        const bool ok = grow < p.n_rows;
-        cp_async4(iring + ((j % kTsPf) * 32 + lane) * 4,
-                  p.nbr + (ok ? (size_t)q.k * p.n_rows + grow : 0), ok ? 4u : 0u);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const uint32_t k = q.k * G + g;
+          const bool ok = grow < p.n_rows && k < p.K;
+          cp_async4(iring + (((j % kTsPf) * G + g) * 32 + lane) * 4,
+                    p.nbr + (ok ? (size_t)k * p.n_rows + grow : 0), ok ? 4u : 0u);
+        }
       }
       cp_async_commit();
     };
 #pragma unroll 1
     for (int d = 0; d < kTsPf; ++d) {
       copy_idx(ppf, (uint32_t)d);
-      if (d + 1 < kTsPf) ppf.advance(kTsGroups, R, p.n_macro, p.K);
+      if (d + 1 < kTsPf) ppf.advance(kTsGroups, R, p.n_macro, p.Kg);
     }
     uint32_t head = 0, tail_j = 0;           // consumed / issued stage counts of this group
     uint32_t wr = 0, used = 0;               // this lane's ring: next slot, slots in use
-    uint32_t g_head = grp, slot_head = grp % p.nA;
+    uint32_t slot_head = grp % p.nA, slot_par = 0;    // TMEM slot of the head stage, its use parity
     while (head < n_j) {
       // ---- run ahead: issue the copies of further stages while every lane has ring space ----
       while (tail_j < n_j && tail_j - head < kTsDepth) {
         // indices of stage tail_j: copied kTsPf issued stages ago (or in the prologue)
         cp_async_wait<kTsPf - 1>();
         __syncwarp();
-        int32_t srow[4];
+        int32_t srow[4][G];
         uint32_t nv = 0;
         const uint32_t grow0 = (pis.st * R + pis.r) * kTileM + quad * 32 + rsub;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
           const uint32_t rq = (m >> 1) * 16 + (m & 1) * 8;
-          int32_t v;
-          asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v)
-                       : "r"(iring + ((tail_j % kTsPf) * 32 + rq + rsub) * 4));
-          srow[m] = (grow0 + rq < p.n_rows) ? v : -1;     // rows past the end were zero-filled
-          nv += srow[m] >= 0;
+          bool any = false;
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            int32_t v;
+            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v)
+                         : "r"(iring + (((tail_j % kTsPf) * G + g) * 32 + rq + rsub) * 4));
+            // rows past the end and offsets past K were zero-filled, not -1
+            const bool in_range = grow0 + rq < p.n_rows && pis.k * G + g < p.K;
+            srow[m][g] = in_range ? v : -1;
+            any |= srow[m][g] >= 0;
+          }
+          if (!any) srow[m][0] = -2;          // the row takes no ring slot at all
+          nv += any;
         }
         if (!__all_sync(0xffffffffu, used + nv <= RS)) break;
         const uint32_t d = tail_j % kTsDepth;
@@ -1635,12 +1662,18 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
           uint32_t code = 0xffu;
-          if (srow[m] >= 0) {
+          if (srow[m][0] != -2) {
             code = wr;
-            const T *src = src0 + (size_t)srow[m] * p.c_red;
             const uint32_t dst = ring + wr * 512u;
 #pragma unroll
-            for (int b = 0; b < NB; ++b) cp_async16(dst + b * RS * 512u, src + b * 32, 16);
+            for (int b = 0; b < NB; ++b) {
+              const int32_t sr = srow[m][b / NBo];
+              // G > 1: block b = channels 32 (b % NBo) of offset b / NBo; a missing offset of a
+              // row that has others is zero-filled by the copy engine
+              const T *src = (G == 1 ? src0 : A) + (sr < 0 ? 0 : (size_t)sr * p.c_red) +
+                             (G == 1 ? b : b % NBo) * 32;
+              cp_async16(dst + b * RS * 512u, src, sr < 0 ? 0u : 16u);
+            }
             if (++wr == RS) wr = 0;
           }
           dw |= code << (8 * m);
@@ -1649,15 +1682,15 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
         desc[d * 32] = dw;
         cp_async_mbar_arrive(landed + d * 8);
         ++tail_j;
-        pis.advance(kTsGroups, R, p.n_macro, p.K);
-        ppf.advance(kTsGroups, R, p.n_macro, p.K);
+        pis.advance(kTsGroups, R, p.n_macro, p.Kg);
+        ppf.advance(kTsGroups, R, p.n_macro, p.Kg);
         __syncwarp();                 // every lane has read stage tail_j - 1's ring row: reuse it
         copy_idx(ppf, tail_j + kTsPf - 1);
       }
       // ---- move the oldest landed stage: shared memory -> registers -> tensor memory ----------
       {
         const uint32_t d = head % kTsDepth;
-        mbar_wait(landed + d * 8, (head / kTsDepth) & 1u);
+        mbar_wait_park(landed + d * 8, (head / kTsDepth) & 1u);
         const uint32_t dw = desc[d * 32];
         uint4 v[4][NB];
 #pragma unroll
@@ -1677,7 +1710,11 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
             for (int b = 0; b < NB; ++b) v[m][b] = make_uint4(0, 0, 0, 0);
           }
         }
-        wait_consumed(consumed, g_head, p.nA, lane);      // A slot recycled by the tensor core?
+        // A slot recycled by the tensor core?  nA is even (ta_config) and the two groups
+        // alternate stages, so a slot always belongs to the same group: its previous use is
+        // this group's own stage and a one-bit parity wait on the "empty" barrier is exact.
+        if (lane == 0) mbar_wait_park(bar_emptyA(bar0, slot_head), slot_par ^ 1u);
+        __syncwarp();
         tc_fence_after();
         const uint32_t ta = tmem_base + p.a_col0 + slot_head * kACols + ((quad * 32u) << 16);
 #pragma unroll
@@ -1694,8 +1731,8 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_fullA(bar0, slot_head));
         ++head;
-        g_head += kTsGroups;
-        slot_head = (slot_head + kTsGroups) % p.nA;
+        slot_head += kTsGroups;
+        if (slot_head >= p.nA) { slot_head -= p.nA; slot_par ^= 1u; }
       }
     }
     cp_async_wait<0>();
@@ -1703,10 +1740,8 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
     ta_epilogue<T>(p, bar0, tmem_base, warp & 3u, lane);
   } else if (warp == NP + kEpilogueWarps) {
     ta_mma<T, NB, BK>(p, sB, bar0, tmem_base);
-  } else if (warp == NP + kEpilogueWarps + 1) {
-    if (lane == 0) ta_release(p, bar0, consumed, total);
-  } else {
-    if (lane == 0) ta_bload<NB, BK>(&mapB, p, sB, bar0);
+  } else if (warp == NP + kEpilogueWarps + 2) {
+    if (lane == 0) ta_bload<NB, BK, G>(&mapB, p, sB, bar0);
   }
 
   tc_fence_before();
@@ -1727,10 +1762,10 @@ static int launch_ta(const CUtensorMap &mB, const TaParams &p, size_t smem_bytes
   MEB_LAUNCH_OK();
   return MEB200_OK;
 }
-template <typename T, int NB, int BK>
+template <typename T, int NB, int BK, int G>
 static int launch_ts(const CUtensorMap &mB, const TaParams &p, size_t smem_bytes, unsigned grid,
                      cudaStream_t stream) {
-  auto kern = k_conv_ts<T, NB, BK>;
+  auto kern = k_conv_ts<T, NB, BK, G>;
   MEB_BIG_SMEM(kern);
   kern<<<grid, kTsThreads, smem_bytes, stream>>>(mB, p);
   count_tc_launch();
@@ -1781,6 +1816,7 @@ static int launch_ta_slice(const void *A, int dtype, uint32_t n_a, uint32_t c_re
   p.n_macro = cfg.n_macro; p.b_stage_bytes = cfg.b_stage_bytes; p.b_sub_bytes = cfg.b_sub_bytes;
   p.a_col0 = cfg.a_col0; p.out_f32 = out_dtype == MEB200_F32; p.out_ld = out_ld;
   p.rs = cfg.rs;
+  p.Kg = (K + cfg.g - 1) / cfg.g;
   CUtensorMap mB;
   memset(&mB, 0, sizeof(mB));
   int rc = make_map_2d(&mB, dtype, Wp_full, (uint64_t)K * c_cols_full, c_reduce, (uint32_t)cfg.bk, c_cols);
@@ -1788,11 +1824,13 @@ static int launch_ta_slice(const void *A, int dtype, uint32_t n_a, uint32_t c_re
   const unsigned grid = p.n_super < (uint32_t)num_sms() ? p.n_super : (unsigned)num_sms();
 #define MEB_TA(TT)                                                                        \
   if (staged) {                                                                           \
-    switch (cfg.nb) {                                                                     \
-      case 1: return launch_ts<TT, 1, 32>(mB, p, cfg.smem_bytes, grid, stream);           \
-      case 2: return launch_ts<TT, 2, 64>(mB, p, cfg.smem_bytes, grid, stream);           \
-      case 3: return launch_ts<TT, 3, 32>(mB, p, cfg.smem_bytes, grid, stream);           \
-      case 4: return launch_ts<TT, 4, 64>(mB, p, cfg.smem_bytes, grid, stream);           \
+    switch (cfg.nb * 10 + cfg.g) {                                                        \
+      case 11: return launch_ts<TT, 1, 32, 1>(mB, p, cfg.smem_bytes, grid, stream);       \
+      case 21: return launch_ts<TT, 2, 64, 1>(mB, p, cfg.smem_bytes, grid, stream);       \
+      case 31: return launch_ts<TT, 3, 32, 1>(mB, p, cfg.smem_bytes, grid, stream);       \
+      case 41: return launch_ts<TT, 4, 64, 1>(mB, p, cfg.smem_bytes, grid, stream);       \
+      case 42: return launch_ts<TT, 4, 64, 2>(mB, p, cfg.smem_bytes, grid, stream);       \
+      case 44: return launch_ts<TT, 4, 32, 4>(mB, p, cfg.smem_bytes, grid, stream);       \
       default: break;                                                                     \
     }                                                                                     \
   } else {                                                                                \
@@ -2495,7 +2533,7 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
     while (!wk.done()) {
       wk.next_stage();
       cp_async_wait<kWpPf - 1>();      // this stage's indices (copied kWpPf stages ago) landed
-      if (lane == 0) mbar_wait(bar_emptyA(bar0, slot), ph ^ 1u);
+      if (lane == 0) mbar_wait_park(bar_emptyA(bar0, slot), ph ^ 1u);
       __syncwarp();
       const uint32_t base = s0 + slot * p.stage_bytes;
       const uint32_t irow = iring + (n % kWpPf) * 64;
@@ -2539,7 +2577,7 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
     while (!wk.done()) {
       uint32_t rb, re, k;
       wk.next_run(rb, re, k);
-      mbar_wait_sleep(bar_tfull(bar0, acc), par, 200);
+      mbar_wait_park(bar_tfull(bar0, acc), par);
       tc_fence_after();
       for (uint32_t t = 0; t < mt; ++t) {
         const uint32_t ci = ch0 + t * 128 + q * 32 + lane;
@@ -2572,11 +2610,11 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
     while (!wk.done()) {
       uint32_t rb, re, k;
       wk.next_run(rb, re, k);
-      mbar_wait(bar_tempty(bar0, acc), par ^ 1u);
+      mbar_wait_park(bar_tempty(bar0, acc), par ^ 1u);
       tc_fence_after();
       const uint32_t d0 = tmem_base + acc * p.mt_cta * p.c_out;
       for (uint32_t st = rb; st < re; ++st) {
-        mbar_wait(bar_fullA(bar0, slot), ph);
+        mbar_wait_park(bar_fullA(bar0, slot), ph);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t abase = s0 + slot * p.stage_bytes, bbase = abase + p.a_bytes;

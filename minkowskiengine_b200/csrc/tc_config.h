@@ -98,9 +98,11 @@ struct TaCfg {
   uint32_t R, acc_sets, n_super, nA, nB;
   uint32_t a_col0, b_sub_bytes, b_stage_bytes, smem_bytes;
   uint32_t rs;            // staged kernel: row slots per producer thread (0 = register kernel)
+  uint32_t g;             // offsets per stage (staged kernel, narrow layers); 1 otherwise
 };
 constexpr uint32_t kTsProducerWarpsCfg = 8;     // k_conv_ts: 2 groups x 4 warps
-constexpr uint32_t kTsTailBytes = 64 + 8 * 8 * 8 + 8 * 8 * 32 * 4 + 8 * 8 * 32 * 4;   // counters, landing barriers, descriptors, index rings
+// counters, landing barriers, descriptors, index rings (8 warps x 8 stages x g offsets x 128 B)
+inline uint32_t ts_tail_bytes(uint32_t g) { return 64 + 8 * 8 * 8 + 8 * 8 * 32 * 4 + 8 * 8 * g * 32 * 4; }
 // staged = true : k_conv_ts (gathered rows wait in per-thread shared-memory rings, up to 4
 //                 blocks = 128 channels per stage)
 // staged = false: k_conv_ta (rows wait in registers, up to 3 blocks per stage)
@@ -109,9 +111,13 @@ inline TaCfg ta_config(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, bool st
   TaCfg c{};
   if (c_red % 32 != 0 || c_cols % 16 != 0 || c_cols < 16 || c_cols > 256) return c;
   uint32_t nb = c_red % 96 == 0 ? 3 : (c_red % 64 == 0 ? 2 : 1);
+  c.g = 1;
   if (staged && c_red % 128 == 0) nb = 4;
-  c.bk = (nb == 2 || nb == 4) ? 64 : 32;
-  c.n_macro = c_red / (32 * nb);
+  // narrow layers: a stage spans g offsets so that it still carries 128 channels of reduction
+  if (staged && c_red == 32) { nb = 4; c.g = 4; }
+  if (staged && c_red == 64) { nb = 4; c.g = 2; }
+  c.bk = (c_red % 64 == 0 && nb != 3) ? 64 : 32;
+  c.n_macro = c.g > 1 ? 1 : c_red / (32 * nb);
   const uint32_t a_cols = 16 * nb;
   const uint32_t tiles = cdiv_u(n_rows, kTileM);
   uint32_t bestR = 0, bestAcc = 0;
@@ -129,6 +135,7 @@ inline TaCfg ta_config(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, bool st
   c.a_col0 = c.acc_sets * c.R * c_cols;
   c.nA = (kTmemCols - c.a_col0) / a_cols;
   if (c.nA > 8) c.nA = 8;
+  if (staged) c.nA &= ~1u;     // even: a slot always belongs to the same producer group
   if (c.nA < 2) return c;
   c.b_sub_bytes = ((c_cols * (uint32_t)c.bk * 2 + 1023) / 1024) * 1024;
   c.b_stage_bytes = (32 * nb / (uint32_t)c.bk) * c.b_sub_bytes;
@@ -142,7 +149,8 @@ inline TaCfg ta_config(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, bool st
     return c;
   }
   // staged: weights ring of 3 (2 if tight) stages, the rest of shared memory goes to the rings
-  const uint32_t budget = kSmemBudget - kBarBytes - 1024 - kTsTailBytes;
+  const uint32_t tail_bytes = ts_tail_bytes(c.g);
+  const uint32_t budget = kSmemBudget - kBarBytes - 1024 - tail_bytes;
   const uint32_t per_slot = kTsProducerWarpsCfg * nb * 512;     // bytes one more row slot costs
   for (uint32_t nB = 3; nB >= 2; --nB) {
     if (nB * c.b_stage_bytes >= budget) continue;
@@ -150,7 +158,7 @@ inline TaCfg ta_config(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, bool st
     if (rs > 8) rs = 8;
     if (rs >= 4) {
       c.nB = nB; c.rs = rs;
-      c.smem_bytes = 1024 + nB * c.b_stage_bytes + rs * per_slot + kBarBytes + kTsTailBytes;
+      c.smem_bytes = 1024 + nB * c.b_stage_bytes + rs * per_slot + kBarBytes + tail_bytes;
       c.nb = nb;
       return c;
     }
@@ -243,9 +251,9 @@ inline WpCfg wgrad_pairs_config(uint32_t c_in, uint32_t c_out, uint32_t K, uint3
   const uint64_t est_stages = (uint64_t)K * n_out / (3 * 64) + 1;
   uint32_t want = (2u * n_sms) / c.n_mtgroups;
   if (want < 1) want = 1;
-  // (per CHUNK: a CTA flushes at least once per chunk it has stages in)
-  const uint32_t min_stages = 8 + mt * c_out / 8;
-  uint64_t by_work = est_stages / n_chunks / min_stages;
+  // (per CHUNK: a CTA flushes at least once per chunk it has stages in; small layers want the
+  // parallelism more than they mind the flushes: 8 stages per CTA and chunk measured best)
+  uint64_t by_work = est_stages / n_chunks / 8;
   if (by_work < 1) by_work = 1;
   c.n_splits = (uint32_t)(by_work < want ? by_work : want);
   c.smem_bytes = 1024 + c.n_stage * c.stage_bytes + tail;
