@@ -1531,11 +1531,11 @@ k_conv_ta(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
 // 128-bit reads back), runs up to kTsDepth stages ahead, and only then moves a landed stage
 // smem -> registers -> tensor memory.  Two groups of 4 warps alternate stages; missing rows take
 // no ring space, so the ring holds ~8 stages of useful bytes per group.
-constexpr int kTsGroups = 2;
+constexpr int kTsGroups = 3;
 constexpr int kTsProducerWarps = 4 * kTsGroups;
 constexpr int kTsThreads = (kTsProducerWarps + kEpilogueWarps + 3) * 32;
 constexpr uint32_t kTsDepth = 8;             // stage descriptors / landing barriers per warp
-constexpr int kTsPf = 8;                     // neighbour indices are copied this many stages ahead
+constexpr int kTsPf = 4;                     // neighbour indices are copied this many of the group's stages ahead
 
 template <typename T, int NB, int BK, int G>
 __global__ void __launch_bounds__(kTsThreads, 1)
@@ -1552,7 +1552,7 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
   uint8_t *smem = reinterpret_cast<uint8_t *>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sB = smem_u32(smem);
-  const uint32_t ring_bytes = NB * p.rs * 512u;                      // per producer warp
+  const uint32_t ring_bytes = NB * (p.rs + 1) * 512u;                // per producer warp: RS row slots + the zero slot
   uint8_t *rings = smem + p.nB * p.b_stage_bytes;
   uint8_t *tail = rings + NP * ring_bytes;
   uint64_t *bars = reinterpret_cast<uint64_t *>(tail);
@@ -1577,6 +1577,12 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
     for (uint32_t i = 0; i < NP * kTsDepth; ++i) mbar_init(smem_u32(landed_all + i), 32);
     mbar_fence_init();
     consumed[0] = 0;
+  }
+  if (warp < NP) {
+    // slot RS of every block of this warp's ring holds zeros for good: rows without a neighbour
+    // point there, so the read-back path has no branches and no register zeroing
+    const uint32_t zbase = smem_u32(rings + warp * ring_bytes) + lane * 16 + p.rs * 512u;
+    for (int b = 0; b < NB; ++b) sts128(zbase + b * (p.rs + 1) * 512u, make_uint4(0, 0, 0, 0));
   }
   if (warp == NP + kEpilogueWarps) {
     tmem_alloc(smem_u32(tmem_slot), kTmemCols);
@@ -1658,10 +1664,11 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
         if (!__all_sync(0xffffffffu, used + nv <= RS)) break;
         const uint32_t d = tail_j % kTsDepth;
         const T *src0 = A + pis.mc * KC;
+        const uint32_t bstride = (RS + 1) * 512u;
         uint32_t dw = 0;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-          uint32_t code = 0xffu;
+          uint32_t code = RS;                 // the zero slot
           if (srow[m][0] != -2) {
             code = wr;
             const uint32_t dst = ring + wr * 512u;
@@ -1672,7 +1679,7 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
               // row that has others is zero-filled by the copy engine
               const T *src = (G == 1 ? src0 : A) + (sr < 0 ? 0 : (size_t)sr * p.c_red) +
                              (G == 1 ? b : b % NBo) * 32;
-              cp_async16(dst + b * RS * 512u, src, sr < 0 ? 0u : 16u);
+              cp_async16(dst + b * bstride, src, sr < 0 ? 0u : 16u);
             }
             if (++wr == RS) wr = 0;
           }
@@ -1693,22 +1700,18 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
         mbar_wait_park(landed + d * 8, (head / kTsDepth) & 1u);
         const uint32_t dw = desc[d * 32];
         uint4 v[4][NB];
+        const uint32_t bstride = (RS + 1) * 512u;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
           const uint32_t code = (dw >> (8 * m)) & 0xffu;
-          if (code != 0xffu) {
-            const uint32_t src = ring + code * 512u;
+          const uint32_t src = ring + code * 512u;          // code == RS: the zero slot
 #pragma unroll
-            for (int b = 0; b < NB; ++b) {
-              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                           : "=r"(v[m][b].x), "=r"(v[m][b].y), "=r"(v[m][b].z), "=r"(v[m][b].w)
-                           : "r"(src + b * RS * 512u));
-            }
-            --used;
-          } else {
-#pragma unroll
-            for (int b = 0; b < NB; ++b) v[m][b] = make_uint4(0, 0, 0, 0);
+          for (int b = 0; b < NB; ++b) {
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(v[m][b].x), "=r"(v[m][b].y), "=r"(v[m][b].z), "=r"(v[m][b].w)
+                         : "r"(src + b * bstride));
           }
+          used -= code != RS;
         }
         // A slot recycled by the tensor core?  nA is even (ta_config) and the two groups
         // alternate stages, so a slot always belongs to the same group: its previous use is
@@ -2384,9 +2387,10 @@ k_wgrad_rs2(const __grid_constant__ CUtensorMap mapG, const Wg2Params p) {
 // no wasted MMAs except the <= 63 pad pairs at the end of each offset.
 // =====================================================================================
 constexpr int kWpRows = 64;
-constexpr int kWpProducerWarps = 8;
+constexpr int kWpProducerWarps = 16;        // the producers are instruction-issue bound: many warps
+constexpr int kWpRowsPerWarp = kWpRows / kWpProducerWarps;   // pairs of a stage one warp copies
 constexpr int kWpThreads = (kWpProducerWarps + kEpilogueWarps + 1) * 32;
-constexpr int kWpMaxSlots = 8;              // 16-byte copies per thread per operand per stage
+constexpr int kWpMaxSlots = 4;              // 16-byte copies per thread per operand per stage
 constexpr int kWpPf = 8;                    // pair indices are copied this many stages ahead
 constexpr uint32_t kWpMaxSeg = 2047;        // (row chunks) x K segments a launch can walk
 
@@ -2400,47 +2404,72 @@ struct WpParams {
   uint32_t blkB, n_stage, a_bytes, stage_bytes, acc_sets;
 };
 
-// This CTA's share of the stage list: for every row chunk c the `split`-th of n_splits equal
-// slices of the chunk's stages — all CTAs sweep the chunks together, so one chunk's rows of both
-// feature matrices stay L2-resident across the K offsets.  Within a chunk the slice is walked
-// segment by segment (segment = one offset of the chunk); every role iterates identically.
+// This CTA's share of the stage list.  The list is physically (row chunk, offset)-ordered; a CTA
+// owns a contiguous range [a, b) of the OFFSET-major cumulative stage count (so it touches one or
+// two offsets and flushes its accumulator once per offset), and takes from EVERY chunk's segment
+// of such an offset the same fraction of the stages.  All CTAs therefore sweep the chunks together
+// (one chunk's rows of both feature matrices stay L2-resident) without flushing per chunk.
+// Every role iterates identically.
 struct WpWalk {
-  const int32_t *seg;      // [n_chunks*K + 1], in stages (shared memory)
-  uint32_t K, n_chunks, split, n_splits;
-  uint32_t c, sgm, s, s_end;             // current chunk, segment, stage, end of this chunk's slice
-  __device__ __forceinline__ void open_chunk() {
-    while (c < n_chunks) {
-      const uint32_t lo = (uint32_t)seg[c * K], hi = (uint32_t)seg[(c + 1) * K];
-      s = lo + (uint32_t)((uint64_t)(hi - lo) * split / n_splits);
-      s_end = lo + (uint32_t)((uint64_t)(hi - lo) * (split + 1) / n_splits);
-      if (s < s_end) {
-        sgm = c * K;
-        while ((uint32_t)seg[sgm + 1] <= s) ++sgm;
-        return;
-      }
-      ++c;
+  const int32_t *seg;      // [C*K + 1], in stages (shared memory)
+  uint32_t K, C, a, b;
+  uint32_t k, c, Sk, Tk, x0, x1, s, s_end;
+  bool fin;
+  __device__ __forceinline__ uint32_t seg_len(uint32_t cc, uint32_t kk) const {
+    return (uint32_t)(seg[cc * K + kk + 1] - seg[cc * K + kk]);
+  }
+  __device__ __forceinline__ uint32_t total_of(uint32_t kk) const {
+    uint32_t t = 0;
+    for (uint32_t cc = 0; cc < C; ++cc) t += seg_len(cc, kk);
+    return t;
+  }
+  __device__ __forceinline__ bool open_c() {      // first non-empty run of offset k at chunk >= c
+    for (; c < C; ++c) {
+      const uint32_t n = seg_len(c, k), lo = (uint32_t)seg[c * K + k];
+      s = lo + (uint32_t)((uint64_t)n * x0 / Tk);
+      s_end = lo + (uint32_t)((uint64_t)n * x1 / Tk);
+      if (s < s_end) return true;
     }
+    return false;
   }
-  __device__ __forceinline__ void init(const int32_t *seg_, uint32_t K_, uint32_t n_chunks_,
-                                       uint32_t split_, uint32_t n_splits_) {
-    seg = seg_; K = K_; n_chunks = n_chunks_; split = split_; n_splits = n_splits_;
-    c = 0; sgm = 0; s = 0; s_end = 0;
-    open_chunk();
+  __device__ __forceinline__ void open_k() {      // first offset >= k this CTA has stages of
+    for (; k < K; ++k) {
+      Tk = total_of(k);
+      if (Sk + Tk > a && Sk < b && Tk > 0) {
+        x0 = (a > Sk ? a : Sk) - Sk;
+        x1 = (b < Sk + Tk ? b : Sk + Tk) - Sk;
+        c = 0;
+        if (x0 < x1 && open_c()) return;
+      }
+      Sk += Tk;
+      if (Sk >= b) break;
+    }
+    fin = true;
   }
-  __device__ __forceinline__ bool done() const { return c >= n_chunks; }
-  // next run of stages inside one segment: [s, e) of offset k; advances past it
-  __device__ __forceinline__ void next_run(uint32_t &run_begin, uint32_t &run_end, uint32_t &k) {
-    run_begin = s;
-    run_end = min(s_end, (uint32_t)seg[sgm + 1]);
-    k = sgm - c * K;
-    s = run_end;
-    if (s >= s_end) { ++c; open_chunk(); }
-    else { while ((uint32_t)seg[sgm + 1] <= s) ++sgm; }
+  __device__ __forceinline__ void init(const int32_t *seg_, uint32_t K_, uint32_t C_,
+                                       uint32_t split, uint32_t n_splits) {
+    seg = seg_; K = K_; C = C_;
+    const uint32_t total = (uint32_t)seg[C * K];
+    a = (uint32_t)((uint64_t)total * split / n_splits);
+    b = (uint32_t)((uint64_t)total * (split + 1) / n_splits);
+    k = 0; c = 0; Sk = 0; Tk = 0; x0 = x1 = 0; s = s_end = 0; fin = a >= b;
+    if (!fin) open_k();
+  }
+  __device__ __forceinline__ bool done() const { return fin; }
+  __device__ __forceinline__ void after_run() {   // s reached s_end
+    ++c;
+    if (!open_c()) { Sk += Tk; ++k; if (Sk >= b) fin = true; else open_k(); }
+  }
+  // next run of stages inside one (chunk, offset) segment: [rb, re) of offset kk
+  __device__ __forceinline__ void next_run(uint32_t &rb, uint32_t &re, uint32_t &kk) {
+    rb = s; re = s_end; kk = k;
+    s = s_end;
+    after_run();
   }
   // single-stage stepping for the producers
   __device__ __forceinline__ uint32_t next_stage() {
     const uint32_t cur = s;
-    if (++s >= s_end) { ++c; open_chunk(); }
+    if (++s >= s_end) after_run();
     return cur;
   }
 };
@@ -2455,8 +2484,8 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
   uint64_t *bars = reinterpret_cast<uint64_t *>(tail);
   const uint32_t bar0 = smem_u32(bars);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * kMaxStages + 4);
-  int32_t *iring_all = reinterpret_cast<int32_t *>(tail + tc::kBarBytes);         // [8 warps][kWpPf][16]
-  int32_t *seg = iring_all + kWpProducerWarps * kWpPf * 16;                        // [n_seg + 1], in STAGES
+  int32_t *iring_all = reinterpret_cast<int32_t *>(tail + tc::kBarBytes);   // [warps][kWpPf][2*kWpRowsPerWarp]
+  int32_t *seg = iring_all + kWpProducerWarps * kWpPf * 2 * kWpRowsPerWarp;  // [n_seg + 1], in STAGES
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t mtg = blockIdx.x % p.n_mtgroups, split = blockIdx.x / p.n_mtgroups;
@@ -2485,45 +2514,46 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
 
   if (warp < kWpProducerWarps) {
     // =============================== PRODUCERS ======================================
+    constexpr uint32_t RW = kWpRowsPerWarp;                   // pairs of a stage this warp copies
     const T *in = reinterpret_cast<const T *>(p.in) + ch0;
     const T *gout = reinterpret_cast<const T *>(p.gout);
     const uint32_t cprA = ch_n / 8, cprB = p.c_out / 8;      // 16-byte chunks per row
-    const uint32_t nA = (8 * cprA + 31) / 32, nB = (8 * cprB + 31) / 32;   // slots per thread
+    const uint32_t nA = (RW * cprA + 31) / 32, nB = (RW * cprB + 31) / 32;   // slots per thread
     // fixed copy slots: slot s of this lane copies chunk `c % cpr` of row `c / cpr` (of the
-    // warp's 8 rows), c = lane + 32 s; destination offsets never change
+    // warp's RW rows), c = lane + 32 s; destination offsets never change
     uint32_t a_dst[kWpMaxSlots], b_dst[kWpMaxSlots], a_meta[kWpMaxSlots], b_meta[kWpMaxSlots];
 #pragma unroll
     for (int sl = 0; sl < kWpMaxSlots; ++sl) {
       const uint32_t c = lane + 32u * sl;
       {
-        const uint32_t rl = c / cprA, chunk = c - rl * cprA;
-        const bool ok = (uint32_t)sl < nA && rl < 8;
+        const uint32_t rl = c / cprA, chunk = c - rl * cprA, row = warp * RW + rl;
+        const bool ok = (uint32_t)sl < nA && rl < RW;
         a_meta[sl] = ok ? (rl | (chunk << 3)) : 0xffffffffu;
-        a_dst[sl] = (chunk >> 3) * kBlkBytes + (warp * 8 + rl) * 128 + (((chunk & 7u) ^ rl) << 4);
+        a_dst[sl] = (chunk >> 3) * kBlkBytes + row * 128 + (((chunk & 7u) ^ (row & 7u)) << 4);
       }
       {
-        const uint32_t rl = c / cprB, chunk = c - rl * cprB;
-        const bool ok = (uint32_t)sl < nB && rl < 8;
+        const uint32_t rl = c / cprB, chunk = c - rl * cprB, row = warp * RW + rl;
+        const bool ok = (uint32_t)sl < nB && rl < RW;
         b_meta[sl] = ok ? (rl | (chunk << 3)) : 0xffffffffu;
-        b_dst[sl] = p.a_bytes + (chunk >> 3) * kBlkBytes + (warp * 8 + rl) * 128 +
-                    (((chunk & 7u) ^ rl) << 4);
+        b_dst[sl] = p.a_bytes + (chunk >> 3) * kBlkBytes + row * 128 +
+                    (((chunk & 7u) ^ (row & 7u)) << 4);
       }
     }
-    // The pair lists stream from HBM: the 8 + 8 row indices of the warp's pairs of a stage are
-    // copied kWpPf stages ahead by cp.async (lanes 0-7 input rows, 8-15 output rows) into a
-    // per-warp ring in shared memory, one commit group per stage (a register ring would make
-    // every stage wait for its newest load).
-    const int32_t *list = (lane & 8u) ? p.pout : p.pin;
-    const uint32_t li = warp * 8 + (lane & 7u);
-    const uint32_t iring = smem_u32(iring_all + warp * kWpPf * 16);
+    // The pair lists stream from HBM: the RW + RW row indices of the warp's pairs of a stage are
+    // copied kWpPf stages ahead by cp.async (lanes [0, RW) input rows, [RW, 2 RW) output rows)
+    // into a per-warp ring in shared memory, one commit group per stage (a register ring would
+    // make every stage wait for its newest load).
+    const int32_t *list = lane < RW ? p.pin : p.pout;
+    const uint32_t li = warp * RW + (lane % RW);
+    const uint32_t iring = smem_u32(iring_all + warp * kWpPf * 2 * RW);
     WpWalk wk, wpf;
     wk.init(seg, p.K, p.n_chunks, split, p.n_splits);
     wpf = wk;
     auto copy_idx = [&](uint32_t n) {
       if (!wpf.done()) {
         const uint32_t stage = wpf.next_stage();
-        if (lane < 16)
-          cp_async4(iring + ((n % kWpPf) * 16 + lane) * 4, list + (size_t)stage * kWpRows + li, 4u);
+        if (lane < 2 * RW)
+          cp_async4(iring + ((n % kWpPf) * 2 * RW + lane) * 4, list + (size_t)stage * kWpRows + li, 4u);
       }
       cp_async_commit();
     };
@@ -2536,7 +2566,7 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
       if (lane == 0) mbar_wait_park(bar_emptyA(bar0, slot), ph ^ 1u);
       __syncwarp();
       const uint32_t base = s0 + slot * p.stage_bytes;
-      const uint32_t irow = iring + (n % kWpPf) * 64;
+      const uint32_t irow = iring + (n % kWpPf) * 2 * RW * 4;
 #pragma unroll
       for (int sl = 0; sl < kWpMaxSlots; ++sl) {
         if ((uint32_t)sl < nA) {
@@ -2555,7 +2585,7 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
           const uint32_t m = b_meta[sl];
           if (m != 0xffffffffu) {
             int32_t row;
-            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(row) : "r"(irow + (8u + (m & 7u)) * 4));
+            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(row) : "r"(irow + (RW + (m & 7u)) * 4));
             const T *src = gout + (row < 0 ? 0 : (size_t)row * p.c_out + (m >> 3) * 8);
             cp_async16(base + b_dst[sl], src, row < 0 ? 0u : 16u);
           }
@@ -2570,13 +2600,15 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
     cp_async_wait<0>();
   } else if (warp < kWpProducerWarps + kEpilogueWarps) {
     // =============================== EPILOGUE =======================================
+    // one flush per offset this CTA has stages of (the walker yields its runs offset by offset)
     const uint32_t q = warp & 3u;
     uint32_t acc = 0, par = 0;
     WpWalk wk;
     wk.init(seg, p.K, p.n_chunks, split, p.n_splits);
     while (!wk.done()) {
-      uint32_t rb, re, k;
+      uint32_t rb, re, k, k2;
       wk.next_run(rb, re, k);
+      while (!wk.done() && wk.k == k) wk.next_run(rb, re, k2);     // skip this offset's other runs
       mbar_wait_park(bar_tfull(bar0, acc), par);
       tc_fence_after();
       for (uint32_t t = 0; t < mt; ++t) {
@@ -2608,28 +2640,33 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
     WpWalk wk;
     wk.init(seg, p.K, p.n_chunks, split, p.n_splits);
     while (!wk.done()) {
-      uint32_t rb, re, k;
-      wk.next_run(rb, re, k);
+      const uint32_t k_cur = wk.k;
       mbar_wait_park(bar_tempty(bar0, acc), par ^ 1u);
       tc_fence_after();
       const uint32_t d0 = tmem_base + acc * p.mt_cta * p.c_out;
-      for (uint32_t st = rb; st < re; ++st) {
-        mbar_wait_park(bar_fullA(bar0, slot), ph);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t abase = s0 + slot * p.stage_bytes, bbase = abase + p.a_bytes;
-          for (uint32_t t = 0; t < mt; ++t) {
+      bool first = true;
+      while (!wk.done() && wk.k == k_cur) {          // all chunks' runs of this offset
+        uint32_t rb, re, k;
+        wk.next_run(rb, re, k);
+        for (uint32_t st = rb; st < re; ++st) {
+          mbar_wait_park(bar_fullA(bar0, slot), ph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t abase = s0 + slot * p.stage_bytes, bbase = abase + p.a_bytes;
+            for (uint32_t t = 0; t < mt; ++t) {
 #pragma unroll
-            for (int j = 0; j < kWpRows / 16; ++j) {
-              const uint64_t da = umma_desc(abase + t * 2 * kBlkBytes + j * 2048, kBlkBytes, 1024, 2);
-              const uint64_t db = umma_desc(bbase + j * 2048, kBlkBytes, 1024, 2);
-              umma_f16(d0 + t * p.c_out, da, db, idesc, (st != rb || j != 0) ? 1u : 0u);
+              for (int j = 0; j < kWpRows / 16; ++j) {
+                const uint64_t da = umma_desc(abase + t * 2 * kBlkBytes + j * 2048, kBlkBytes, 1024, 2);
+                const uint64_t db = umma_desc(bbase + j * 2048, kBlkBytes, 1024, 2);
+                umma_f16(d0 + t * p.c_out, da, db, idesc, (!first || j != 0) ? 1u : 0u);
+              }
             }
+            umma_commit(bar_emptyA(bar0, slot));
           }
-          umma_commit(bar_emptyA(bar0, slot));
+          __syncwarp();
+          first = false;
+          if (++slot == p.n_stage) { slot = 0; ph ^= 1u; }
         }
-        __syncwarp();
-        if (++slot == p.n_stage) { slot = 0; ph ^= 1u; }
       }
       if (elect_one()) umma_commit(bar_tfull(bar0, acc));
       __syncwarp();

@@ -100,9 +100,13 @@ struct TaCfg {
   uint32_t rs;            // staged kernel: row slots per producer thread (0 = register kernel)
   uint32_t g;             // offsets per stage (staged kernel, narrow layers); 1 otherwise
 };
-constexpr uint32_t kTsProducerWarpsCfg = 8;     // k_conv_ts: 2 groups x 4 warps
-// counters, landing barriers, descriptors, index rings (8 warps x 8 stages x g offsets x 128 B)
-inline uint32_t ts_tail_bytes(uint32_t g) { return 64 + 8 * 8 * 8 + 8 * 8 * 32 * 4 + 8 * 8 * g * 32 * 4; }
+constexpr uint32_t kTsGroupsCfg = 3;            // k_conv_ts: producer groups of 4 warps
+constexpr uint32_t kTsProducerWarpsCfg = 4 * kTsGroupsCfg;
+// counters, landing barriers (8 per warp), descriptors (8 x 128 B per warp), index rings
+// (4 stages x g offsets x 128 B per warp)
+inline uint32_t ts_tail_bytes(uint32_t g) {
+  return 64 + kTsProducerWarpsCfg * (8 * 8 + 8 * 32 * 4 + 4 * g * 32 * 4);
+}
 // staged = true : k_conv_ts (gathered rows wait in per-thread shared-memory rings, up to 4
 //                 blocks = 128 channels per stage)
 // staged = false: k_conv_ta (rows wait in registers, up to 3 blocks per stage)
@@ -126,7 +130,10 @@ inline TaCfg ta_config(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, bool st
     for (uint32_t R = 4; R >= 1; R >>= 1) {
       if (force_R && (int)R != force_R) continue;
       if (R > 1 && R > tiles) continue;
-      if (acc * R * c_cols + 2 * a_cols <= kTmemCols) { bestR = R; bestAcc = acc; break; }
+      // the staged kernel wants one A slot per producer group at least
+      if (acc * R * c_cols + (staged ? kTsGroupsCfg : 2u) * a_cols <= kTmemCols) {
+        bestR = R; bestAcc = acc; break;
+      }
     }
   }
   if (bestR == 0) return c;
@@ -135,7 +142,7 @@ inline TaCfg ta_config(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, bool st
   c.a_col0 = c.acc_sets * c.R * c_cols;
   c.nA = (kTmemCols - c.a_col0) / a_cols;
   if (c.nA > 8) c.nA = 8;
-  if (staged) c.nA &= ~1u;     // even: a slot always belongs to the same producer group
+  if (staged) c.nA = c.nA / kTsGroupsCfg * kTsGroupsCfg;   // a slot always belongs to the same producer group
   if (c.nA < 2) return c;
   c.b_sub_bytes = ((c_cols * (uint32_t)c.bk * 2 + 1023) / 1024) * 1024;
   c.b_stage_bytes = (32 * nb / (uint32_t)c.bk) * c.b_sub_bytes;
@@ -153,12 +160,12 @@ inline TaCfg ta_config(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, bool st
   const uint32_t budget = kSmemBudget - kBarBytes - 1024 - tail_bytes;
   const uint32_t per_slot = kTsProducerWarpsCfg * nb * 512;     // bytes one more row slot costs
   for (uint32_t nB = 3; nB >= 2; --nB) {
-    if (nB * c.b_stage_bytes >= budget) continue;
-    uint32_t rs = (budget - nB * c.b_stage_bytes) / per_slot;
+    if (nB * c.b_stage_bytes + per_slot >= budget) continue;
+    uint32_t rs = (budget - nB * c.b_stage_bytes) / per_slot - 1;   // one slot is the zero slot
     if (rs > 8) rs = 8;
     if (rs >= 4) {
       c.nB = nB; c.rs = rs;
-      c.smem_bytes = 1024 + nB * c.b_stage_bytes + rs * per_slot + kBarBytes + tail_bytes;
+      c.smem_bytes = 1024 + nB * c.b_stage_bytes + (rs + 1) * per_slot + kBarBytes + tail_bytes;
       c.nb = nb;
       return c;
     }
@@ -241,7 +248,7 @@ inline WpCfg wgrad_pairs_config(uint32_t c_in, uint32_t c_out, uint32_t K, uint3
   c.a_bytes = mt * 2 * kBlkBytes;
   c.stage_bytes = c.a_bytes + c.blkB * kBlkBytes;
   c.acc_sets = 2 * mt * c_out <= kTmemCols ? 2 : 1;
-  const uint32_t tail = kBarBytes + 8 * 8 * 16 * 4 + (K * n_chunks + 1) * 4 + 64;   // barriers, index rings, segment table
+  const uint32_t tail = kBarBytes + 16 * 8 * 8 * 4 + (K * n_chunks + 1) * 4 + 64;   // barriers, index rings (16 warps x 8 stages x 8 indices), segment table
   c.n_stage = (kSmemBudget - 1024 - tail) / c.stage_bytes;
   if (c.n_stage > 16) c.n_stage = 16;
   if (c.n_stage < 2) return c;
@@ -251,9 +258,7 @@ inline WpCfg wgrad_pairs_config(uint32_t c_in, uint32_t c_out, uint32_t K, uint3
   const uint64_t est_stages = (uint64_t)K * n_out / (3 * 64) + 1;
   uint32_t want = (2u * n_sms) / c.n_mtgroups;
   if (want < 1) want = 1;
-  // (per CHUNK: a CTA flushes at least once per chunk it has stages in; small layers want the
-  // parallelism more than they mind the flushes: 8 stages per CTA and chunk measured best)
-  uint64_t by_work = est_stages / n_chunks / 8;
+  uint64_t by_work = est_stages / 8;
   if (by_work < 1) by_work = 1;
   c.n_splits = (uint32_t)(by_work < want ? by_work : want);
   c.smem_bytes = 1024 + c.n_stage * c.stage_bytes + tail;
