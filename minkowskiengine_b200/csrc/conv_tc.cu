@@ -2387,11 +2387,12 @@ k_wgrad_rs2(const __grid_constant__ CUtensorMap mapG, const Wg2Params p) {
 // no wasted MMAs except the <= 63 pad pairs at the end of each offset.
 // =====================================================================================
 constexpr int kWpRows = 64;
-constexpr int kWpProducerWarps = 16;        // the producers are instruction-issue bound: many warps
-constexpr int kWpRowsPerWarp = kWpRows / kWpProducerWarps;   // pairs of a stage one warp copies
+constexpr int kWpGroups = 3;                // producer groups: group g owns stages n = g (mod 3)
+constexpr int kWpProducerWarps = 4 * kWpGroups;   // 4 warps per group, 16 pairs of a stage each
+constexpr int kWpRowsPerWarp = 16;
 constexpr int kWpThreads = (kWpProducerWarps + kEpilogueWarps + 1) * 32;
-constexpr int kWpMaxSlots = 4;              // 16-byte copies per thread per operand per stage
-constexpr int kWpPf = 8;                    // pair indices are copied this many stages ahead
+constexpr int kWpMaxSlots = 8;              // 16-byte copies per thread per operand per 8 rows
+constexpr int kWpPf = 4;                    // pair indices are copied this many of the group's stages ahead
 constexpr uint32_t kWpMaxSeg = 2047;        // (row chunks) x K segments a launch can walk
 
 struct WpParams {
@@ -2472,6 +2473,15 @@ struct WpWalk {
     if (++s >= s_end) after_run();
     return cur;
   }
+  __device__ __forceinline__ void skip(uint32_t n) {      // pass over n stages
+    while (n > 0 && !fin) {
+      const uint32_t left = s_end - s;
+      if (n < left) { s += n; return; }
+      n -= left;
+      s = s_end;
+      after_run();
+    }
+  }
 };
 
 template <typename T>
@@ -2484,8 +2494,8 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
   uint64_t *bars = reinterpret_cast<uint64_t *>(tail);
   const uint32_t bar0 = smem_u32(bars);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * kMaxStages + 4);
-  int32_t *iring_all = reinterpret_cast<int32_t *>(tail + tc::kBarBytes);   // [warps][kWpPf][2*kWpRowsPerWarp]
-  int32_t *seg = iring_all + kWpProducerWarps * kWpPf * 2 * kWpRowsPerWarp;  // [n_seg + 1], in STAGES
+  int32_t *iring_all = reinterpret_cast<int32_t *>(tail + tc::kBarBytes);   // [warps][kWpPf][32]
+  int32_t *seg = iring_all + kWpProducerWarps * kWpPf * 32;                  // [n_seg + 1], in STAGES
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t mtg = blockIdx.x % p.n_mtgroups, split = blockIdx.x / p.n_mtgroups;
@@ -2497,7 +2507,7 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
   for (uint32_t i = threadIdx.x; i <= n_seg; i += kWpThreads) seg[i] = __ldg(p.seg_start + i) / kWpRows;
   if (threadIdx.x == 0) {
     for (uint32_t i = 0; i < p.n_stage; ++i) {
-      mbar_init(bar_fullA(bar0, i), kWpProducerWarps * 32);
+      mbar_init(bar_fullA(bar0, i), 4 * 32);       // the four warps of the owning group
       mbar_init(bar_emptyA(bar0, i), 1);
     }
     for (uint32_t i = 0; i < 2; ++i) { mbar_init(bar_tfull(bar0, i), 1); mbar_init(bar_tempty(bar0, i), kEpilogueWarps * 32); }
@@ -2514,89 +2524,105 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
 
   if (warp < kWpProducerWarps) {
     // =============================== PRODUCERS ======================================
-    constexpr uint32_t RW = kWpRowsPerWarp;                   // pairs of a stage this warp copies
+    // The producers are bound by the instruction latency of a single warp (~10 cycles per
+    // instruction, ~150 instructions per stage): with all warps filling every stage in lockstep a
+    // stage cost ~1500 cycles whatever the memory system did (r2_run5/7).  So the stages are dealt
+    // to kWpGroups groups of 4 warps; a group fills its stage alone (16 pairs per warp, as two
+    // halves of 8 rows over the fixed copy slots) while the other groups fill theirs.
+    const uint32_t grp = warp >> 2, qw = warp & 3u;
     const T *in = reinterpret_cast<const T *>(p.in) + ch0;
     const T *gout = reinterpret_cast<const T *>(p.gout);
     const uint32_t cprA = ch_n / 8, cprB = p.c_out / 8;      // 16-byte chunks per row
-    const uint32_t nA = (RW * cprA + 31) / 32, nB = (RW * cprB + 31) / 32;   // slots per thread
-    // fixed copy slots: slot s of this lane copies chunk `c % cpr` of row `c / cpr` (of the
-    // warp's RW rows), c = lane + 32 s; destination offsets never change
+    const uint32_t nA = (8 * cprA + 31) / 32, nB = (8 * cprB + 31) / 32;   // slots per thread per 8 rows
+    // fixed copy slots: slot s of this lane copies chunk `c % cpr` of row `c / cpr` (of 8 rows),
+    // c = lane + 32 s; destination offsets never change (the second half adds 8 rows = 1024 B)
     uint32_t a_dst[kWpMaxSlots], b_dst[kWpMaxSlots], a_meta[kWpMaxSlots], b_meta[kWpMaxSlots];
 #pragma unroll
     for (int sl = 0; sl < kWpMaxSlots; ++sl) {
       const uint32_t c = lane + 32u * sl;
       {
-        const uint32_t rl = c / cprA, chunk = c - rl * cprA, row = warp * RW + rl;
-        const bool ok = (uint32_t)sl < nA && rl < RW;
+        const uint32_t rl = c / cprA, chunk = c - rl * cprA;
+        const bool ok = (uint32_t)sl < nA && rl < 8;
         a_meta[sl] = ok ? (rl | (chunk << 3)) : 0xffffffffu;
-        a_dst[sl] = (chunk >> 3) * kBlkBytes + row * 128 + (((chunk & 7u) ^ (row & 7u)) << 4);
+        a_dst[sl] = (chunk >> 3) * kBlkBytes + (qw * 16 + rl) * 128 + (((chunk & 7u) ^ rl) << 4);
       }
       {
-        const uint32_t rl = c / cprB, chunk = c - rl * cprB, row = warp * RW + rl;
-        const bool ok = (uint32_t)sl < nB && rl < RW;
+        const uint32_t rl = c / cprB, chunk = c - rl * cprB;
+        const bool ok = (uint32_t)sl < nB && rl < 8;
         b_meta[sl] = ok ? (rl | (chunk << 3)) : 0xffffffffu;
-        b_dst[sl] = p.a_bytes + (chunk >> 3) * kBlkBytes + row * 128 +
-                    (((chunk & 7u) ^ (row & 7u)) << 4);
+        b_dst[sl] = p.a_bytes + (chunk >> 3) * kBlkBytes + (qw * 16 + rl) * 128 +
+                    (((chunk & 7u) ^ rl) << 4);
       }
     }
-    // The pair lists stream from HBM: the RW + RW row indices of the warp's pairs of a stage are
-    // copied kWpPf stages ahead by cp.async (lanes [0, RW) input rows, [RW, 2 RW) output rows)
-    // into a per-warp ring in shared memory, one commit group per stage (a register ring would
-    // make every stage wait for its newest load).
-    const int32_t *list = lane < RW ? p.pin : p.pout;
-    const uint32_t li = warp * RW + (lane % RW);
-    const uint32_t iring = smem_u32(iring_all + warp * kWpPf * 2 * RW);
+    // The pair lists stream from HBM: the 16 + 16 row indices of the warp's pairs of a stage are
+    // copied kWpPf of the group's stages ahead by cp.async (lanes 0-15 input rows, 16-31 output
+    // rows) into a per-warp ring in shared memory, one commit group per stage (a register ring
+    // would make every stage wait for its newest load).
+    const int32_t *list = lane < 16 ? p.pin : p.pout;
+    const uint32_t li = qw * 16 + (lane & 15u);
+    const uint32_t iring = smem_u32(iring_all + warp * kWpPf * 32);
     WpWalk wk, wpf;
     wk.init(seg, p.K, p.n_chunks, split, p.n_splits);
-    wpf = wk;
-    auto copy_idx = [&](uint32_t n) {
-      if (!wpf.done()) {
-        const uint32_t stage = wpf.next_stage();
-        if (lane < 2 * RW)
-          cp_async4(iring + ((n % kWpPf) * 2 * RW + lane) * 4, list + (size_t)stage * kWpRows + li, 4u);
-      }
-      cp_async_commit();
-    };
+    wk.skip(grp);
+    wpf.init(seg, p.K, p.n_chunks, split, p.n_splits);
+    wpf.skip(grp);
+    // (a macro, not a lambda: a by-reference capture would put the walkers in local memory)
+#define MEB_WP_COPY_IDX(nn)                                                                       \
+    do {                                                                                          \
+      if (!wpf.done()) {                                                                          \
+        const uint32_t stage__ = wpf.s;                                                           \
+        wpf.skip(kWpGroups);                                                                      \
+        cp_async4(iring + (((nn) % kWpPf) * 32 + lane) * 4, list + (size_t)stage__ * kWpRows + li, 4u); \
+      }                                                                                           \
+      cp_async_commit();                                                                          \
+    } while (0)
 #pragma unroll 1
-    for (uint32_t d = 0; d < (uint32_t)kWpPf; ++d) copy_idx(d);
-    uint32_t slot = 0, ph = 0, n = 0;
+    for (uint32_t d = 0; d < (uint32_t)kWpPf; ++d) MEB_WP_COPY_IDX(d);
+    // the group's stage n uses ring slot (grp + 3 n) % n_stage; n_stage is a multiple of 3, so a
+    // slot always belongs to the same group and a one-bit parity wait on "empty" is exact
+    uint32_t slot = grp, ph = 0, n = 0;
     while (!wk.done()) {
-      wk.next_stage();
+      wk.skip(kWpGroups);
       cp_async_wait<kWpPf - 1>();      // this stage's indices (copied kWpPf stages ago) landed
       if (lane == 0) mbar_wait_park(bar_emptyA(bar0, slot), ph ^ 1u);
       __syncwarp();
       const uint32_t base = s0 + slot * p.stage_bytes;
-      const uint32_t irow = iring + (n % kWpPf) * 2 * RW * 4;
+      const uint32_t irow = iring + (n % kWpPf) * 128;
 #pragma unroll
-      for (int sl = 0; sl < kWpMaxSlots; ++sl) {
-        if ((uint32_t)sl < nA) {
-          const uint32_t m = a_meta[sl];
-          if (m != 0xffffffffu) {
-            int32_t row;
-            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(row) : "r"(irow + (m & 7u) * 4));
-            const T *src = in + (row < 0 ? 0 : (size_t)row * p.c_in + (m >> 3) * 8);
-            cp_async16(base + a_dst[sl], src, row < 0 ? 0u : 16u);
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int sl = 0; sl < kWpMaxSlots; ++sl) {
+          if ((uint32_t)sl < nA) {
+            const uint32_t m = a_meta[sl];
+            if (m != 0xffffffffu) {
+              int32_t row;
+              asm volatile("ld.shared.s32 %0, [%1];" : "=r"(row) : "r"(irow + (h * 8 + (m & 7u)) * 4));
+              const T *src = in + (row < 0 ? 0 : (size_t)row * p.c_in + (m >> 3) * 8);
+              cp_async16(base + a_dst[sl] + h * 1024, src, row < 0 ? 0u : 16u);
+            }
           }
         }
-      }
 #pragma unroll
-      for (int sl = 0; sl < kWpMaxSlots; ++sl) {
-        if ((uint32_t)sl < nB) {
-          const uint32_t m = b_meta[sl];
-          if (m != 0xffffffffu) {
-            int32_t row;
-            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(row) : "r"(irow + (RW + (m & 7u)) * 4));
-            const T *src = gout + (row < 0 ? 0 : (size_t)row * p.c_out + (m >> 3) * 8);
-            cp_async16(base + b_dst[sl], src, row < 0 ? 0u : 16u);
+        for (int sl = 0; sl < kWpMaxSlots; ++sl) {
+          if ((uint32_t)sl < nB) {
+            const uint32_t m = b_meta[sl];
+            if (m != 0xffffffffu) {
+              int32_t row;
+              asm volatile("ld.shared.s32 %0, [%1];" : "=r"(row) : "r"(irow + (16 + h * 8 + (m & 7u)) * 4));
+              const T *src = gout + (row < 0 ? 0 : (size_t)row * p.c_out + (m >> 3) * 8);
+              cp_async16(base + b_dst[sl] + h * 1024, src, row < 0 ? 0u : 16u);
+            }
           }
         }
       }
       cp_async_mbar_arrive(bar_fullA(bar0, slot));
-      if (++slot == p.n_stage) { slot = 0; ph ^= 1u; }
+      slot += kWpGroups;
+      if (slot >= p.n_stage) { slot -= p.n_stage; ph ^= 1u; }
       __syncwarp();                    // ring row n % kWpPf fully read: reuse it
-      copy_idx(n + kWpPf);
+      MEB_WP_COPY_IDX(n + kWpPf);
       ++n;
     }
+#undef MEB_WP_COPY_IDX
     cp_async_wait<0>();
   } else if (warp < kWpProducerWarps + kEpilogueWarps) {
     // =============================== EPILOGUE =======================================

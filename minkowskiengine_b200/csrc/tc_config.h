@@ -248,10 +248,11 @@ inline WpCfg wgrad_pairs_config(uint32_t c_in, uint32_t c_out, uint32_t K, uint3
   c.a_bytes = mt * 2 * kBlkBytes;
   c.stage_bytes = c.a_bytes + c.blkB * kBlkBytes;
   c.acc_sets = 2 * mt * c_out <= kTmemCols ? 2 : 1;
-  const uint32_t tail = kBarBytes + 16 * 8 * 8 * 4 + (K * n_chunks + 1) * 4 + 64;   // barriers, index rings (16 warps x 8 stages x 8 indices), segment table
+  const uint32_t tail = kBarBytes + 12 * 4 * 32 * 4 + (K * n_chunks + 1) * 4 + 64;   // barriers, index rings (12 warps x 4 stages x 32 indices), segment table
   c.n_stage = (kSmemBudget - 1024 - tail) / c.stage_bytes;
-  if (c.n_stage > 16) c.n_stage = 16;
-  if (c.n_stage < 2) return c;
+  if (c.n_stage > 12) c.n_stage = 12;
+  c.n_stage = c.n_stage / 3 * 3;       // a multiple of the 3 producer groups (slot ownership)
+  if (c.n_stage < 3) return c;
   // row-range splits: two waves of CTAs at most, and enough stages per CTA to amortise its
   // accumulator flush (mt*128 x c_out reductions into dW; ~one stage's time per 16 columns) on
   // the estimate "a third of the K*n_out table entries are pairs"
