@@ -254,21 +254,6 @@ int meb200_bn_backward_apply_fused(const void *dy, const void *x, const void *y_
                                    const double *d_count, void *dx, void *d_residual,
                                    void *stream);
 
-/* ---- experimental: forward convolution over spatially ordered row tiles -------------------
- * Same result as meb200_conv_forward (reference: ConvolutionForwardKernelGPU
- * src/convolution_kernel.cu:320-496), but the 128-row tiles of the kernel walk the output rows
- * in the order `row_ids` (a permutation of [0, n_out), e.g. Morton order of the coordinates):
- * tile_nbr[k][j] = out_nbr[k][row_ids[j]] and the result of tile row j is stored to row
- * row_ids[j] of `out`.  A tile of spatially adjacent rows re-reads the same source rows for most
- * of its offsets (4.8x on the bench's clouds), which the kernel's L1-allocating gathers can
- * serve from cache.  Tensor-core path only (bf16, the 96-channel shape in round 1); returns
- * MEB200_ERR_UNSUPPORTED otherwise.  Written at the end of round 1, not yet run on a GPU. */
-int meb200_conv_forward_ordered(const void *in, int in_dtype, uint32_t n_in, uint32_t c_in,
-                                const void *weight, uint32_t K, uint32_t c_out,
-                                const int32_t *tile_nbr, const int32_t *row_ids, uint32_t n_out,
-                                void *out, int out_dtype, void *workspace,
-                                uint64_t workspace_bytes, void *stream);
-
 /* ---- synchronised batch norm: statistics exchange over NVLink peer memory ----------------
  * Replaces the per-layer NCCL all-reduce of torch.nn.SyncBatchNorm (reference:
  * MinkowskiEngine/MinkowskiNormalization.py:101-192, examples/multigpu_ddp.py:91-95) by one

@@ -61,8 +61,6 @@ PROTOTYPES = {
     "meb200_bn_backward_reduce_fused": (_i32, [_vp, _vp, _vp, _i32, _u32, _u32, _vp, _vp, _vp, _vp]),
     "meb200_bn_backward_apply_fused": (_i32, [_vp, _vp, _vp, _i32, _u32, _u32, _vp, _vp, _vp, _vp,
                                               C.c_double, _vp, _vp, _vp, _vp]),
-    "meb200_conv_forward_ordered": (_i32, [_vp, _i32, _u32, _u32, _vp, _u32, _u32, _vp, _vp, _u32,
-                                           _vp, _i32, _vp, C.c_uint64, _vp]),
     "meb200_peer_allreduce_f64": (_i32, [_vp, C.c_uint64, _u32, _u32, _u32, _u32, _vp, _vp]),
 }
 

@@ -80,7 +80,7 @@ int meb200_conv_forward_packed(const void *in, int in_dtype, uint32_t n_in, uint
   }
   // W^T[k][c_out][c_in] is operand B as the kernels want it: the "no transpose" entry
   return conv_forward_tc(in, in_dtype, n_in, c_in, weight_t, K, c_out, /*dgrad=*/true, out_nbr,
-                         n_out, out, out_dtype, nullptr, stream, nullptr,
+                         n_out, out, out_dtype, nullptr, stream,
                          c_in % 32 == 0 ? weight_tp : nullptr);
 }
 
@@ -106,7 +106,7 @@ int meb200_conv_backward_packed(const void *in, const void *grad_out, int dtype,
   if (grad_in != nullptr && n_in > 0) {
     MEB_CHECK_ARG(in_nbr && w_cast && (grad_out || n_out == 0), "null buffer");
     int rc = conv_forward_tc(grad_out, dtype, n_out, c_out, w_cast, K, c_in, /*dgrad=*/true, in_nbr,
-                             n_in, grad_in, grad_in_dtype, nullptr, stream, nullptr,
+                             n_in, grad_in, grad_in_dtype, nullptr, stream,
                              c_out % 32 == 0 ? w_cp : nullptr);
     if (rc != MEB200_OK) return rc;
   }
@@ -126,27 +126,6 @@ int meb200_conv_backward_packed(const void *in, const void *grad_out, int dtype,
     return conv_wgrad_tc(in, grad_out, dtype, c_in, K, c_out, out_nbr, n_out, grad_weight, stream);
   }
   return MEB200_OK;
-}
-
-int meb200_conv_forward_ordered(const void *in, int in_dtype, uint32_t n_in, uint32_t c_in,
-                                const void *weight, uint32_t K, uint32_t c_out,
-                                const int32_t *tile_nbr, const int32_t *row_ids, uint32_t n_out,
-                                void *out, int out_dtype, void *workspace,
-                                uint64_t workspace_bytes, void *stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  if (n_out == 0) return MEB200_OK;
-  MEB_CHECK_ARG(in_dtype >= 0 && in_dtype <= 2 && out_dtype >= 0 && out_dtype <= 2, "dtype");
-  MEB_CHECK_ARG(out_dtype == MEB200_F32 || out_dtype == in_dtype,
-                "output dtype must be fp32 or the input dtype");
-  MEB_CHECK_ARG(out && weight && tile_nbr && row_ids && in, "null buffer");
-  MEB_CHECK_ARG(c_in > 0 && c_out > 0 && K > 0, "empty channel/kernel dims");
-  if (!conv_tc_supported(in_dtype, c_in, c_out) || c_out > 256 ||
-      workspace_bytes < (uint64_t)K * c_in * c_out * 2) {
-    set_error("ordered convolution: shape/dtype outside the tensor-core path or workspace too small");
-    return MEB200_ERR_UNSUPPORTED;
-  }
-  return conv_forward_tc(in, in_dtype, n_in, c_in, weight, K, c_out, /*dgrad=*/false, tile_nbr,
-                         n_out, out, out_dtype, workspace, stream, row_ids);
 }
 
 int meb200_conv_backward(const void *in, const void *grad_out, int dtype, uint32_t n_in,

@@ -38,8 +38,6 @@ using tc::kBlkBytes;
 constexpr int kProducerWarps = 4;   // wgrad kernel
 constexpr int kEpilogueWarps = 4;
 constexpr int kThreads = (kProducerWarps + kEpilogueWarps + 1) * 32;
-constexpr int kFwdProducerWarps = 8;  // forward/dgrad kernel: one warp fills a whole stage
-constexpr int kFwdThreads = (kFwdProducerWarps + kEpilogueWarps + 1) * 32;
 
 struct TcParams {
   const void *A;        // [n_a, c_red] gathered operand
@@ -57,23 +55,7 @@ struct TcParams {
   uint32_t lag;          // cp.async groups each producer thread keeps in flight
   uint32_t wb_k_stride;  // elements between consecutive offsets in Wb
   uint32_t out_ld;       // leading dimension (elements) of `out`
-  // EXP bit 3 (ordered tiles): output row of tile row j when the tiles walk the rows in another
-  // order than the tensor stores them (nbr is then indexed by tile row); nullptr otherwise
-  const int32_t *row_ids;
 };
-
-// Runs f(integral_constant<int, d>) for the run-time d in [0, N): a warp-uniform compare chain
-// that lets a REGISTER array (a prefetch ring) be addressed by a run-time position without
-// unrolling the caller by N or demoting the array to local memory.
-template <int I, int N, typename F>
-__device__ __forceinline__ void static_switch(uint32_t d, F &&f) {
-  if constexpr (I + 1 >= N) {
-    f(std::integral_constant<int, I>{});
-  } else {
-    if (d == (uint32_t)I) f(std::integral_constant<int, I>{});
-    else static_switch<I + 1, N>(d, f);
-  }
-}
 
 template <int BK>
 struct Swz {
@@ -115,25 +97,17 @@ __device__ __forceinline__ uint32_t bar_tfull(uint32_t b0, uint32_t i) { return 
 __device__ __forceinline__ uint32_t bar_tempty(uint32_t b0, uint32_t i) { return b0 + 8u * (4 * kMaxStages + 2 + i); }
 
 // Epilogue warps: accumulator (TMEM) -> registers -> converted 16-byte global stores.
-// EXP (experiments, see k_conv_rs): bit 1 = output stores carry an L2 evict-first policy.
-template <typename T, int RT, int EXP = 0>
+template <typename T, int RT>
 __device__ __forceinline__ void epilogue_role(const TcParams &p, uint32_t bar0, uint32_t tmem_base,
                                               uint32_t q, uint32_t lane) {
   constexpr uint32_t R = RT;
-  uint64_t pol_stream = 0;
-  if constexpr ((EXP & 2) != 0) pol_stream = l2_policy_evict_first();
-  (void)pol_stream;
   uint32_t t = 0;
   for (uint32_t st = blockIdx.x; st < p.n_super; st += gridDim.x, ++t) {
     const uint32_t acc = t & 1u, par = (t >> 1) & 1u;   // two accumulator sets
-    mbar_wait(bar_tfull(bar0, acc), par);
+    mbar_wait_park(bar_tfull(bar0, acc), par);
     tc_fence_after();
     for (uint32_t r = 0; r < R; ++r) {
       const uint32_t row = (st * R + r) * kTileM + q * 32 + lane;
-      uint32_t orow = row;       // where the row lives in the output tensor
-      if constexpr ((EXP & 8) != 0) {
-        if (row < p.n_rows) orow = (uint32_t)__ldg(p.row_ids + row);
-      }
       const uint32_t col0 = (acc * R + r) * p.c_cols;
       for (uint32_t c = 0; c < p.c_cols; c += 16) {
         uint32_t v[16];
@@ -142,19 +116,14 @@ __device__ __forceinline__ void epilogue_role(const TcParams &p, uint32_t bar0, 
         if (row < p.n_rows) {
           if (p.out_f32) {
             float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) +
-                                                     (size_t)orow * p.out_ld + c);
+                                                     (size_t)row * p.out_ld + c);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if constexpr ((EXP & 2) != 0)
-                stg128_hint(dst + i, make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]),
-                            pol_stream);
-              else
-                dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                     __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-            }
+            for (int i = 0; i < 4; ++i)
+              dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                   __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
           } else {
             uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<T *>(p.out) +
-                                                   (size_t)orow * p.out_ld + c);
+                                                   (size_t)row * p.out_ld + c);
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
               uint4 w;
@@ -162,8 +131,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams &p, uint32_t bar0, 
               w.y = pack2<T>(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
               w.z = pack2<T>(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
               w.w = pack2<T>(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
-              if constexpr ((EXP & 2) != 0) stg128_hint(dst + i, w, pol_stream);
-              else dst[i] = w;
+              dst[i] = w;
             }
           }
         }
@@ -301,36 +269,16 @@ __device__ __forceinline__ uint4 ldg128(const void *p) {
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
-// L1-allocating variant: with spatially ordered tiles a CTA gathers the same row for several
-// offsets, so the copy in L1 is worth keeping (EXP bit 3).
-__device__ __forceinline__ uint4 ldg128_l1(const void *p) {
-  uint4 v;
-  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  return v;
-}
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// EXP selects experiments prepared at the end of round 1 (MEB200_RS_EXP, only instantiated for
-// the 96-channel shape <bf16, 32, 2, 3>; EXP = 0 is the measured kernel, bit for bit):
-//   bit 0: per-slot dirty-row masks - a stage is zeroed once at kernel start, afterwards only
-//          rows that held data in the slot's previous use and hold none now are cleared
-//          (instead of storing the full 24 KB of zeros per stage);
-//   bit 1: the streamed data (neighbour table, output rows) carries an L2 evict-first policy;
-//   bit 2: the gathered feature rows carry an L2 evict-last policy;
-//   bit 3: ordered tiles - the tiles walk the rows in a spatially coherent order (p.nbr is
-//          indexed by tile row, the epilogue stores to p.row_ids[row]) and the gathers allocate
-//          in L1, where a tile's ~5x re-reads of the same source rows can hit
-//          (meb200_conv_forward_ordered, minkowskiengine_b200/tile_order.py).
-template <typename T, int BK, int RT, int CPS, int EXP = 0>
+template <typename T, int BK, int RT, int CPS>
 __global__ void __launch_bounds__(kRsThreads, 1)
 k_conv_rs(const __grid_constant__ CUtensorMap mapB, const TcParams p) {
   using S = Swz<BK>;
   constexpr int NP = kRsProducerWarps;
   constexpr uint32_t R = RT;
-  constexpr bool kDirty = (EXP & 1) != 0, kStreamHint = (EXP & 2) != 0, kKeepHint = (EXP & 4) != 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -344,18 +292,9 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapB, const TcParams p) {
   uint2 *scratch_all = reinterpret_cast<uint2 *>(tail + tc::kBarBytes);
   volatile uint32_t *consumed = reinterpret_cast<volatile uint32_t *>(
       tail + tc::kBarBytes + kRsProducerWarps * kTileM * 8);
-  // kDirty: [nA][4] row masks (bit = the row holds data), after the scratch area proper
-  uint32_t *dirty = reinterpret_cast<uint32_t *>(tail + tc::kBarBytes + tc::kRsScratchBytes);
-  (void)dirty;
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if constexpr (kDirty) {
-    for (uint32_t off = threadIdx.x * 16; off < p.nA * p.a_stage_bytes; off += kRsThreads * 16)
-      sts128(sA + off, make_uint4(0, 0, 0, 0));
-    for (uint32_t i = threadIdx.x; i < p.nA * 4; i += kRsThreads) dirty[i] = 0;
-    fence_proxy_async();   // the zeros must be visible to the tensor core's reads
-  }
   if (threadIdx.x == 0) {
     for (uint32_t i = 0; i < p.nA; ++i) { mbar_init(bar_fullA(bar0, i), 1); mbar_init(bar_emptyA(bar0, i), 1); }
     for (uint32_t i = 0; i < p.nB; ++i) { mbar_init(bar_fullB(bar0, i), 1); mbar_init(bar_emptyB(bar0, i), 1); }
@@ -395,10 +334,6 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapB, const TcParams p) {
       return q;
     };
     int32_t idx_cur[4], idx_nxt[4];
-    uint64_t pol_stream = 0, pol_keep = 0;
-    if constexpr (kStreamHint) pol_stream = l2_policy_evict_first();
-    if constexpr (kKeepHint) pol_keep = l2_policy_evict_last();
-    (void)pol_stream; (void)pol_keep;
     auto load_idx = [&](uint32_t g, int32_t (&dst)[4]) {
       const Pos q = decode(g);
       const int32_t *nbr_k = p.nbr + (size_t)q.k * p.n_rows;
@@ -406,8 +341,7 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapB, const TcParams p) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const uint32_t grow = row0 + i * 32;
-        if constexpr (kStreamHint) dst[i] = (grow < p.n_rows) ? ldg32_hint(nbr_k + grow, pol_stream) : -1;
-        else dst[i] = (grow < p.n_rows) ? __ldg(nbr_k + grow) : -1;
+        dst[i] = (grow < p.n_rows) ? __ldg(nbr_k + grow) : -1;
       }
     };
     constexpr uint32_t step = NP;   // every producer warp takes stages (see release_role)
@@ -422,16 +356,13 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapB, const TcParams p) {
       const uint32_t c0 = q.mc * p.cps * BK;
       // ---- compact the valid rows of this stage into the warp's scratch list ----------
       uint32_t V = 0;
-      uint32_t mnew[4];   // kDirty: which tile rows of this stage hold data
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const bool ok = idx_cur[i] >= 0;
         const uint32_t m = __ballot_sync(0xffffffffu, ok);
         if (ok) scratch[V + __popc(m & lane_lt)] = make_uint2((uint32_t)idx_cur[i], (uint32_t)(i * 32 + lane));
         V += __popc(m);
-        mnew[i] = m;
       }
-      (void)mnew;
       __syncwarp();
       const uint32_t dstA = sA + sa * p.a_stage_bytes;
       bool slot_ready = false;
@@ -451,9 +382,7 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapB, const TcParams p) {
             const T *src = srcA + (size_t)srow * p.c_red;
 #pragma unroll
             for (int sc = 0; sc < CPS; ++sc) {
-              if constexpr (kKeepHint) v[ri * CPS + sc] = ldg128_hint(src + sc * BK, pol_keep);
-              else if constexpr ((EXP & 8) != 0) v[ri * CPS + sc] = ldg128_l1(src + sc * BK);
-              else v[ri * CPS + sc] = ldg128(src + sc * BK);
+              v[ri * CPS + sc] = ldg128(src + sc * BK);
             }
           } else {
 #pragma unroll
@@ -474,32 +403,8 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapB, const TcParams p) {
               tma_load_2d(dstB + sbi * p.b_sub_bytes, &mapB, (int32_t)(c0 + sbi * BK), brow,
                           bar_fullB(bar0, sb));
           }
-          if constexpr (kDirty) {
-            // clear only rows that were written by the slot's previous user and are empty now
-            constexpr uint32_t kLanesPerRow = CPS * S::kChunks;      // 16-byte pieces of a row
-            constexpr uint32_t kRowsPerPass = 32 / kLanesPerRow;
-            const uint32_t sel = lane / kLanesPerRow, piece = lane % kLanesPerRow;
-            const uint32_t psc = piece / S::kChunks, pchunk = piece % S::kChunks;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint32_t z = dirty[sa * 4 + i] & ~mnew[i];
-              while (z) {                                   // warp-uniform
-                uint32_t zz = z;                            // this lane group's row: the
-                for (uint32_t j = 0; j < sel; ++j) zz &= zz - 1;   // sel-th lowest set bit
-                if (sel < kRowsPerPass && zz) {
-                  const uint32_t row = (uint32_t)i * 32 + (uint32_t)__ffs(zz) - 1u;
-                  sts128(dstA + psc * p.a_sub_bytes + S::offset(row, pchunk), make_uint4(0, 0, 0, 0));
-                }
-                for (uint32_t j = 0; j < kRowsPerPass && z; ++j) z &= z - 1;
-              }
-            }
-            __syncwarp();
-            if (lane < 4)
-              dirty[sa * 4 + lane] = lane == 0 ? mnew[0] : (lane == 1 ? mnew[1] : (lane == 2 ? mnew[2] : mnew[3]));
-          } else {
-            for (uint32_t off = lane * 16; off < p.a_stage_bytes; off += 512)
-              sts128(dstA + off, make_uint4(0, 0, 0, 0));
-          }
+          for (uint32_t off = lane * 16; off < p.a_stage_bytes; off += 512)
+            sts128(dstA + off, make_uint4(0, 0, 0, 0));
           __syncwarp();
           slot_ready = true;
         }
@@ -523,316 +428,12 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapB, const TcParams p) {
       for (int i = 0; i < 4; ++i) idx_cur[i] = idx_nxt[i];
     }
   } else if (warp < NP + kEpilogueWarps) {
-    epilogue_role<T, RT, EXP>(p, bar0, tmem_base, warp & 3u, lane);
+    epilogue_role<T, RT>(p, bar0, tmem_base, warp & 3u, lane);
   } else if (warp == NP + kEpilogueWarps) {
     mma_role_fast<T, BK, RT, CPS>(p, sA, sB, bar0, tmem_base);   // whole warp, one lane issues
   } else if (lane == 0) {
     // its own warp: a thread parked in mbarrier.try_wait must not hold up the MMA issuer
     release_role<RT>(p, bar0, consumed);
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == NP + kEpilogueWarps) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
-  }
-}
-
-// TMA = true : operands are fetched by the TMA unit (row gather4 for A, tile loads for B);
-// TMA = false: cp.async path (kept as a fallback; the LSU-driven copies top out near
-//              20 B/cycle/SM on B200).
-template <typename T, int BK, int RT, bool TMA>
-__global__ void __launch_bounds__(kFwdThreads, 1)
-k_conv_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-          const TcParams p) {
-  using S = Swz<BK>;
-  constexpr int NP = kFwdProducerWarps;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // dynamic smem base is only guaranteed 16 B aligned: round up to the swizzle atom
-  uint8_t *smem = reinterpret_cast<uint8_t *>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t sA = smem_u32(smem);
-  const uint32_t sB = sA + p.nA * p.a_stage_bytes;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + p.nA * p.a_stage_bytes +
-                                                p.nB * p.b_stage_bytes);
-  const uint32_t bar0 = smem_u32(bars);
-  // barrier slots: fullA[kMax] emptyA[kMax] fullB[kMax] emptyB[kMax] tfull[2] tempty[2]
-  auto fullA = [&](uint32_t i) { return bar0 + 8u * i; };
-  auto emptyA = [&](uint32_t i) { return bar0 + 8u * (kMaxStages + i); };
-  auto fullB = [&](uint32_t i) { return bar0 + 8u * (2 * kMaxStages + i); };
-  auto emptyB = [&](uint32_t i) { return bar0 + 8u * (3 * kMaxStages + i); };
-  auto tfull = [&](uint32_t i) { return bar0 + 8u * (4 * kMaxStages + i); };
-  auto tempty = [&](uint32_t i) { return bar0 + 8u * (4 * kMaxStages + 2 + i); };
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * kMaxStages + 4);
-
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr uint32_t R = RT;
-
-  if (threadIdx.x == 0) {
-    for (uint32_t i = 0; i < p.nA; ++i) {
-      // cp.async: the 32 lanes of the producer warp that fills the stage; TMA: one
-      // arrive.expect_tx, the copies complete the transaction count
-      mbar_init(fullA(i), TMA ? 1 : 32);
-      mbar_init(emptyA(i), 1);
-    }
-    for (uint32_t i = 0; i < p.nB; ++i) {
-      mbar_init(fullB(i), TMA ? 1 : 32);
-      mbar_init(emptyB(i), 1);
-    }
-    for (uint32_t i = 0; i < 2; ++i) {
-      mbar_init(tfull(i), 1);
-      mbar_init(tempty(i), kEpilogueWarps * 32);
-    }
-    mbar_fence_init();
-  }
-  if (warp == NP + kEpilogueWarps) {
-    tmem_alloc(smem_u32(tmem_slot), kTmemCols);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (TMA && warp < NP) {
-    // =============================== TMA PRODUCERS ==================================
-    // Stages are dealt round-robin to (at most) two issuing warps.  Per stage a warp reads the
-    // 128 neighbour rows of the tile (lane l owns rows 4l..4l+3, fetched one stage ahead) and
-    // every lane issues ONE row-gather of its four rows per channel chunk; lane 0 arms the
-    // barrier with the byte count and loads the B slice when the stage opens a new group.
-    constexpr uint32_t NPT = 2;
-    const uint32_t SPK = p.n_macro * R;
-    const uint32_t SPS = p.K * SPK;
-    const uint32_t n_my = p.n_super > blockIdx.x
-                              ? (p.n_super - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const uint32_t total = n_my * SPS;
-    struct Pos { uint32_t st, k, mc, r; };
-    auto decode = [&](uint32_t g) {
-      Pos q;
-      const uint32_t t = g / SPS, rem = g - t * SPS;
-      q.st = blockIdx.x + t * gridDim.x;
-      q.k = rem / SPK;
-      const uint32_t rem2 = rem - q.k * SPK;
-      q.mc = rem2 / R;
-      q.r = rem2 - q.mc * R;
-      return q;
-    };
-    int32_t idx_cur[4], idx_nxt[4];
-    auto load_idx = [&](uint32_t g, int32_t (&dst)[4]) {
-      const Pos q = decode(g);
-      const int32_t *nbr_k = p.nbr + (size_t)q.k * p.n_rows;
-      const uint32_t row0 = (q.st * R + q.r) * kTileM + lane * 4;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t grow = row0 + i;
-        const int32_t v = (grow < p.n_rows) ? __ldg(nbr_k + grow) : -1;
-        dst[i] = v < 0 ? (int32_t)p.n_a : v;   // out of bounds -> TMA zero fill
-      }
-    };
-    const uint32_t step = p.nA < NPT ? p.nA : NPT;
-    uint32_t g = warp < step ? warp : total;
-    if (warp < step && lane == 0) { tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB); }
-    if (g < total) load_idx(g, idx_cur);
-    for (; g < total; g += step) {
-      if (g + step < total) load_idx(g + step, idx_nxt);
-      const Pos q = decode(g);
-      const uint32_t sa = g % p.nA, pha = (g / p.nA) & 1u;
-      const int32_t c0 = (int32_t)(q.mc * p.cps * BK);
-      mbar_wait(emptyA(sa), pha ^ 1u);
-      if (q.r == 0) {
-        const uint32_t gb = g / R, sb = gb % p.nB, phb = (gb / p.nB) & 1u;
-        mbar_wait(emptyB(sb), phb ^ 1u);
-        if (lane == 0) {
-          mbar_arrive_expect_tx(fullB(sb), p.cps * p.c_cols * BK * 2);
-          const uint32_t dstB = sB + sb * p.b_stage_bytes;
-          const int32_t brow = (int32_t)(q.k * p.wb_rows_per_k + p.wb_row0);
-          for (uint32_t s = 0; s < p.cps; ++s)
-            tma_load_2d(dstB + s * p.b_sub_bytes, &mapB, c0 + (int32_t)(s * BK), brow, fullB(sb));
-        }
-      }
-      if (lane == 0) mbar_arrive_expect_tx(fullA(sa), p.cps * kTileM * BK * 2);
-      __syncwarp();
-      const uint32_t dstA = sA + sa * p.a_stage_bytes + lane * 4 * S::kRowBytes;
-      for (uint32_t s = 0; s < p.cps; ++s)
-        tma_gather4(dstA + s * p.a_sub_bytes, &mapA, c0 + (int32_t)(s * BK), idx_cur[0], idx_cur[1],
-                    idx_cur[2], idx_cur[3], fullA(sa));
-#pragma unroll
-      for (int i = 0; i < 4; ++i) idx_cur[i] = idx_nxt[i];
-    }
-  } else if (!TMA && warp < NP) {
-    // =============================== PRODUCERS ======================================
-    // Pipeline stages are dealt round-robin to the NP producer warps; a warp fills its whole
-    // stage (128 gathered rows x cps channel chunks, plus the B slice when it owns the first
-    // row tile of a (offset, chunk) group), so NP different stages are being filled at once.
-    const uint32_t sub_row = lane / S::kChunks, chunk = lane % S::kChunks;
-    const T *A = reinterpret_cast<const T *>(p.A);
-    const T *Wb = reinterpret_cast<const T *>(p.Wb);
-    const uint32_t SPK = p.n_macro * R;   // A stages per (super tile, offset)
-    const uint32_t SPS = p.K * SPK;       // A stages per super tile
-    const uint32_t n_my = p.n_super > blockIdx.x
-                              ? (p.n_super - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const uint32_t total = n_my * SPS;
-    struct Pos { uint32_t st, k, mc, r; };
-    auto decode = [&](uint32_t g) {
-      Pos q;
-      const uint32_t t = g / SPS, rem = g - t * SPS;
-      q.st = blockIdx.x + t * gridDim.x;
-      q.k = rem / SPK;
-      const uint32_t rem2 = rem - q.k * SPK;
-      q.mc = rem2 / R;
-      q.r = rem2 - q.mc * R;
-      return q;
-    };
-    // lane l holds the neighbour rows of tile rows l, l+32, l+64, l+96 (coalesced table reads);
-    // the copy loop pulls them out with shuffles.  The indices of the warp's next kCpRing stages
-    // sit in a register ring addressed through static_switch:
-    // with one stage of look-ahead every stage waited out most of an index-load latency (the
-    // same stall profiles/r1_ncu_k_wgrad_tc_block8_96x96.txt shows for the wgrad producers).
-    constexpr int kCpRing = 4;
-    auto load_idx = [&](uint32_t g, int32_t (&dst)[4]) {
-      const Pos q = decode(g);
-      const int32_t *nbr_k = p.nbr + (size_t)q.k * p.n_rows;
-      const uint32_t row0 = (q.st * R + q.r) * kTileM + lane;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t grow = row0 + i * 32;
-        dst[i] = (grow < p.n_rows) ? __ldg(nbr_k + grow) : -1;
-      }
-    };
-    // Only min(NP, nA) warps take stages: a warp's consecutive stages (g, g + step) must be at
-    // most one ring revolution apart, otherwise the parity wait on the empty barrier could be
-    // satisfied by a phase two uses back (the mbarrier only remembers one parity bit).
-    const uint32_t step = p.nA < (uint32_t)NP ? p.nA : (uint32_t)NP;
-    auto fill_stage = [&](uint32_t g, const int32_t (&idx_cur)[4]) {
-      const Pos q = decode(g);
-      const uint32_t sa = g % p.nA, pha = (g / p.nA) & 1u;
-      const uint32_t c0 = q.mc * p.cps * BK + chunk * 8;   // first channel this lane copies
-      mbar_wait(emptyA(sa), pha ^ 1u);
-      if (q.r == 0) {
-        const uint32_t gb = g / R, sb = gb % p.nB, phb = (gb / p.nB) & 1u;
-        mbar_wait(emptyB(sb), phb ^ 1u);
-        const uint32_t dstB = sB + sb * p.b_stage_bytes;
-        const T *srcB = Wb + (size_t)q.k * p.wb_k_stride + c0;
-        for (uint32_t n = sub_row; n < p.c_cols; n += S::kRowsPerInstr) {
-          const T *src = srcB + (size_t)n * p.c_red;
-          const uint32_t dst = dstB + S::offset(n, chunk);
-          for (uint32_t s = 0; s < p.cps; ++s) cp_async16(dst + s * p.b_sub_bytes, src + s * BK, 16);
-        }
-        cp_async_mbar_arrive(fullB(sb));
-      }
-      const uint32_t dstA = sA + sa * p.a_stage_bytes;
-#pragma unroll
-      for (int it = 0; it < S::kItersA; ++it) {
-        const int slot = (it * S::kRowsPerInstr) / 32;
-        const uint32_t row = it * S::kRowsPerInstr + sub_row;
-        const int32_t src_row = __shfl_sync(0xffffffffu, idx_cur[slot], row & 31u);
-        const T *src = A + (size_t)(src_row < 0 ? 0 : src_row) * p.c_red + c0;
-        const uint32_t dst = dstA + S::offset(row, chunk);
-        const uint32_t nbytes = src_row < 0 ? 0u : 16u;
-        for (uint32_t s = 0; s < p.cps; ++s) cp_async16(dst + s * p.a_sub_bytes, src + s * BK, nbytes);
-      }
-      cp_async_mbar_arrive(fullA(sa));   // fires once this warp's copies for the stage landed
-    };
-    int32_t ring[kCpRing][4];
-    const uint32_t g0 = warp < step ? warp : total;
-#pragma unroll
-    for (int d = 0; d < kCpRing; ++d) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) ring[d][i] = -1;
-      if (g0 + d * step < total) load_idx(g0 + d * step, ring[d]);
-    }
-    uint32_t d = 0;
-    for (uint32_t g = g0; g < total; g += step) {
-      int32_t idx_cur[4];
-      static_switch<0, kCpRing>(d, [&](auto D) {      // waits for ring[d]'s loads only
-#pragma unroll
-        for (int i = 0; i < 4; ++i) idx_cur[i] = ring[decltype(D)::value][i];
-      });
-      fill_stage(g, idx_cur);
-      const uint32_t gn = g + kCpRing * step;
-      if (gn < total)
-        static_switch<0, kCpRing>(d, [&](auto D) { load_idx(gn, ring[decltype(D)::value]); });
-      if (++d == (uint32_t)kCpRing) d = 0;
-    }
-    cp_async_wait<0>();  // nothing of this thread may still be in flight at teardown
-  } else if (warp < NP + kEpilogueWarps) {
-    // =============================== EPILOGUE =======================================
-    const uint32_t q = warp & 3u;  // TMEM lane quadrant this warp may access
-    uint32_t t = 0;
-    for (uint32_t st = blockIdx.x; st < p.n_super; st += gridDim.x, ++t) {
-      const uint32_t acc = t & 1u, par = (t >> 1) & 1u;   // two accumulator sets
-      mbar_wait(tfull(acc), par);
-      tc_fence_after();
-      for (uint32_t r = 0; r < R; ++r) {
-        const uint32_t row = (st * R + r) * kTileM + q * 32 + lane;
-        const uint32_t col0 = (acc * R + r) * p.c_cols;
-        for (uint32_t c = 0; c < p.c_cols; c += 16) {
-          uint32_t v[16];
-          tmem_ld16(tmem_base + ((q * 32u) << 16) + col0 + c, v);
-          tmem_ld_wait();
-          if (row < p.n_rows) {
-            if (p.out_f32) {
-              float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) +
-                                                       (size_t)row * p.out_ld + c);
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                     __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-            } else {
-              uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<T *>(p.out) +
-                                                     (size_t)row * p.out_ld + c);
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                uint4 w;
-                w.x = pack2<T>(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]));
-                w.y = pack2<T>(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
-                w.z = pack2<T>(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
-                w.w = pack2<T>(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
-                dst[i] = w;
-              }
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(tempty(acc));
-    }
-  } else if (lane == 0) {
-    // =============================== MMA ISSUER =====================================
-    const uint32_t idesc = umma_idesc_f16(Fmt<T>::v, kTileM, p.c_cols, 0, 0);
-    uint32_t t = 0, sa = 0, pha = 0, sb = 0, phb = 0;
-    for (uint32_t st = blockIdx.x; st < p.n_super; st += gridDim.x, ++t) {
-      const uint32_t acc = t & 1u, par = (t >> 1) & 1u;
-      mbar_wait(tempty(acc), par ^ 1u);
-      tc_fence_after();
-      for (uint32_t k = 0; k < p.K; ++k) {
-        for (uint32_t mc = 0; mc < p.n_macro; ++mc) {
-          mbar_wait(fullB(sb), phb);
-          const uint32_t bbase = sB + sb * p.b_stage_bytes;
-#pragma unroll
-          for (int r = 0; r < RT; ++r) {
-            mbar_wait(fullA(sa), pha);
-            tc_fence_after();
-            const uint32_t abase = sA + sa * p.a_stage_bytes;
-            const uint32_t d = tmem_base + (acc * R + r) * p.c_cols;
-            for (uint32_t s = 0; s < p.cps; ++s) {
-#pragma unroll
-              for (int j = 0; j < BK / 16; ++j) {
-                uint64_t da = umma_desc(abase + s * p.a_sub_bytes + j * 32, 16, S::kSbo, S::kLayout);
-                uint64_t db = umma_desc(bbase + s * p.b_sub_bytes + j * 32, 16, S::kSbo, S::kLayout);
-                umma_f16(d, da, db, idesc, (k | mc | s | (uint32_t)j) != 0u);
-              }
-            }
-            umma_commit(emptyA(sa));
-            if (++sa == p.nA) { sa = 0; pha ^= 1u; }
-          }
-          umma_commit(emptyB(sb));
-          if (++sb == p.nB) { sb = 0; phb ^= 1u; }
-        }
-      }
-      umma_commit(tfull(acc));
-    }
   }
 
   tc_fence_before();
@@ -973,18 +574,6 @@ static int make_map_2d(CUtensorMap *m, int dtype, const void *base, uint64_t row
   return MEB200_OK;
 }
 
-// operand-A fetch strategy: 2 = register staged (default), 1 = TMA row gather, 0 = cp.async
-static int gather_mode() {
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("MEB200_TC_GATHER");   // "rs" (default) | "tma" | "cpasync"
-    v = (e && e[0] == 'c') ? 0 : ((e && e[0] == 't') ? 1 : 2);
-    if (v != 0 && encode_tiled_fn() == nullptr) v = 0;
-  }
-  return v;
-}
-
-
 // Opt a kernel in to >48 KB of dynamic shared memory.  The attribute is per (function, device):
 // the flags are keyed on the function pointer VALUE and the current device (round 1 kept one
 // static flag inside a generic lambda, which every k_wgrad_tc<T,PF> instantiation shared because
@@ -1006,10 +595,10 @@ static int ensure_big_smem(const void *fn) {
 }
 #define MEB_BIG_SMEM(kern) do { int rc__ = ensure_big_smem((const void *)(kern)); if (rc__ != MEB200_OK) return rc__; } while (0)
 
-template <typename T, int BK, int RT, int CPS, int EXP = 0>
+template <typename T, int BK, int RT, int CPS>
 static int launch_rs(const CUtensorMap &mB, const TcParams &p, size_t smem_bytes, unsigned grid,
                      cudaStream_t stream) {
-  auto kern = k_conv_rs<T, BK, RT, CPS, EXP>;
+  auto kern = k_conv_rs<T, BK, RT, CPS>;
   MEB_BIG_SMEM(kern);
   kern<<<grid, kRsThreads, smem_bytes, stream>>>(mB, p);
   count_tc_launch();
@@ -1039,149 +628,48 @@ static int launch_rs_bk_r(int bk, uint32_t R, uint32_t cps, const CUtensorMap &m
 #undef MEB_RS_R
 }
 
-template <typename T, int BK, int RT, bool TMA>
-static int launch_tc(const CUtensorMap &mA, const CUtensorMap &mB, const TcParams &p,
-                     size_t smem_bytes, unsigned grid, cudaStream_t stream) {
-  auto kern = k_conv_tc<T, BK, RT, TMA>;
-  MEB_BIG_SMEM(kern);
-  kern<<<grid, kFwdThreads, smem_bytes, stream>>>(mA, mB, p);
-  count_tc_launch();
-  MEB_LAUNCH_OK();
-  return MEB200_OK;
-}
-
-template <typename T>
-static int launch_tc_bk_r(int bk, uint32_t R, bool tma, const CUtensorMap &mA,
-                          const CUtensorMap &mB, const TcParams &p, size_t smem, unsigned grid,
-                          cudaStream_t s) {
-#define MEB_TC_R(BKV, TM)                                                     \
-  switch (R) {                                                                \
-    case 4: return launch_tc<T, BKV, 4, TM>(mA, mB, p, smem, grid, s);        \
-    case 2: return launch_tc<T, BKV, 2, TM>(mA, mB, p, smem, grid, s);        \
-    default: return launch_tc<T, BKV, 1, TM>(mA, mB, p, smem, grid, s);       \
-  }
-  if (tma) {
-    switch (bk) {
-      case 64: MEB_TC_R(64, true)
-      case 32: MEB_TC_R(32, true)
-      default: MEB_TC_R(16, true)
-    }
-  }
-  switch (bk) {
-    case 64: MEB_TC_R(64, false)
-    case 32: MEB_TC_R(32, false)
-    default: MEB_TC_R(16, false)
-  }
-#undef MEB_TC_R
-}
-
-// One launch over output columns [0, c_cols) of a problem whose B operand / output may be
-// slices of wider tensors (N-splitting for c_cols > 256).
+// One launch of k_conv_rs over output columns [0, c_cols) of a problem whose B operand / output
+// may be slices of wider tensors (N-splitting for c_cols > 256).  The fallback for reduction
+// widths that are not a multiple of 32 channels and for callers that pass un-packed weights.
 static int launch_tc_slice(const void *A, int dtype, uint32_t n_a, uint32_t c_reduce,
                            const void *Wb_full, uint32_t c_cols_full, uint32_t n0, uint32_t K,
                            uint32_t c_cols, const int32_t *nbr, uint32_t n_rows, void *out,
-                           uint32_t out_ld, int out_dtype, cudaStream_t stream,
-                           const int32_t *row_ids = nullptr) {
+                           uint32_t out_ld, int out_dtype, cudaStream_t stream) {
   const void *Wb = reinterpret_cast<const uint8_t *>(Wb_full) + (size_t)n0 * c_reduce * 2;
-  const uint32_t wb_k_stride = c_cols_full * c_reduce;
   TcParams p{};
   p.A = A; p.Wb = Wb; p.nbr = nbr; p.out = out;
   p.c_red = c_reduce; p.c_cols = c_cols; p.K = K; p.n_rows = n_rows;
   p.out_f32 = out_dtype == MEB200_F32;
-  p.wb_k_stride = wb_k_stride; p.out_ld = out_ld;
+  p.wb_k_stride = c_cols_full * c_reduce; p.out_ld = out_ld;
   p.n_a = n_a; p.wb_row0 = n0; p.wb_rows_per_k = c_cols_full;
-  p.row_ids = row_ids;
-  // tuning knob MEB200_TC_STAGE_KB: largest A stage.  24 KB = one 128B-swizzle chunk per stage
-  // for BK=64 and three 64B-swizzle chunks for BK=32 — the best of the sweep in profiles/.
-  static int max_stage_kb = -1;
-  if (max_stage_kb < 0) {
-    const char *e = getenv("MEB200_TC_STAGE_KB");
-    max_stage_kb = e ? atoi(e) : 24;
-    if (max_stage_kb <= 0) max_stage_kb = 24;
+  if ((reinterpret_cast<uintptr_t>(A) & 15) != 0 || (reinterpret_cast<uintptr_t>(Wb_full) & 15) != 0 ||
+      encode_tiled_fn() == nullptr) {
+    set_error("conv tc: operands must be 16-byte aligned and the driver must provide tensor maps");
+    return MEB200_ERR_UNSUPPORTED;
   }
-  const bool aligned = (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
-                       (reinterpret_cast<uintptr_t>(Wb_full) & 15) == 0;
-  const int mode = (n_a > 0 && aligned) ? gather_mode() : 0;
-  // MEB200_RS_EXP = 1 | 2 | 6 | 7: experiments inside k_conv_rs (see the kernel), compiled for
-  // the 96-channel bf16 shape only; anything else runs the measured kernel.
-  int rs_exp = 0;
-  if (const char *e = getenv("MEB200_RS_EXP")) rs_exp = atoi(e);
-  uint32_t budget = tc::kSmemBudget;
-  if (row_ids != nullptr) {
-    // ordered tiles (meb200_conv_forward_ordered): bit 3 plus, optionally, the hints (2) or the
-    // hints and the dirty-row masks (3) from MEB200_RS_EXP; MEB200_TC_SMEM_KB shrinks the ring so
-    // that the unified L1/shared array keeps room for L1
-    rs_exp = 8 | ((rs_exp & 3) == 3 ? 3 : (rs_exp & 2));
-    if (const char *e = getenv("MEB200_TC_SMEM_KB")) {
-      const int kb = atoi(e);
-      if (kb >= 64 && kb * 1024 < (int)tc::kSmemBudget) budget = (uint32_t)kb * 1024;
-    }
-    if (dtype != MEB200_BF16 || mode != 2) {
-      set_error("conv tc: ordered tiles need bf16 features and the register-staged kernel");
-      return MEB200_ERR_UNSUPPORTED;
-    }
-  } else if (!(rs_exp == 1 || rs_exp == 2 || rs_exp == 6 || rs_exp == 7) || dtype != MEB200_BF16 ||
-             mode != 2) {
-    rs_exp = 0;
-  }
-  const uint32_t rs_extra = (rs_exp & 1) ? 512u : 0u;   // dirty-row masks behind the scratch area
-  tc::FwdCfg cfg = tc::fwd_config(c_reduce, c_cols, n_rows, (uint32_t)max_stage_kb * 1024,
-                                  mode == 2 ? tc::kRsScratchBytes + rs_extra : 0, budget);
-  if (rs_exp != 0 && !(cfg.bk == 32 && cfg.R == 2 && cfg.cps == 3)) {
-    if (row_ids != nullptr) {
-      set_error("conv tc: ordered tiles are compiled for the <bf16, 32, 2, 3> shape only "
-                "(got bk=%d R=%u cps=%u)", cfg.bk, cfg.R, cfg.cps);
-      return MEB200_ERR_UNSUPPORTED;
-    }
-    rs_exp = 0;
-    if (rs_extra)
-      cfg = tc::fwd_config(c_reduce, c_cols, n_rows, (uint32_t)max_stage_kb * 1024, tc::kRsScratchBytes);
-  }
-  if (mode == 2 && !((cfg.bk == 64 && cfg.cps <= 2) || (cfg.bk != 64 && (cfg.cps == 1 || cfg.cps == 3))))
+  // 24 KB stages: one 128B-swizzle chunk per stage for BK = 64, three 64B-swizzle chunks for
+  // BK = 32 (the best of the round-1 sweep)
+  tc::FwdCfg cfg = tc::fwd_config(c_reduce, c_cols, n_rows, 24 * 1024, tc::kRsScratchBytes);
+  if (!((cfg.bk == 64 && cfg.cps <= 2) || (cfg.bk != 64 && (cfg.cps == 1 || cfg.cps == 3))))
     cfg = tc::fwd_config(c_reduce, c_cols, n_rows, 1, tc::kRsScratchBytes);   // one chunk per stage
   if (cfg.bk == 0 || cfg.pipe.lag < 1) {
     set_error("conv tc: no pipeline configuration fits (c_red=%u c_cols=%u)", c_reduce, c_cols);
     return MEB200_ERR_UNSUPPORTED;
   }
-  const int bk = cfg.bk;
   const uint32_t R = cfg.R;
   p.R = R; p.acc_stages = 2; p.n_super = cfg.n_super;
   p.a_stage_bytes = cfg.a_stage_bytes; p.b_stage_bytes = cfg.b_stage_bytes;
-  p.cps = cfg.cps; p.n_macro = c_reduce / (uint32_t)bk / cfg.cps;
+  p.cps = cfg.cps; p.n_macro = c_reduce / (uint32_t)cfg.bk / cfg.cps;
   p.a_sub_bytes = cfg.a_sub_bytes; p.b_sub_bytes = cfg.b_sub_bytes;
   p.lag = cfg.pipe.lag; p.nA = cfg.pipe.nA; p.nB = cfg.pipe.nB;
-  size_t smem_bytes = cfg.smem_bytes;
-  unsigned grid = p.n_super < (uint32_t)num_sms() ? p.n_super : (unsigned)num_sms();
-  CUtensorMap mA, mB;
-  memset(&mA, 0, sizeof(mA));
+  const unsigned grid = p.n_super < (uint32_t)num_sms() ? p.n_super : (unsigned)num_sms();
+  CUtensorMap mB;
   memset(&mB, 0, sizeof(mB));
-  const bool tma = mode == 1;
-  if (mode != 0) {
-    int rc = make_map_2d(&mB, dtype, Wb_full, (uint64_t)K * c_cols_full, c_reduce, (uint32_t)bk, c_cols);
-    if (rc != MEB200_OK) return rc;
-    if (mode == 1) {
-      rc = make_map_2d(&mA, dtype, A, n_a, c_reduce, (uint32_t)bk, 1);
-      if (rc != MEB200_OK) return rc;
-    }
-  }
-  if (mode == 2) {
-    switch (rs_exp) {
-      case 1: return launch_rs<__nv_bfloat16, 32, 2, 3, 1>(mB, p, smem_bytes, grid, stream);
-      case 2: return launch_rs<__nv_bfloat16, 32, 2, 3, 2>(mB, p, smem_bytes, grid, stream);
-      case 6: return launch_rs<__nv_bfloat16, 32, 2, 3, 6>(mB, p, smem_bytes, grid, stream);
-      case 7: return launch_rs<__nv_bfloat16, 32, 2, 3, 7>(mB, p, smem_bytes, grid, stream);
-      case 8: return launch_rs<__nv_bfloat16, 32, 2, 3, 8>(mB, p, smem_bytes, grid, stream);
-      case 10: return launch_rs<__nv_bfloat16, 32, 2, 3, 10>(mB, p, smem_bytes, grid, stream);
-      case 11: return launch_rs<__nv_bfloat16, 32, 2, 3, 11>(mB, p, smem_bytes, grid, stream);
-      default: break;
-    }
-    if (dtype == MEB200_BF16)
-      return launch_rs_bk_r<__nv_bfloat16>(bk, R, cfg.cps, mB, p, smem_bytes, grid, stream);
-    return launch_rs_bk_r<__half>(bk, R, cfg.cps, mB, p, smem_bytes, grid, stream);
-  }
+  int rc = make_map_2d(&mB, dtype, Wb_full, (uint64_t)K * c_cols_full, c_reduce, (uint32_t)cfg.bk, c_cols);
+  if (rc != MEB200_OK) return rc;
   if (dtype == MEB200_BF16)
-    return launch_tc_bk_r<__nv_bfloat16>(bk, R, tma, mA, mB, p, smem_bytes, grid, stream);
-  return launch_tc_bk_r<__half>(bk, R, tma, mA, mB, p, smem_bytes, grid, stream);
+    return launch_rs_bk_r<__nv_bfloat16>(cfg.bk, R, cfg.cps, mB, p, cfg.smem_bytes, grid, stream);
+  return launch_rs_bk_r<__half>(cfg.bk, R, cfg.cps, mB, p, cfg.smem_bytes, grid, stream);
 }
 
 // =====================================================================================
@@ -1207,11 +695,6 @@ static int launch_tc_slice(const void *A, int dtype, uint32_t n_a, uint32_t c_re
 // long as B agrees, so the weights are PACKED in that order once per optimizer step
 // (k_pack_w, ta_perm) instead of shuffling registers in the hot loop.
 // =====================================================================================
-constexpr int kTaGroups = 3;
-constexpr int kTaProducerWarps = 4 * kTaGroups;
-// warps [0,12) producers, [12,16) epilogue, 16 MMA, 17 release, 18 B loader
-constexpr int kTaThreads = (kTaProducerWarps + kEpilogueWarps + 3) * 32;
-
 struct TaParams {
   const void *A;        // [n_a, c_red] gathered operand
   const int32_t *nbr;   // [K, n_rows]
@@ -1340,19 +823,6 @@ __device__ __forceinline__ void ta_mma(const TaParams &p, uint32_t sB, uint32_t 
   }
 }
 
-// consumes the A-slot "empty" completions strictly in order and publishes a monotonic count
-// (a producer group may run several ring revolutions ahead of a one-bit parity wait)
-__device__ __forceinline__ void ta_release(const TaParams &p, uint32_t bar0,
-                                           volatile uint32_t *consumed, uint32_t total) {
-  uint32_t sa = 0, pha = 0, done = 0;
-  for (uint32_t g = 0; g < total; ++g) {
-    mbar_wait_park(bar_emptyA(bar0, sa), pha);
-    __threadfence_block();
-    sts_volatile(consumed, ++done);
-    if (++sa == p.nA) { sa = 0; pha ^= 1u; }
-  }
-}
-
 // G > 1: a stage spans G consecutive offsets (narrow layers: c_red = 32 NB / G channels each),
 // its B sub-tiles come from G different offsets; offsets past K repeat the last one (their A
 // blocks are zero).
@@ -1410,123 +880,10 @@ struct TaPos {
   }
 };
 
-// ---- v1: gathered rows wait in REGISTERS (3 producer groups, one stage each) -------------------
-// NB = 32-channel blocks per stage (stage = 32 NB channels = 16 NB TMEM columns);
-// BK = channel width of one B sub-tile in shared memory (64 -> 128B swizzle, 32 -> 64B swizzle).
-template <typename T, int NB, int BK>
-__global__ void __launch_bounds__(kTaThreads, 1)
-k_conv_ta(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
-  constexpr uint32_t KC = 32u * NB;            // channels per stage
-  constexpr uint32_t kACols = 16u * NB;        // TMEM columns of one A slot
-  constexpr int NP = kTaProducerWarps;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t sB = smem_u32(smem);
-  uint8_t *tail = smem + p.nB * p.b_stage_bytes;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(tail);
-  const uint32_t bar0 = smem_u32(bars);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * kMaxStages + 4);
-  volatile uint32_t *consumed = reinterpret_cast<volatile uint32_t *>(tail + tc::kBarBytes);
-
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t R = p.R;
-  const uint32_t SPS = p.Kg * p.n_macro * R;   // A stages per super tile
-  const uint32_t n_my = p.n_super > blockIdx.x
-                            ? (p.n_super - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const uint32_t total = n_my * SPS;
-
-  if (threadIdx.x == 0) {
-    for (uint32_t i = 0; i < p.nA; ++i) { mbar_init(bar_fullA(bar0, i), 4); mbar_init(bar_emptyA(bar0, i), 1); }
-    for (uint32_t i = 0; i < p.nB; ++i) { mbar_init(bar_fullB(bar0, i), 1); mbar_init(bar_emptyB(bar0, i), 1); }
-    for (uint32_t i = 0; i < 2; ++i) { mbar_init(bar_tfull(bar0, i), 1); mbar_init(bar_tempty(bar0, i), kEpilogueWarps * 32); }
-    mbar_fence_init();
-    consumed[0] = 0;
-  }
-  if (warp == NP + kEpilogueWarps) {
-    tmem_alloc(smem_u32(tmem_slot), kTmemCols);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp < NP) {
-    // =============================== PRODUCERS ======================================
-    const uint32_t grp = warp >> 2, quad = warp & 3u;
-    const uint32_t piece = lane & 3u, rsub = lane >> 2;
-    const T *A = reinterpret_cast<const T *>(p.A);
-    TaPos cur, nxt;
-    cur.init(grp, R, p.n_macro, p.Kg);
-    nxt = cur;
-    // lane l fetches the neighbour of row l of this warp's quadrant (one coalesced 128-byte read)
-    auto load_idx = [&](const TaPos &q) -> int32_t {
-      const uint32_t grow = (q.st * R + q.r) * kTileM + quad * 32 + lane;
-      return grow < p.n_rows ? __ldg(p.nbr + (size_t)q.k * p.n_rows + grow) : -1;
-    };
-    uint32_t g = grp, slot = grp % p.nA;
-    int32_t idx_cur = g < total ? load_idx(cur) : -1, idx_nxt = -1;
-    for (; g < total; g += kTaGroups) {
-      nxt.advance(kTaGroups, R, p.n_macro, p.Kg);
-      if (g + kTaGroups < total) idx_nxt = load_idx(nxt);
-      const T *src0 = A + cur.mc * KC + piece * 8;
-      // rows m = 2*half + hi  ->  quadrant row half*16 + hi*8 + rsub
-      uint4 v[4][NB];
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const int32_t srow = __shfl_sync(0xffffffffu, idx_cur, (m >> 1) * 16 + (m & 1) * 8 + (int)rsub);
-        if (srow >= 0) {
-          const T *src = src0 + (size_t)srow * p.c_red;
-#pragma unroll
-          for (int b = 0; b < NB; ++b) v[m][b] = ldg128(src + b * 32);
-        } else {
-#pragma unroll
-          for (int b = 0; b < NB; ++b) v[m][b] = make_uint4(0, 0, 0, 0);
-        }
-      }
-      wait_consumed(consumed, g, p.nA, lane);      // A slot recycled by the tensor core?
-      tc_fence_after();
-      const uint32_t ta = tmem_base + p.a_col0 + slot * kACols + ((quad * 32u) << 16);
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-          const uint4 lo = v[2 * half][b], hi = v[2 * half + 1][b];
-          tmem_st_16x256b_x2(ta + ((uint32_t)(half * 16) << 16) + b * 16,
-                             lo.x, lo.y, hi.x, hi.y, lo.z, lo.w, hi.z, hi.w);
-        }
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_fullA(bar0, slot));
-      idx_cur = idx_nxt;
-      cur = nxt;
-      slot = (slot + kTaGroups) % p.nA;
-    }
-  } else if (warp < NP + kEpilogueWarps) {
-    ta_epilogue<T>(p, bar0, tmem_base, warp & 3u, lane);
-  } else if (warp == NP + kEpilogueWarps) {
-    ta_mma<T, NB, BK>(p, sB, bar0, tmem_base);
-  } else if (warp == NP + kEpilogueWarps + 1) {
-    if (lane == 0) ta_release(p, bar0, consumed, total);
-  } else {
-    if (lane == 0) ta_bload<NB, BK>(&mapB, p, sB, bar0);
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == NP + kEpilogueWarps) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
-  }
-}
-
-// ---- v2: gathered rows wait in SHARED MEMORY, one private ring per thread ----------------------
-// v1 keeps 3 stages x ~7.6 KB of useful loads in flight per SM; measured (profiles/r2_notes.md)
-// that leaves a stage at ~1200 cycles, the gather latency under load, against 288 cycles of
-// tensor time.  Here a producer thread copies its VALID rows with cp.async into a private ring
+// ---- gathered rows wait in SHARED MEMORY, one private ring per thread ---------------------------
+// (A first version kept them in registers: 3 stages x ~7.6 KB of useful loads in flight per SM,
+// ~1200 cycles per stage, profiles/r2_notes.md.)  A producer thread copies its VALID rows with
+// cp.async into a private ring
 // of RS row slots (layout [block][slot][lane] x 16 B: conflict free for the copies and for the
 // 128-bit reads back), runs up to kTsDepth stages ahead, and only then moves a landed stage
 // smem -> registers -> tensor memory.  Two groups of 4 warps alternate stages; missing rows take
@@ -1755,16 +1112,6 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
   }
 }
 
-template <typename T, int NB, int BK>
-static int launch_ta(const CUtensorMap &mB, const TaParams &p, size_t smem_bytes, unsigned grid,
-                     cudaStream_t stream) {
-  auto kern = k_conv_ta<T, NB, BK>;
-  MEB_BIG_SMEM(kern);
-  kern<<<grid, kTaThreads, smem_bytes, stream>>>(mB, p);
-  count_tc_launch();
-  MEB_LAUNCH_OK();
-  return MEB200_OK;
-}
 template <typename T, int NB, int BK, int G>
 static int launch_ts(const CUtensorMap &mB, const TaParams &p, size_t smem_bytes, unsigned grid,
                      cudaStream_t stream) {
@@ -1776,19 +1123,18 @@ static int launch_ts(const CUtensorMap &mB, const TaParams &p, size_t smem_bytes
   return MEB200_OK;
 }
 
-// forward/dgrad kernel family: 2 = k_conv_ts (A in TMEM, rows staged in shared-memory rings,
-// default), 1 = k_conv_ta (A in TMEM, rows staged in registers), 0 = k_conv_rs (A in shared memory)
-static int ta_mode() {
+// MEB200_TC_KERNEL=rs forces the round-1 kernel (A in shared memory) for A/B measurements.
+static bool ts_enabled() {
   static int v = -1;
   if (v < 0) {
-    const char *e = getenv("MEB200_TC_KERNEL");     // "ts" (default) | "ta" | "rs"
-    v = (e && e[0] == 'r') ? 0 : ((e && e[0] == 't' && e[1] == 'a') ? 1 : 2);
+    const char *e = getenv("MEB200_TC_KERNEL");
+    v = (e && e[0] == 'r') ? 0 : 1;
     if (encode_tiled_fn() == nullptr) v = 0;
   }
-  return v;
+  return v == 1;
 }
 
-// One launch of the A-in-TMEM kernels over output columns [n0, n0 + c_cols) (c_cols <= 256).
+// One launch of k_conv_ts over output columns [n0, n0 + c_cols) (c_cols <= 256).
 // Wp = PERMUTED packed weights [K, c_cols_full, c_reduce] (reduction axis in ta_perm order).
 static int launch_ta_slice(const void *A, int dtype, uint32_t n_a, uint32_t c_reduce,
                            const void *Wp_full, uint32_t c_cols_full, uint32_t n0, uint32_t K,
@@ -1803,13 +1149,8 @@ static int launch_ta_slice(const void *A, int dtype, uint32_t n_a, uint32_t c_re
     e = getenv("MEB200_TA_ACC");
     force_acc = e ? atoi(e) : 0;
   }
-  bool staged = ta_mode() == 2;
-  tc::TaCfg cfg = tc::ta_config(c_reduce, c_cols, n_rows, staged, force_R, force_acc);
-  if (cfg.nb == 0 && (force_R || force_acc)) cfg = tc::ta_config(c_reduce, c_cols, n_rows, staged);
-  if (cfg.nb == 0 && staged) {
-    staged = false;
-    cfg = tc::ta_config(c_reduce, c_cols, n_rows, false);
-  }
+  tc::TaCfg cfg = tc::ta_config(c_reduce, c_cols, n_rows, force_R, force_acc);
+  if (cfg.nb == 0 && (force_R || force_acc)) cfg = tc::ta_config(c_reduce, c_cols, n_rows);
   if (cfg.nb == 0) return MEB200_ERR_UNSUPPORTED;
   TaParams p{};
   p.A = A; p.nbr = nbr; p.out = out;
@@ -1826,23 +1167,14 @@ static int launch_ta_slice(const void *A, int dtype, uint32_t n_a, uint32_t c_re
   if (rc != MEB200_OK) return rc;
   const unsigned grid = p.n_super < (uint32_t)num_sms() ? p.n_super : (unsigned)num_sms();
 #define MEB_TA(TT)                                                                        \
-  if (staged) {                                                                           \
-    switch (cfg.nb * 10 + cfg.g) {                                                        \
-      case 11: return launch_ts<TT, 1, 32, 1>(mB, p, cfg.smem_bytes, grid, stream);       \
-      case 21: return launch_ts<TT, 2, 64, 1>(mB, p, cfg.smem_bytes, grid, stream);       \
-      case 31: return launch_ts<TT, 3, 32, 1>(mB, p, cfg.smem_bytes, grid, stream);       \
-      case 41: return launch_ts<TT, 4, 64, 1>(mB, p, cfg.smem_bytes, grid, stream);       \
-      case 42: return launch_ts<TT, 4, 64, 2>(mB, p, cfg.smem_bytes, grid, stream);       \
-      case 44: return launch_ts<TT, 4, 32, 4>(mB, p, cfg.smem_bytes, grid, stream);       \
-      default: break;                                                                     \
-    }                                                                                     \
-  } else {                                                                                \
-    switch (cfg.nb) {                                                                     \
-      case 1: return launch_ta<TT, 1, 32>(mB, p, cfg.smem_bytes, grid, stream);           \
-      case 2: return launch_ta<TT, 2, 64>(mB, p, cfg.smem_bytes, grid, stream);           \
-      case 3: return launch_ta<TT, 3, 32>(mB, p, cfg.smem_bytes, grid, stream);           \
-      default: break;                                                                     \
-    }                                                                                     \
+  switch (cfg.nb * 10 + cfg.g) {                                                          \
+    case 11: return launch_ts<TT, 1, 32, 1>(mB, p, cfg.smem_bytes, grid, stream);         \
+    case 21: return launch_ts<TT, 2, 64, 1>(mB, p, cfg.smem_bytes, grid, stream);         \
+    case 31: return launch_ts<TT, 3, 32, 1>(mB, p, cfg.smem_bytes, grid, stream);         \
+    case 41: return launch_ts<TT, 4, 64, 1>(mB, p, cfg.smem_bytes, grid, stream);         \
+    case 42: return launch_ts<TT, 4, 64, 2>(mB, p, cfg.smem_bytes, grid, stream);         \
+    case 44: return launch_ts<TT, 4, 32, 4>(mB, p, cfg.smem_bytes, grid, stream);         \
+    default: break;                                                                       \
   }
   if (dtype == MEB200_BF16) { MEB_TA(__nv_bfloat16) } else { MEB_TA(__half) }
 #undef MEB_TA
@@ -1858,7 +1190,7 @@ bool conv_tc_supported(int dtype, uint32_t c_reduce, uint32_t c_cols) {
 int conv_forward_tc(const void *A, int dtype, uint32_t n_a, uint32_t c_reduce, const void *W,
                     uint32_t K, uint32_t c_cols, bool dgrad, const int32_t *nbr, uint32_t n_rows,
                     void *out, int out_dtype, void *workspace, cudaStream_t stream,
-                    const int32_t *row_ids, const void *Wperm) {
+                    const void *Wperm) {
   if (n_rows == 0) return MEB200_OK;
   MEB_CHECK_ARG(conv_tc_supported(dtype, c_reduce, c_cols), "shape not supported by tc path");
   const uint8_t *Wb = reinterpret_cast<const uint8_t *>(W);
@@ -1881,7 +1213,7 @@ int conv_forward_tc(const void *A, int dtype, uint32_t n_a, uint32_t c_reduce, c
                          (reinterpret_cast<uintptr_t>(Wperm) & 15) == 0;
   for (uint32_t n0 = 0; n0 < c_cols; n0 += 256) {
     uint32_t nc = c_cols - n0 < 256 ? c_cols - n0 : 256;
-    if (Wperm != nullptr && row_ids == nullptr && aligned16 && c_reduce % 32 == 0 && ta_mode() != 0) {
+    if (Wperm != nullptr && aligned16 && c_reduce % 32 == 0 && ts_enabled()) {
       // operand A in tensor memory: needs the weights packed in ta_perm order
       int rc = launch_ta_slice(A, dtype, n_a, c_reduce, Wperm, c_cols, n0, K, nc, nbr, n_rows,
                                reinterpret_cast<uint8_t *>(out) + (size_t)n0 * out_esz, c_cols,
@@ -1891,7 +1223,7 @@ int conv_forward_tc(const void *A, int dtype, uint32_t n_a, uint32_t c_reduce, c
     }
     int rc = launch_tc_slice(A, dtype, n_a, c_reduce, Wb, c_cols, n0, K, nc, nbr, n_rows,
                              reinterpret_cast<uint8_t *>(out) + (size_t)n0 * out_esz, c_cols,
-                             out_dtype, stream, row_ids);
+                             out_dtype, stream);
     if (rc != MEB200_OK) return rc;
   }
   return MEB200_OK;
@@ -1923,11 +1255,8 @@ struct WgParams {
   uint32_t lag;
 };
 
-// PF = how many (chunk, offset) work items ahead of use the neighbour indices are fetched.
-// PF == 0 is the round-1 kernel (one item ahead: every stage then waits out most of one index
-// load latency, profiles/r1_ncu_k_wgrad_tc_block8_96x96.txt); PF > 0 keeps a register ring of
-// PF index sets so the index latency is covered by PF stages of copy issue.
-template <typename T, int PF>
+// The round-1 dense kernel: the fallback when the caller has no compacted pair lists.
+template <typename T>
 __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(const WgParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>(
@@ -2026,54 +1355,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(const WgParams p) {
         cp_async_mbar_arrive(fullA(sa));
         if (++sa == p.nA) { sa = 0; pha ^= 1u; }
     };
-    if constexpr (PF == 0) {
-      int32_t idx_cur[kWgRows / 16], idx_nxt[kWgRows / 16];
-      if (n_chunks > 0) load_idx(0, 0, idx_cur);
-      for (uint32_t c = 0; c < n_chunks; ++c) {
-        for (uint32_t kk = 0; kk < G; ++kk) {
-          {
-            uint32_t nc = c, nkk = kk + 1;
-            if (nkk == G) { nkk = 0; nc = c + 1; }
-            if (nc < n_chunks) load_idx(nc, nkk, idx_nxt);
-          }
-          issue_stage(c, kk, idx_cur);
-#pragma unroll
-          for (int it = 0; it < kWgRows / 16; ++it) idx_cur[it] = idx_nxt[it];
+    int32_t idx_cur[kWgRows / 16], idx_nxt[kWgRows / 16];
+    if (n_chunks > 0) load_idx(0, 0, idx_cur);
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+      for (uint32_t kk = 0; kk < G; ++kk) {
+        {
+          uint32_t nc = c, nkk = kk + 1;
+          if (nkk == G) { nkk = 0; nc = c + 1; }
+          if (nc < n_chunks) load_idx(nc, nkk, idx_nxt);
         }
-      }
-    } else {
-      // register ring of PF index sets, addressed through static_switch: slot d is refilled with
-      // work item w + PF right after item w's copies were issued from it.
-      int32_t ring[PF][kWgRows / 16];
-      const uint32_t n_work = n_chunks * G;
-      uint32_t pc = 0, pkk = 0, c = 0, kk = 0;
-#pragma unroll
-      for (int d = 0; d < PF; ++d) {
-#pragma unroll
-        for (int it = 0; it < kWgRows / 16; ++it) ring[d][it] = -1;
-        if (pc < n_chunks) load_idx(pc, pkk, ring[d]);
-        if (++pkk == G) { pkk = 0; ++pc; }
-      }
-      uint32_t d = 0;
-      for (uint32_t w = 0; w < n_work; ++w) {
-        int32_t idx_cur[kWgRows / 16];
-        static_switch<0, PF>(d, [&](auto D) {       // waits for ring[d]'s loads only
-#pragma unroll
-          for (int it = 0; it < kWgRows / 16; ++it) idx_cur[it] = ring[decltype(D)::value][it];
-        });
         issue_stage(c, kk, idx_cur);
-        if (pc < n_chunks)
-          static_switch<0, PF>(d, [&](auto D) { load_idx(pc, pkk, ring[decltype(D)::value]); });
-        if (++pkk == G) { pkk = 0; ++pc; }
-        if (++kk == G) { kk = 0; ++c; }
-        if (++d == (uint32_t)PF) d = 0;
+#pragma unroll
+        for (int it = 0; it < kWgRows / 16; ++it) idx_cur[it] = idx_nxt[it];
       }
     }
     cp_async_wait<0>();
   } else if (warp < kProducerWarps + kEpilogueWarps) {
     const uint32_t q = warp & 3u;
-    if constexpr (PF == 0) mbar_wait(tfull, 0);
-    else mbar_wait_sleep(tfull, 0, 500);   // parked for the whole main loop
+    mbar_wait_park(tfull, 0);              // parked for the whole main loop
     tc_fence_after();
     for (uint32_t kk = 0; kk < G; ++kk) {
       for (uint32_t t = 0; t < mt; ++t) {
@@ -2126,242 +1425,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(const WgParams p) {
   tc_fence_before();
   __syncthreads();
   if (warp == kProducerWarps + kEpilogueWarps) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
-  }
-}
-
-// =====================================================================================
-// wgrad with the forward kernel's producer scheme (default when its stages fit): dense 128-row
-// windows, one producer warp per stage (ballot compaction, valid rows through registers,
-// zero-filled MN-major stage), the window's dOut rows fetched by TMA once per group of G offsets.
-// =====================================================================================
-struct Wg2Params {
-  const void *in;
-  const int32_t *nbr;
-  float *dW;
-  uint32_t c_in, c_out, K, n_out;
-  uint32_t G, n_kgroups, mt_cta, n_mtgroups, rows_per_split, n_splits;
-  uint32_t blkA, blkB, nA, nB, a_stage_bytes, b_stage_bytes;
-};
-constexpr int kWg2Warps = (int)tc::kWg2ProducerWarps;
-constexpr int kWg2Threads = (kWg2Warps + kEpilogueWarps + 2) * 32;
-constexpr uint32_t kWg2Blk = tc::kWg2BlkBytes;
-
-template <typename T>
-__global__ void __launch_bounds__(kWg2Threads, 1)
-k_wgrad_rs2(const __grid_constant__ CUtensorMap mapG, const Wg2Params p) {
-  constexpr int NP = kWg2Warps;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t sA = smem_u32(smem);
-  const uint32_t sB = sA + p.nA * p.a_stage_bytes;
-  uint8_t *tail = smem + p.nA * p.a_stage_bytes + p.nB * p.b_stage_bytes;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(tail);
-  const uint32_t bar0 = smem_u32(bars);
-  const uint32_t tfull = bar_tfull(bar0, 0);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * kMaxStages + 4);
-  uint2 *scratch_all = reinterpret_cast<uint2 *>(tail + tc::kBarBytes);
-  volatile uint32_t *consumed = reinterpret_cast<volatile uint32_t *>(
-      tail + tc::kBarBytes + NP * tc::kWg2Rows * 8);
-
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t wi = blockIdx.x;
-  const uint32_t kg = wi % p.n_kgroups; wi /= p.n_kgroups;
-  const uint32_t mtg = wi % p.n_mtgroups; wi /= p.n_mtgroups;
-  const uint32_t split = wi;
-  const uint32_t k0 = kg * p.G;
-  const uint32_t G = min(p.G, p.K - k0);
-  const uint32_t r_begin = split * p.rows_per_split;
-  const uint32_t r_end = min(r_begin + p.rows_per_split, p.n_out);
-  const uint32_t n_win = (r_end - r_begin + tc::kWg2Rows - 1) / tc::kWg2Rows;
-  const uint32_t total = G * n_win;
-  const uint32_t ch0 = mtg * p.mt_cta * 128;
-  const uint32_t mt = min(p.mt_cta, (p.c_in - ch0 + 127) / 128);
-
-  if (threadIdx.x == 0) {
-    for (uint32_t i = 0; i < p.nA; ++i) { mbar_init(bar_fullA(bar0, i), 1); mbar_init(bar_emptyA(bar0, i), 1); }
-    for (uint32_t i = 0; i < p.nB; ++i) { mbar_init(bar_fullB(bar0, i), 1); mbar_init(bar_emptyB(bar0, i), 1); }
-    mbar_init(tfull, 1);
-    mbar_fence_init();
-    consumed[0] = 0;
-    consumed[1] = 0;
-  }
-  if (warp == NP + kEpilogueWarps) {
-    tmem_alloc(smem_u32(tmem_slot), kTmemCols);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp < NP) {
-    // ------------------------------- producers -----------------------------------------
-    const uint32_t sub_row = lane >> 3, j8 = lane & 7;
-    const T *in = reinterpret_cast<const T *>(p.in);
-    uint2 *scratch = scratch_all + warp * tc::kWg2Rows;
-    const uint32_t scratch_s = smem_u32(scratch);
-    const uint32_t lane_lt = (1u << lane) - 1u;
-    int32_t idx_cur[4], idx_nxt[4];
-    auto load_idx = [&](uint32_t g, int32_t (&dst)[4]) {
-      const uint32_t w = g / G, kk = g - w * G;
-      const int32_t *nbr_k = p.nbr + (size_t)(k0 + kk) * p.n_out;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t o = r_begin + w * tc::kWg2Rows + i * 32 + lane;
-        dst[i] = (o < r_end) ? __ldg(nbr_k + o) : -1;
-      }
-    };
-    if (warp == 0 && lane == 0) tma_prefetch_desc(&mapG);
-    uint32_t g = warp;
-    if (g < total) load_idx(g, idx_cur);
-    for (; g < total; g += NP) {
-      if (g + NP < total) load_idx(g + NP, idx_nxt);
-      const uint32_t w = g / G, kk = g - w * G;
-      const uint32_t sa = g % p.nA;
-      uint32_t V = 0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const bool ok = idx_cur[i] >= 0;
-        const uint32_t m = __ballot_sync(0xffffffffu, ok);
-        if (ok) scratch[V + __popc(m & lane_lt)] = make_uint2((uint32_t)idx_cur[i], (uint32_t)(i * 32 + lane));
-        V += __popc(m);
-      }
-      __syncwarp();
-      const uint32_t dstA = sA + sa * p.a_stage_bytes;
-      const uint32_t its = 16u / p.blkA;          // row groups (4 rows each) per batch of 16 loads
-      bool slot_ready = false;
-      uint32_t e0 = 0;
-      do {
-        uint4 v[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const uint32_t it = (uint32_t)q / p.blkA, blk = (uint32_t)q - it * p.blkA;
-          const uint32_t e = e0 + it * 4 + sub_row;
-          const uint32_t chn = ch0 + blk * 64 + j8 * 8;
-          if (it < its && e < V && chn < p.c_in) {
-            uint32_t row;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(scratch_s + e * 8));
-            v[q] = ldg128(in + (size_t)row * p.c_in + chn);
-          } else {
-            v[q] = make_uint4(0, 0, 0, 0);
-          }
-        }
-        if (!slot_ready) {
-          wait_consumed(consumed, g, p.nA, lane);
-          if (kk == 0 && lane == 0) {   // this stage opens window w: fetch its dOut rows
-            const uint32_t sb = w % p.nB;
-            while ((int32_t)(w - lds_volatile(consumed + 1)) >= (int32_t)p.nB) __nanosleep(20);
-            __threadfence_block();
-            mbar_arrive_expect_tx(bar_fullB(bar0, sb), p.blkB * kWg2Blk);
-            const uint32_t dstB = sB + sb * p.b_stage_bytes;
-            for (uint32_t b = 0; b < p.blkB; ++b)
-              tma_load_2d(dstB + b * kWg2Blk, &mapG, (int32_t)(b * 64),
-                          (int32_t)(r_begin + w * tc::kWg2Rows), bar_fullB(bar0, sb));
-          }
-          for (uint32_t off = lane * 16; off < p.a_stage_bytes; off += 512)
-            sts128(dstA + off, make_uint4(0, 0, 0, 0));
-          __syncwarp();
-          slot_ready = true;
-        }
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const uint32_t it = (uint32_t)q / p.blkA, blk = (uint32_t)q - it * p.blkA;
-          const uint32_t e = e0 + it * 4 + sub_row;
-          if (it < its && e < V) {
-            uint32_t trow;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(trow) : "r"(scratch_s + e * 8 + 4));
-            sts128(dstA + blk * kWg2Blk + trow * 128 + ((j8 ^ (trow & 7u)) << 4), v[q]);
-          }
-        }
-        e0 += its * 4;
-      } while (e0 < V);
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_fullA(bar0, sa));
-#pragma unroll
-      for (int i = 0; i < 4; ++i) idx_cur[i] = idx_nxt[i];
-    }
-  } else if (warp < NP + kEpilogueWarps) {
-    // ------------------------------- epilogue ------------------------------------------
-    const uint32_t q = warp & 3u;
-    mbar_wait(tfull, 0);
-    tc_fence_after();
-    for (uint32_t kk = 0; kk < G; ++kk) {
-      for (uint32_t t = 0; t < mt; ++t) {
-        const uint32_t ci = ch0 + t * 128 + q * 32 + lane;
-        const uint32_t col0 = (kk * p.mt_cta + t) * p.c_out;
-        float *dst_row = p.dW + ((size_t)(k0 + kk) * p.c_in + ci) * p.c_out;
-        for (uint32_t c = 0; c < p.c_out; c += 16) {
-          uint32_t v[16];
-          tmem_ld16(tmem_base + ((q * 32u) << 16) + col0 + c, v);
-          tmem_ld_wait();
-          if (ci < p.c_in && total > 0) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float f = __uint_as_float(v[i]);
-              if (f != 0.f) atomicAdd(dst_row + c + i, f);
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == NP + kEpilogueWarps) {
-    // ------------------------------- MMA (whole warp, one lane issues) -----------------
-    const uint32_t idesc = umma_idesc_f16(Fmt<T>::v, kTileM, p.c_out, 1, 1);
-    constexpr uint32_t kHi = umma_desc_hi(1024, 2);
-    const uint32_t a_lo0 = umma_desc_lo(sA, kWg2Blk), b_lo0 = umma_desc_lo(sB, kWg2Blk);
-    const uint32_t a_inc = p.a_stage_bytes >> 4, b_inc = p.b_stage_bytes >> 4;
-    const uint32_t t1_off = (2 * kWg2Blk) >> 4;
-    uint32_t a_lo = a_lo0, b_lo = b_lo0, sa = 0, pha = 0, sb = 0, phb = 0;
-    for (uint32_t w = 0; w < n_win; ++w) {
-      mbar_wait(bar_fullB(bar0, sb), phb);
-      for (uint32_t kk = 0; kk < G; ++kk) {
-        mbar_wait(bar_fullA(bar0, sa), pha);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t d = tmem_base + kk * p.mt_cta * p.c_out;
-#pragma unroll
-          for (int j = 0; j < (int)tc::kWg2Rows / 16; ++j) {
-            const uint32_t acc_flag = (w | (uint32_t)j) != 0u;
-            const uint64_t db = pack_desc(b_lo + j * 128, kHi);
-            umma_f16(d, pack_desc(a_lo + j * 128, kHi), db, idesc, acc_flag);
-            if (mt > 1) umma_f16(d + p.c_out, pack_desc(a_lo + t1_off + j * 128, kHi), db, idesc, acc_flag);
-          }
-          umma_commit(bar_emptyA(bar0, sa));
-          if (kk == G - 1) umma_commit(bar_emptyB(bar0, sb));
-        }
-        __syncwarp();
-        a_lo += a_inc;
-        if (++sa == p.nA) { sa = 0; pha ^= 1u; a_lo = a_lo0; }
-      }
-      b_lo += b_inc;
-      if (++sb == p.nB) { sb = 0; phb ^= 1u; b_lo = b_lo0; }
-    }
-    if (elect_one()) umma_commit(tfull);
-    __syncwarp();
-  } else if (lane == 0) {
-    // ------------------------------- release warp --------------------------------------
-    uint32_t sa = 0, pha = 0, sb = 0, phb = 0, nA_done = 0;
-    for (uint32_t w = 0; w < n_win; ++w) {
-      for (uint32_t kk = 0; kk < G; ++kk) {
-        mbar_wait(bar_emptyA(bar0, sa), pha);
-        __threadfence_block();
-        sts_volatile(consumed, ++nA_done);
-        if (++sa == p.nA) { sa = 0; pha ^= 1u; }
-      }
-      mbar_wait(bar_emptyB(bar0, sb), phb);
-      __threadfence_block();
-      sts_volatile(consumed + 1, w + 1);
-      if (++sb == p.nB) { sb = 0; phb ^= 1u; }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == NP + kEpilogueWarps) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -2754,44 +1817,6 @@ int conv_wgrad_tc(const void *in, const void *grad_out, int dtype, uint32_t c_in
                   cudaStream_t stream) {
   MEB_CUDA(cudaMemsetAsync(grad_weight, 0, (size_t)K * c_in * c_out * sizeof(float), stream));
   if (n_out == 0 || K == 0) return MEB200_OK;
-  // MEB200_TC_WGRAD=win selects k_wgrad_rs2 (the forward kernel's register-staged producers over
-  // 128-row windows).  Measured slower than the cp.async kernel below (2.7 vs 1.8 ms on the
-  // largest layer, profiles/r1_notes.md), so it is opt-in; a pair-compacting variant was slower
-  // still and has been removed.
-  static int dense = -1;   // 1 = k_wgrad_tc (default), 2 = k_wgrad_rs2
-  if (dense < 0) {
-    const char *e = getenv("MEB200_TC_WGRAD");
-    dense = (e && e[0] == 'w') ? 2 : 1;
-    if (dense == 2 && encode_tiled_fn() == nullptr) dense = 1;
-  }
-  // (needs full 64-channel TMA boxes of dOut: c_out >= 64)
-  if (dense == 2 && c_out >= 64 && (reinterpret_cast<uintptr_t>(grad_out) & 15) == 0) {
-    const tc::Wg2Cfg cfg = tc::wgrad2_config(c_in, c_out, K, n_out, (uint32_t)num_sms());
-    if (cfg.mt_cta != 0) {
-      CUtensorMap mG;
-      memset(&mG, 0, sizeof(mG));
-      int rc = make_map_2d(&mG, dtype, grad_out, n_out, c_out, 64, tc::kWg2Rows);
-      if (rc != MEB200_OK) return rc;
-      Wg2Params q{};
-      q.in = in; q.nbr = out_nbr; q.dW = grad_weight;
-      q.c_in = c_in; q.c_out = c_out; q.K = K; q.n_out = n_out;
-      q.G = cfg.G; q.n_kgroups = cfg.n_kgroups; q.mt_cta = cfg.mt_cta; q.n_mtgroups = cfg.n_mtgroups;
-      q.rows_per_split = cfg.rows_per_split; q.n_splits = cfg.n_splits;
-      q.blkA = cfg.blkA; q.blkB = cfg.blkB; q.nA = cfg.pipe.nA; q.nB = cfg.pipe.nB;
-      q.a_stage_bytes = cfg.a_stage_bytes; q.b_stage_bytes = cfg.b_stage_bytes;
-      unsigned grid = cfg.n_kgroups * cfg.n_mtgroups * cfg.n_splits;
-      if (dtype == MEB200_BF16) {
-        MEB_BIG_SMEM(k_wgrad_rs2<__nv_bfloat16>);
-        k_wgrad_rs2<__nv_bfloat16><<<grid, kWg2Threads, cfg.smem_bytes, stream>>>(mG, q);
-      } else {
-        MEB_BIG_SMEM(k_wgrad_rs2<__half>);
-        k_wgrad_rs2<__half><<<grid, kWg2Threads, cfg.smem_bytes, stream>>>(mG, q);
-      }
-      count_tc_launch();
-      MEB_LAUNCH_OK();
-      return MEB200_OK;
-    }
-  }
   WgParams p{};
   p.in = in; p.gout = grad_out; p.nbr = out_nbr; p.dW = grad_weight;
   p.c_in = c_in; p.c_out = c_out; p.K = K; p.n_out = n_out;
@@ -2807,23 +1832,13 @@ int conv_wgrad_tc(const void *in, const void *grad_out, int dtype, uint32_t c_in
   p.rows_per_split = cfg.rows_per_split; p.n_splits = cfg.n_splits;
   size_t smem_bytes = cfg.smem_bytes;
   unsigned grid = cfg.n_kgroups * cfg.n_mtgroups * cfg.n_splits;
-  // MEB200_WG_PREFETCH = 4 | 8 | 16: experimental deeper index prefetch (see k_wgrad_tc); default 0
-  int pf = 0;
-  if (const char *e = getenv("MEB200_WG_PREFETCH")) pf = atoi(e);
-  auto launch = [&](void (*kern)(const WgParams)) -> int {
-    MEB_BIG_SMEM(kern);
-    kern<<<grid, kThreads, smem_bytes, stream>>>(p);
-    return MEB200_OK;
-  };
-  int rc;
+  int rc = MEB200_OK;
   if (dtype == MEB200_BF16) {
-    rc = pf >= 16 ? launch(k_wgrad_tc<__nv_bfloat16, 16>)
-         : pf >= 8 ? launch(k_wgrad_tc<__nv_bfloat16, 8>)
-         : pf >= 4 ? launch(k_wgrad_tc<__nv_bfloat16, 4>) : launch(k_wgrad_tc<__nv_bfloat16, 0>);
+    MEB_BIG_SMEM(k_wgrad_tc<__nv_bfloat16>);
+    k_wgrad_tc<__nv_bfloat16><<<grid, kThreads, smem_bytes, stream>>>(p);
   } else {
-    rc = pf >= 16 ? launch(k_wgrad_tc<__half, 16>)
-         : pf >= 8 ? launch(k_wgrad_tc<__half, 8>)
-         : pf >= 4 ? launch(k_wgrad_tc<__half, 4>) : launch(k_wgrad_tc<__half, 0>);
+    MEB_BIG_SMEM(k_wgrad_tc<__half>);
+    k_wgrad_tc<__half><<<grid, kThreads, smem_bytes, stream>>>(p);
   }
   if (rc != MEB200_OK) return rc;
   count_tc_launch();

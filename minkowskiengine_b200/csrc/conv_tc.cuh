@@ -14,8 +14,7 @@ bool conv_wgrad_tc_supported(int dtype, uint32_t c_in, uint32_t c_out);
 int conv_forward_tc(const void *A, int dtype, uint32_t n_a, uint32_t c_reduce, const void *W,
                     uint32_t K, uint32_t c_cols, bool dgrad, const int32_t *nbr, uint32_t n_rows,
                     void *out, int out_dtype, void *workspace, cudaStream_t stream,
-                    const int32_t *row_ids = nullptr,    // ordered tiles: see TcParams::row_ids
-                    const void *Wperm = nullptr);        // operand B in ta_perm order (k_conv_ta)
+                    const void *Wperm = nullptr);        // operand B in ta_perm order (k_conv_ts)
 
 // fp32 W[K,c_in,c_out] -> w_cast [K,c_in,c_out], w_t [K,c_out,c_in] and their k_conv_ta twins
 // w_cp / w_tp (reduction axis permuted within 32-channel blocks; may be NULL) in bf16/fp16.

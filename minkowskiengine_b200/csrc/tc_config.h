@@ -97,8 +97,8 @@ struct TaCfg {
   uint32_t n_macro;       // stages per (tile, offset) = c_red / (32 nb)
   uint32_t R, acc_sets, n_super, nA, nB;
   uint32_t a_col0, b_sub_bytes, b_stage_bytes, smem_bytes;
-  uint32_t rs;            // staged kernel: row slots per producer thread (0 = register kernel)
-  uint32_t g;             // offsets per stage (staged kernel, narrow layers); 1 otherwise
+  uint32_t rs;            // row slots per producer thread's ring
+  uint32_t g;             // offsets per stage (narrow layers); 1 otherwise
 };
 constexpr uint32_t kTsGroupsCfg = 3;            // k_conv_ts: producer groups of 4 warps
 constexpr uint32_t kTsProducerWarpsCfg = 4 * kTsGroupsCfg;
@@ -107,11 +107,9 @@ constexpr uint32_t kTsProducerWarpsCfg = 4 * kTsGroupsCfg;
 inline uint32_t ts_tail_bytes(uint32_t g) {
   return 64 + kTsProducerWarpsCfg * (8 * 8 + 8 * 32 * 4 + 4 * g * 32 * 4);
 }
-// staged = true : k_conv_ts (gathered rows wait in per-thread shared-memory rings, up to 4
-//                 blocks = 128 channels per stage)
-// staged = false: k_conv_ta (rows wait in registers, up to 3 blocks per stage)
-inline TaCfg ta_config(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, bool staged = true,
-                       int force_R = 0, int force_acc = 0) {
+inline TaCfg ta_config(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, int force_R = 0,
+                       int force_acc = 0) {
+  constexpr bool staged = true;
   TaCfg c{};
   if (c_red % 32 != 0 || c_cols % 16 != 0 || c_cols < 16 || c_cols > 256) return c;
   uint32_t nb = c_red % 96 == 0 ? 3 : (c_red % 64 == 0 ? 2 : 1);
@@ -146,15 +144,6 @@ inline TaCfg ta_config(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, bool st
   if (c.nA < 2) return c;
   c.b_sub_bytes = ((c_cols * (uint32_t)c.bk * 2 + 1023) / 1024) * 1024;
   c.b_stage_bytes = (32 * nb / (uint32_t)c.bk) * c.b_sub_bytes;
-  if (!staged) {
-    const uint32_t budget = kSmemBudget - kBarBytes - 1024 - 64;
-    c.nB = budget / c.b_stage_bytes;
-    if (c.nB > 8) c.nB = 8;
-    if (c.nB < 2) return c;
-    c.smem_bytes = 1024 + c.nB * c.b_stage_bytes + kBarBytes + 64;
-    c.nb = nb;
-    return c;
-  }
   // staged: weights ring of 3 (2 if tight) stages, the rest of shared memory goes to the rings
   const uint32_t tail_bytes = ts_tail_bytes(c.g);
   const uint32_t budget = kSmemBudget - kBarBytes - 1024 - tail_bytes;
@@ -170,7 +159,7 @@ inline TaCfg ta_config(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, bool st
       return c;
     }
   }
-  return c;   // nb = 0: the caller falls back to the register kernel
+  return c;   // nb = 0: the caller falls back to k_conv_rs
 }
 
 // ---- wgrad: dW[K, c_in, c_out] reduced over n_out rows --------------------------------------
@@ -265,53 +254,6 @@ inline WpCfg wgrad_pairs_config(uint32_t c_in, uint32_t c_out, uint32_t K, uint3
   c.smem_bytes = 1024 + c.n_stage * c.stage_bytes + tail;
   c.mt_cta = mt;
   return c;
-}
-
-// ---- wgrad, register-staged producers over dense 128-row windows (opt-in variant) ----
-// Stage A = the gathered (zero padded) input rows of one (window, offset): blkA blocks of
-// [128 rows][128 B]; stage B = the window's dOut rows, blkB blocks, shared by the G offsets of
-// the CTA's group.  Same producer scheme as the forward kernel (k_conv_rs).
-constexpr uint32_t kWg2ProducerWarps = 10;
-constexpr uint32_t kWg2Rows = 128;
-constexpr uint32_t kWg2BlkBytes = kWg2Rows * 128;
-constexpr uint32_t kWg2ScratchBytes = kWg2ProducerWarps * kWg2Rows * 8 + 64;
-struct Wg2Cfg {
-  uint32_t mt_cta;   // 0 = use the 64-row dense kernel instead
-  uint32_t n_mtgroups, G, n_kgroups, blkA, blkB, a_stage_bytes, b_stage_bytes;
-  PipeCfg pipe;
-  uint32_t rows_per_split, n_splits, smem_bytes;
-};
-inline Wg2Cfg wgrad2_config(uint32_t c_in, uint32_t c_out, uint32_t K, uint32_t n_out, uint32_t n_sms) {
-  Wg2Cfg best{};
-  const uint32_t mt_total = cdiv_u(c_in, 128);
-  uint32_t mt_max = mt_total < kTmemCols / c_out ? mt_total : kTmemCols / c_out;
-  if (mt_max > 2) mt_max = 2;
-  const uint32_t budget = kSmemBudget - kBarBytes - 1024 - kWg2ScratchBytes;
-  for (uint32_t mt = mt_max; mt >= 1; --mt) {
-    Wg2Cfg c{};
-    c.mt_cta = mt;
-    c.n_mtgroups = cdiv_u(mt_total, mt);
-    c.G = kTmemCols / (mt * c_out);
-    if (c.G > K) c.G = K;
-    if (c.G > 8) c.G = 8;
-    c.n_kgroups = cdiv_u(K, c.G);
-    c.blkA = mt * 2;
-    c.blkB = cdiv_u(c_out, 64);
-    c.a_stage_bytes = c.blkA * kWg2BlkBytes;
-    c.b_stage_bytes = c.blkB * kWg2BlkBytes;
-    c.pipe = pick_pipeline(c.a_stage_bytes, c.b_stage_bytes, c.G, budget);
-    if (c.pipe.nA >= 3 && c.pipe.nB >= 2) { best = c; break; }
-  }
-  if (best.mt_cta == 0) return best;
-  uint32_t base = best.n_kgroups * best.n_mtgroups;
-  uint32_t want = cdiv_u(2ull * n_sms, base);
-  uint32_t max_splits = cdiv_u(n_out, 4 * kWg2Rows);
-  uint32_t splits = want < 1 ? 1 : (want > max_splits ? max_splits : want);
-  best.rows_per_split = cdiv_u(cdiv_u(n_out, splits), kWg2Rows) * kWg2Rows;
-  best.n_splits = cdiv_u(n_out, best.rows_per_split);
-  best.smem_bytes = 1024 + best.pipe.nA * best.a_stage_bytes + best.pipe.nB * best.b_stage_bytes +
-                    kBarBytes + kWg2ScratchBytes;
-  return best;
 }
 
 }  // namespace tc

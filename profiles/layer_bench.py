@@ -56,9 +56,6 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--json", default=None)
     ap.add_argument("--only", default=None)
-    ap.add_argument("--ordered", action="store_true",
-                    help="also time the forward pass over Morton-ordered tiles "
-                         "(meb200_conv_forward_ordered; 96-channel bf16 layers in round 1)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[a.dtype]
@@ -89,22 +86,10 @@ def main():
         t_f = time_ms(lambda: backend._conv_forward(feats, w if dt != torch.float32 else wl, km), a.iters)   # fp32 master -> packed operands
         t_d = time_ms(lambda: backend._conv_backward(feats, gout, w, km, True, False), a.iters)
         t_w = time_ms(lambda: backend._conv_backward(feats, gout, w, km, False, True), a.iters)
-        t_o = None
-        if a.ordered and not tr and st == 1:
-            from minkowskiengine_b200 import _lib, tile_order
-            try:
-                tile_nbr, row_ids = tile_order.ordered_tables(km.out_nbr, mgr.get_coordinates(out_key), lvl)
-                y_o = tile_order.conv_forward_ordered(feats, wl, tile_nbr, row_ids)
-                y = backend._conv_forward(feats, wl, km)
-                err = (y_o.float() - y.float()).abs().max().item() / max(y.float().abs().max().item(), 1e-30)
-                t_o = time_ms(lambda: tile_order.conv_forward_ordered(feats, wl, tile_nbr, row_ids), a.iters)
-                print(f"{name:24s} ordered fwd {t_o:7.3f} ms (max rel diff vs default {err:.1e})", flush=True)
-            except _lib.BackendError as exc:
-                print(f"{name:24s} ordered fwd: {exc}", flush=True)
         flops = 2.0 * P * cin * cout
         byt_f = n_in * cin * esz + n_out * cout * esz + K * cin * cout * esz + P * 8
         r = {"layer": name, "n_in": n_in, "n_out": n_out, "K": K, "pairs": P,
-             "ms_fwd": t_f, "ms_dgrad": t_d, "ms_wgrad": t_w, "ms_fwd_ordered": t_o,
+             "ms_fwd": t_f, "ms_dgrad": t_d, "ms_wgrad": t_w,
              "tflops_fwd": flops / t_f / 1e9, "tflops_dgrad": flops / t_d / 1e9,
              "tflops_wgrad": flops / t_w / 1e9, "gbs_fwd": byt_f / t_f / 1e6}
         rows.append(r)

@@ -45,14 +45,34 @@ int main() {
     if (!ok) { printf("WG BAD ci=%u co=%u K=%u rows=%u\n", ci, co, K, rows); ++bad; }
     printf("wg %u %u %u %u : mt=%u G=%u lag=%u nA=%u nB=%u splits=%u smem=%u\n", ci, co, K, rows, w.mt_cta, w.G, w.pipe.lag, w.pipe.nA, w.pipe.nB, w.n_splits, w.smem_bytes);
   }
+  /* k_conv_ts: A slots in TMEM (a multiple of the 3 producer groups), accumulators, rings */
+  for (unsigned cr : chans) for (unsigned cc : ncs) for (unsigned rows : {1u, 129u, 5000u, 800000u}) {
+    TaCfg t = ta_config(cr, cc, rows);
+    if (cr % 32 != 0) { if (t.nb != 0) { printf("TA BAD (should be unsupported) cr=%u\n", cr); ++bad; } continue; }
+    if (t.nb == 0) { printf("ta %u %u %u : falls back to k_conv_rs\n", cr, cc, rows); continue; }
+    const unsigned a_cols = 16 * t.nb;
+    bool ok = t.nb * 32 * t.n_macro * (t.g > 1 ? 1 : 1) == (t.g > 1 ? t.nb * 32 : cr) &&
+              (t.g == 1 || cr * t.g == t.nb * 32) &&
+              t.acc_sets * t.R * cc + t.nA * a_cols <= kTmemCols && t.a_col0 == t.acc_sets * t.R * cc &&
+              t.nA >= 3 && t.nA % 3 == 0 && t.nB >= 2 && t.rs >= 4 && t.rs <= 8 &&
+              t.smem_bytes <= 227 * 1024 && t.b_stage_bytes == (32 * t.nb / t.bk) * t.b_sub_bytes &&
+              t.b_sub_bytes >= cc * t.bk * 2 && t.b_sub_bytes % 1024 == 0 &&
+              1024 + t.nB * t.b_stage_bytes + (t.rs + 1) * 12 * t.nb * 512 + kBarBytes + ts_tail_bytes(t.g) == t.smem_bytes;
+    if (!ok) { printf("TA BAD cr=%u cc=%u rows=%u nb=%u g=%u\n", cr, cc, rows, t.nb, t.g); ++bad; }
+    printf("ta %u %u %u : nb=%u g=%u bk=%d R=%u acc=%u nA=%u nB=%u rs=%u smem=%u\n", cr, cc, rows, t.nb, t.g, t.bk, t.R, t.acc_sets, t.nA, t.nB, t.rs, t.smem_bytes);
+  }
+  /* k_wgrad_pairs: ring a multiple of the 3 producer groups, accumulators within TMEM */
   for (unsigned ci : cins) for (unsigned co : ncs) for (unsigned K : {1u, 8u, 27u, 125u}) for (unsigned rows : {1u, 300u, 800000u}) {
-    Wg2Cfg w = wgrad2_config(ci, co, K, rows, 148);
-    if (w.mt_cta == 0) continue;   // falls back to the 64-row kernel
-    bool ok = w.pipe.nA >= 3 && w.pipe.nB >= 2 && w.smem_bytes <= 227 * 1024 &&
-              w.G * w.mt_cta * co <= kTmemCols && w.n_splits * w.rows_per_split >= rows &&
-              w.a_stage_bytes == w.blkA * kWg2BlkBytes && w.blkB * 64 >= co;
-    if (!ok) { printf("WG2 BAD ci=%u co=%u K=%u rows=%u\n", ci, co, K, rows); ++bad; }
-    printf("wg2 %u %u %u %u : mt=%u G=%u nA=%u nB=%u splits=%u smem=%u\n", ci, co, K, rows, w.mt_cta, w.G, w.pipe.nA, w.pipe.nB, w.n_splits, w.smem_bytes);
+    const unsigned chunks = (rows + 65535) / 65536;
+    WpCfg w = wgrad_pairs_config(ci, co, K, chunks, rows, 148);
+    if (K * chunks > 2047) { if (w.mt_cta != 0) { printf("WP BAD (too many segments)\n"); ++bad; } continue; }
+    bool ok = w.mt_cta >= 1 && w.mt_cta <= 2 && w.acc_sets * w.mt_cta * co <= kTmemCols &&
+              w.n_stage >= 3 && w.n_stage % 3 == 0 && w.smem_bytes <= 227 * 1024 &&
+              w.n_mtgroups * w.mt_cta * 128 >= ci && w.n_splits >= 1 &&
+              w.n_splits * w.n_mtgroups <= 2 * 148 + w.n_mtgroups &&
+              w.stage_bytes == w.a_bytes + w.blkB * kBlkBytes && w.blkB * 64 >= co;
+    if (!ok) { printf("WP BAD ci=%u co=%u K=%u rows=%u\n", ci, co, K, rows); ++bad; }
+    printf("wp %u %u %u %u : mt=%u groups=%u splits=%u stages=%u acc=%u smem=%u\n", ci, co, K, rows, w.mt_cta, w.n_mtgroups, w.n_splits, w.n_stage, w.acc_sets, w.smem_bytes);
   }
   printf("bad=%d\n", bad);
   return bad != 0;
