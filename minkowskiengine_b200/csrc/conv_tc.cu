@@ -1454,7 +1454,6 @@ constexpr int kWpGroups = 3;                // producer groups: group g owns sta
 constexpr int kWpProducerWarps = 4 * kWpGroups;   // 4 warps per group, 16 pairs of a stage each
 constexpr int kWpRowsPerWarp = 16;
 constexpr int kWpThreads = (kWpProducerWarps + kEpilogueWarps + 1) * 32;
-constexpr int kWpMaxSlots = 8;              // 16-byte copies per thread per operand per 8 rows
 constexpr int kWpPf = 4;                    // pair indices are copied this many of the group's stages ahead
 constexpr uint32_t kWpMaxSeg = 2047;        // (row chunks) x K segments a launch can walk
 
@@ -1547,7 +1546,10 @@ struct WpWalk {
   }
 };
 
-template <typename T>
+// S = copy slots per thread per operand per 8 rows = ceil(channels / 32), a template parameter so
+// that the slot tables live in registers and no dead slot is ever stepped over (with 8 generic
+// slots the loop was 672 instructions per stage and warp, its tables spilled to local memory).
+template <typename T, int S>
 __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>(
@@ -1599,9 +1601,9 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
     const uint32_t nA = (8 * cprA + 31) / 32, nB = (8 * cprB + 31) / 32;   // slots per thread per 8 rows
     // fixed copy slots: slot s of this lane copies chunk `c % cpr` of row `c / cpr` (of 8 rows),
     // c = lane + 32 s; destination offsets never change (the second half adds 8 rows = 1024 B)
-    uint32_t a_dst[kWpMaxSlots], b_dst[kWpMaxSlots], a_meta[kWpMaxSlots], b_meta[kWpMaxSlots];
+    uint32_t a_dst[S], b_dst[S], a_meta[S], b_meta[S];
 #pragma unroll
-    for (int sl = 0; sl < kWpMaxSlots; ++sl) {
+    for (int sl = 0; sl < S; ++sl) {
       const uint32_t c = lane + 32u * sl;
       {
         const uint32_t rl = c / cprA, chunk = c - rl * cprA;
@@ -1654,7 +1656,7 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
 #pragma unroll
-        for (int sl = 0; sl < kWpMaxSlots; ++sl) {
+        for (int sl = 0; sl < S; ++sl) {
           if ((uint32_t)sl < nA) {
             const uint32_t m = a_meta[sl];
             if (m != 0xffffffffu) {
@@ -1666,7 +1668,7 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
           }
         }
 #pragma unroll
-        for (int sl = 0; sl < kWpMaxSlots; ++sl) {
+        for (int sl = 0; sl < S; ++sl) {
           if ((uint32_t)sl < nB) {
             const uint32_t m = b_meta[sl];
             if (m != 0xffffffffu) {
@@ -1795,13 +1797,26 @@ int conv_wgrad_pairs(const void *in, const void *grad_out, int dtype, uint32_t c
   p.blkB = cfg.blkB; p.n_stage = cfg.n_stage; p.a_bytes = cfg.a_bytes;
   p.stage_bytes = cfg.stage_bytes; p.acc_sets = cfg.acc_sets;
   const unsigned grid = cfg.n_mtgroups * cfg.n_splits;
-  if (dtype == MEB200_BF16) {
-    MEB_BIG_SMEM(k_wgrad_pairs<__nv_bfloat16>);
-    k_wgrad_pairs<__nv_bfloat16><<<grid, kWpThreads, cfg.smem_bytes, stream>>>(p);
-  } else {
-    MEB_BIG_SMEM(k_wgrad_pairs<__half>);
-    k_wgrad_pairs<__half><<<grid, kWpThreads, cfg.smem_bytes, stream>>>(p);
-  }
+  // slots per thread: the wider of the two operands' rows (A: this CTA's channel slice)
+  const uint32_t ch_a = c_in < cfg.mt_cta * 128 ? c_in : cfg.mt_cta * 128;
+  const uint32_t slots = ((ch_a > c_out ? ch_a : c_out) + 31) / 32;
+#define MEB_WP(SV)                                                                              \
+  do {                                                                                          \
+    if (dtype == MEB200_BF16) {                                                                 \
+      MEB_BIG_SMEM((k_wgrad_pairs<__nv_bfloat16, SV>));                                         \
+      k_wgrad_pairs<__nv_bfloat16, SV><<<grid, kWpThreads, cfg.smem_bytes, stream>>>(p);        \
+    } else {                                                                                    \
+      MEB_BIG_SMEM((k_wgrad_pairs<__half, SV>));                                                \
+      k_wgrad_pairs<__half, SV><<<grid, kWpThreads, cfg.smem_bytes, stream>>>(p);               \
+    }                                                                                           \
+  } while (0)
+  if (slots <= 1) MEB_WP(1);
+  else if (slots == 2) MEB_WP(2);
+  else if (slots == 3) MEB_WP(3);
+  else if (slots == 4) MEB_WP(4);
+  else if (slots <= 6) MEB_WP(6);
+  else MEB_WP(8);
+#undef MEB_WP
   count_tc_launch();
   MEB_LAUNCH_OK();
   return MEB200_OK;
