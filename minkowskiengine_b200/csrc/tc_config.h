@@ -107,19 +107,13 @@ constexpr uint32_t kTsProducerWarpsCfg = 4 * kTsGroupsCfg;
 inline uint32_t ts_tail_bytes(uint32_t g) {
   return 64 + kTsProducerWarpsCfg * (8 * 8 + 8 * 32 * 4 + 4 * g * 32 * 4);
 }
-inline TaCfg ta_config(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, int force_R = 0,
-                       int force_acc = 0) {
-  constexpr bool staged = true;
+// One candidate: nb 32-channel blocks per stage, g offsets per stage.
+inline TaCfg ta_try(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, uint32_t nb, uint32_t g,
+                    int force_R, int force_acc) {
   TaCfg c{};
-  if (c_red % 32 != 0 || c_cols % 16 != 0 || c_cols < 16 || c_cols > 256) return c;
-  uint32_t nb = c_red % 96 == 0 ? 3 : (c_red % 64 == 0 ? 2 : 1);
-  c.g = 1;
-  if (staged && c_red % 128 == 0) nb = 4;
-  // narrow layers: a stage spans g offsets so that it still carries 128 channels of reduction
-  if (staged && c_red == 32) { nb = 4; c.g = 4; }
-  if (staged && c_red == 64) { nb = 4; c.g = 2; }
-  c.bk = (c_red % 64 == 0 && nb != 3) ? 64 : 32;
-  c.n_macro = c.g > 1 ? 1 : c_red / (32 * nb);
+  c.g = g;
+  c.bk = (nb % 2 == 0 && (g == 1 || (32 * nb / g) % 64 == 0)) ? 64 : 32;
+  c.n_macro = g > 1 ? 1 : c_red / (32 * nb);
   const uint32_t a_cols = 16 * nb;
   const uint32_t tiles = cdiv_u(n_rows, kTileM);
   uint32_t bestR = 0, bestAcc = 0;
@@ -128,10 +122,8 @@ inline TaCfg ta_config(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, int for
     for (uint32_t R = 4; R >= 1; R >>= 1) {
       if (force_R && (int)R != force_R) continue;
       if (R > 1 && R > tiles) continue;
-      // the staged kernel wants one A slot per producer group at least
-      if (acc * R * c_cols + (staged ? kTsGroupsCfg : 2u) * a_cols <= kTmemCols) {
-        bestR = R; bestAcc = acc; break;
-      }
+      // one A slot per producer group at least
+      if (acc * R * c_cols + kTsGroupsCfg * a_cols <= kTmemCols) { bestR = R; bestAcc = acc; break; }
     }
   }
   if (bestR == 0) return c;
@@ -139,27 +131,41 @@ inline TaCfg ta_config(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, int for
   c.n_super = cdiv_u(tiles, c.R);
   c.a_col0 = c.acc_sets * c.R * c_cols;
   c.nA = (kTmemCols - c.a_col0) / a_cols;
-  if (c.nA > 8) c.nA = 8;
-  if (staged) c.nA = c.nA / kTsGroupsCfg * kTsGroupsCfg;   // a slot always belongs to the same producer group
-  if (c.nA < 2) return c;
+  if (c.nA > 9) c.nA = 9;
+  c.nA = c.nA / kTsGroupsCfg * kTsGroupsCfg;   // a slot always belongs to the same producer group
+  if (c.nA < kTsGroupsCfg) return c;
   c.b_sub_bytes = ((c_cols * (uint32_t)c.bk * 2 + 1023) / 1024) * 1024;
   c.b_stage_bytes = (32 * nb / (uint32_t)c.bk) * c.b_sub_bytes;
-  // staged: weights ring of 3 (2 if tight) stages, the rest of shared memory goes to the rings
-  const uint32_t tail_bytes = ts_tail_bytes(c.g);
+  // weights ring of 3 (2 if tight) stages, the rest of shared memory goes to the row rings
+  const uint32_t tail_bytes = ts_tail_bytes(g);
   const uint32_t budget = kSmemBudget - kBarBytes - 1024 - tail_bytes;
   const uint32_t per_slot = kTsProducerWarpsCfg * nb * 512;     // bytes one more row slot costs
   for (uint32_t nB = 3; nB >= 2; --nB) {
-    if (nB * c.b_stage_bytes + per_slot >= budget) continue;
+    if (nB * c.b_stage_bytes + 5 * per_slot > budget) continue;
     uint32_t rs = (budget - nB * c.b_stage_bytes) / per_slot - 1;   // one slot is the zero slot
     if (rs > 8) rs = 8;
-    if (rs >= 4) {
-      c.nB = nB; c.rs = rs;
-      c.smem_bytes = 1024 + nB * c.b_stage_bytes + (rs + 1) * per_slot + kBarBytes + tail_bytes;
-      c.nb = nb;
-      return c;
-    }
+    c.nB = nB; c.rs = rs;
+    c.smem_bytes = 1024 + nB * c.b_stage_bytes + (rs + 1) * per_slot + kBarBytes + tail_bytes;
+    c.nb = nb;
+    return c;
   }
-  return c;   // nb = 0: the caller falls back to k_conv_rs
+  return c;
+}
+inline TaCfg ta_config(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, int force_R = 0,
+                       int force_acc = 0) {
+  TaCfg none{};
+  if (c_red % 32 != 0 || c_cols % 16 != 0 || c_cols < 16 || c_cols > 256) return none;
+  // narrow layers: a stage spans g offsets so that it still carries 128 channels of reduction
+  if (c_red == 32) return ta_try(c_red, c_cols, n_rows, 4, 4, force_R, force_acc);
+  if (c_red == 64) return ta_try(c_red, c_cols, n_rows, 4, 2, force_R, force_acc);
+  // otherwise the fattest stage (most 32-channel blocks) whose weights + row rings fit
+  const uint32_t cands[4] = {4, 3, 2, 1};
+  for (uint32_t nb : cands) {
+    if (c_red % (32 * nb) != 0) continue;
+    TaCfg c = ta_try(c_red, c_cols, n_rows, nb, 1, force_R, force_acc);
+    if (c.nb != 0) return c;
+  }
+  return none;   // the caller falls back to k_conv_rs
 }
 
 // ---- wgrad: dW[K, c_in, c_out] reduced over n_out rows --------------------------------------
