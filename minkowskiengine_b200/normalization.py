@@ -38,9 +38,18 @@ class _PeerExchange:
 
     @classmethod
     def get(cls, group, device):
+        """The exchange buffer of (group, device), or None when symmetric memory cannot be set
+        up here (every rank then takes the NCCL exchange: the failure is a property of the
+        installation, not of the rank)."""
         key = (id(group), device.index)
         if key not in cls._cache:
-            cls._cache[key] = cls(group, device)
+            try:
+                cls._cache[key] = cls(group, device)
+            except Exception as exc:                  # noqa: BLE001
+                import warnings
+                warnings.warn(f"MEB200_SYNCBN_PEER: symmetric memory unavailable ({exc!r}); "
+                              "using the NCCL exchange")
+                cls._cache[key] = None
         return cls._cache[key]
 
     def __init__(self, group, device):
