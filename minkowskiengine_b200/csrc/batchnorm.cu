@@ -18,6 +18,13 @@ constexpr int kBnThreads = 256;
 
 template <typename T> struct Vec8;   // eight consecutive channels = one 16-byte (bf16/fp16) load
 template <> struct Vec8<__nv_bfloat16> {
+  using Raw = uint4;     // the 16 bytes as loaded; unpacked to fp32 only when used
+  static __device__ __forceinline__ Raw load_raw(const __nv_bfloat16 *p) { return *reinterpret_cast<const uint4 *>(p); }
+  static __device__ __forceinline__ void unpack(const Raw &v, float (&f)[8]) {
+    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  }
   static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float (&f)[8]) {
     uint4 v = *reinterpret_cast<const uint4 *>(p);
     const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
@@ -33,6 +40,13 @@ template <> struct Vec8<__nv_bfloat16> {
   }
 };
 template <> struct Vec8<__half> {
+  using Raw = uint4;
+  static __device__ __forceinline__ Raw load_raw(const __half *p) { return *reinterpret_cast<const uint4 *>(p); }
+  static __device__ __forceinline__ void unpack(const Raw &v, float (&f)[8]) {
+    const __half2 *h = reinterpret_cast<const __half2 *>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  }
   static __device__ __forceinline__ void load(const __half *p, float (&f)[8]) {
     uint4 v = *reinterpret_cast<const uint4 *>(p);
     const __half2 *h = reinterpret_cast<const __half2 *>(&v);
@@ -48,6 +62,13 @@ template <> struct Vec8<__half> {
   }
 };
 template <> struct Vec8<float> {
+  struct Raw { float4 a, b; };
+  static __device__ __forceinline__ Raw load_raw(const float *p) {
+    Raw r; r.a = reinterpret_cast<const float4 *>(p)[0]; r.b = reinterpret_cast<const float4 *>(p)[1]; return r;
+  }
+  static __device__ __forceinline__ void unpack(const Raw &v, float (&f)[8]) {
+    f[0] = v.a.x; f[1] = v.a.y; f[2] = v.a.z; f[3] = v.a.w; f[4] = v.b.x; f[5] = v.b.y; f[6] = v.b.z; f[7] = v.b.w;
+  }
   static __device__ __forceinline__ void load(const float *p, float (&f)[8]) {
     float4 a = reinterpret_cast<const float4 *>(p)[0], b = reinterpret_cast<const float4 *>(p)[1];
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
@@ -92,23 +113,41 @@ k_bn_reduce(const T *__restrict__ a, const T *__restrict__ x, const T *__restric
 #pragma unroll
       for (int i = 0; i < 8; ++i) { m[i] = mean[cg * 8 + i]; is[i] = invstd[cg * 8 + i]; }
     }
-    for (uint32_t r = row_begin + r0; r < row_end; r += g.rows_per_pass) {
-      float va[8];
-      Vec8<T>::load(a + (size_t)r * C + cg * 8, va);
-      if (MODE == 0) {
+    // four rows per iteration: the loads of all four (up to 12 x 16 B) are issued before the
+    // first use — one row per iteration left the passes latency bound (1.2 TB/s on [800k, 96])
+    constexpr int U = 4;
+    const uint32_t step = g.rows_per_pass;
+    for (uint32_t r = row_begin + r0; r < row_end; r += U * step) {
+      typename Vec8<T>::Raw ra[U], rx[U], ry[U];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { s1[i] += va[i]; s2[i] = fmaf(va[i], va[i], s2[i]); }
-      } else {
-        float vx[8];
-        Vec8<T>::load(x + (size_t)r * C + cg * 8, vx);
-        if (ymask != nullptr) {      // ReLU folded into the layer: dy passes where y > 0
-          float vy[8];
-          Vec8<T>::load(ymask + (size_t)r * C + cg * 8, vy);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) va[i] = vy[i] > 0.f ? va[i] : 0.f;
+      for (int u = 0; u < U; ++u) {
+        const uint32_t ru = min(r + u * step, row_end - 1);     // clamped: tail rows are skipped below
+        ra[u] = Vec8<T>::load_raw(a + (size_t)ru * C + cg * 8);
+        if (MODE == 1) {
+          rx[u] = Vec8<T>::load_raw(x + (size_t)ru * C + cg * 8);
+          if (ymask != nullptr) ry[u] = Vec8<T>::load_raw(ymask + (size_t)ru * C + cg * 8);
         }
+      }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { s1[i] += va[i]; s2[i] = fmaf(va[i], (vx[i] - m[i]) * is[i], s2[i]); }
+      for (int u = 0; u < U; ++u) {
+        if (r + u * step >= row_end) break;
+        float va[8];
+        Vec8<T>::unpack(ra[u], va);
+        if (MODE == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { s1[i] += va[i]; s2[i] = fmaf(va[i], va[i], s2[i]); }
+        } else {
+          float vx[8];
+          Vec8<T>::unpack(rx[u], vx);
+          if (ymask != nullptr) {      // ReLU folded into the layer: dy passes where y > 0
+            float vy[8];
+            Vec8<T>::unpack(ry[u], vy);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) va[i] = vy[i] > 0.f ? va[i] : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { s1[i] += va[i]; s2[i] = fmaf(va[i], (vx[i] - m[i]) * is[i], s2[i]); }
+        }
       }
     }
 #pragma unroll
@@ -175,36 +214,46 @@ k_bn_apply(const T *__restrict__ a, const T *__restrict__ x, const T *__restrict
       k2[i] = (float)(gsums[C + c] / count);
     }
   }
-  for (uint32_t r = row_begin + r0; r < row_end; r += g.rows_per_pass) {
-    float va[8], vo[8];
-    Vec8<T>::load(a + (size_t)r * C + cg * 8, va);
-    if (MODE == 0) {
-      float vr[8];
+  constexpr int U = 4;      // rows per iteration, all loads first (see k_bn_reduce)
+  const uint32_t step = g.rows_per_pass;
+  for (uint32_t r = row_begin + r0; r < row_end; r += U * step) {
+    typename Vec8<T>::Raw ra[U], rb[U], rc[U];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) vr[i] = 0.f;
-      if (aux != nullptr) Vec8<T>::load(aux + (size_t)r * C + cg * 8, vr);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float y = fmaf(va[i], sc[i], sh[i]) + vr[i];
-        vo[i] = relu ? fmaxf(y, 0.f) : y;
-      }
-    } else {
-      float vx[8];
-      Vec8<T>::load(x + (size_t)r * C + cg * 8, vx);
-      if (aux != nullptr) {
-        float vy[8];
-        Vec8<T>::load(aux + (size_t)r * C + cg * 8, vy);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) va[i] = vy[i] > 0.f ? va[i] : 0.f;
-      }
-      if (out2 != nullptr) Vec8<T>::store(out2 + (size_t)r * C + cg * 8, va);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float xhat = (vx[i] - m[i]) * is[i];
-        vo[i] = (va[i] - k1[i] - xhat * k2[i]) * sc[i];
-      }
+    for (int u = 0; u < U; ++u) {
+      const uint32_t ru = min(r + u * step, row_end - 1);
+      ra[u] = Vec8<T>::load_raw(a + (size_t)ru * C + cg * 8);
+      if (MODE == 1) rb[u] = Vec8<T>::load_raw(x + (size_t)ru * C + cg * 8);
+      if (aux != nullptr) rc[u] = Vec8<T>::load_raw(aux + (size_t)ru * C + cg * 8);
     }
-    Vec8<T>::store(out + (size_t)r * C + cg * 8, vo);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t ru = r + u * step;
+      if (ru >= row_end) break;
+      float va[8], vo[8], vc[8];
+      Vec8<T>::unpack(ra[u], va);
+      if (aux != nullptr) Vec8<T>::unpack(rc[u], vc);
+      if (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float y = fmaf(va[i], sc[i], sh[i]) + (aux != nullptr ? vc[i] : 0.f);
+          vo[i] = relu ? fmaxf(y, 0.f) : y;
+        }
+      } else {
+        float vb[8];
+        Vec8<T>::unpack(rb[u], vb);
+        if (aux != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) va[i] = vc[i] > 0.f ? va[i] : 0.f;
+        }
+        if (out2 != nullptr) Vec8<T>::store(out2 + (size_t)ru * C + cg * 8, va);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float xhat = (vb[i] - m[i]) * is[i];
+          vo[i] = (va[i] - k1[i] - xhat * k2[i]) * sc[i];
+        }
+      }
+      Vec8<T>::store(out + (size_t)ru * C + cg * 8, vo);
+    }
   }
 }
 
@@ -213,7 +262,7 @@ static inline uint32_t bn_rows_per_cta(uint32_t n, uint32_t C, unsigned *grid) {
   // ~8 CTAs per SM, at least 4 passes each
   uint32_t want = 8u * (uint32_t)num_sms();
   uint32_t rows = cdiv(n, want);
-  uint32_t min_rows = 4 * rows_per_pass;
+  uint32_t min_rows = 8 * rows_per_pass;
   if (rows < min_rows) rows = min_rows;
   rows = cdiv(rows, rows_per_pass) * rows_per_pass;
   *grid = cdiv(n, rows);

@@ -4,7 +4,9 @@ set -u
 OUT=gpurun_out/r2_run11
 mkdir -p "$OUT"
 PT="python -m pytest -q --timeout 300 --timeout-method=thread"
-echo "== SyncBN numerics, NCCL exchange (1 and 2 ranks)" | tee "$OUT/summary.txt"
+echo "== batch-norm kernels (unrolled passes)" | tee "$OUT/summary.txt"
+timeout 300 $PT tests/test_gpu_batchnorm.py 2>&1 | tail -3 | tee -a "$OUT/summary.txt"
+echo "== SyncBN numerics, NCCL exchange (1 and 2 ranks)" | tee -a "$OUT/summary.txt"
 timeout 400 $PT tests/test_gpu_zz_syncbn.py 2>&1 | tail -6 | tee -a "$OUT/summary.txt"
 echo "== SyncBN numerics, peer-memory exchange" | tee -a "$OUT/summary.txt"
 MEB200_SYNCBN_PEER=1 timeout 400 $PT tests/test_gpu_zz_syncbn.py 2>&1 | tail -12 | tee -a "$OUT/summary.txt"
