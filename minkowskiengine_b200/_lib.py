@@ -112,7 +112,13 @@ def ptr(t):
 
 
 def current_stream():
+    """Raw handle of torch's current CUDA stream on the current device (the fast private
+    accessor when this torch has it: the public one builds a Stream object per call and this
+    runs once per native launch, ~1000 times per training step)."""
     import torch
+    raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    if raw is not None:
+        return raw(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
