@@ -163,8 +163,8 @@ class _BatchNormFunction(torch.autograd.Function):
                 _lib.ptr(invstd), _lib.ptr(gs), stream))
             grad_w = grad_b = None
             if ctx.has_affine:   # local sums; DDP averages parameter gradients across ranks
-                grad_b = gs[:C].to(ctx.param_dtype, copy=True)
-                grad_w = gs[C:].to(ctx.param_dtype, copy=True)
+                g32 = gs.to(ctx.param_dtype, copy=True)        # one conversion for both halves
+                grad_b, grad_w = g32[:C], g32[C:]
             if ctx.use_running:
                 gs = torch.zeros_like(gs)      # statistics are constants: dx = dy' * invstd * w
             elif peer is not None:
