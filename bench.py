@@ -392,6 +392,7 @@ def run_ours(args):
     is_net = cfg["kind"] == "net"
     loss_check = None
     flush_l2 = False
+    ablate = []
 
     torch.manual_seed(0)
     if is_net:
@@ -399,8 +400,12 @@ def run_ours(args):
         digest = weights_digest(net)
         net = net.to(dev)
         raw_net = net
-        if world > 1:
+        # MEB200_BENCH_ABLATE=nosyncbn,noddp,samedata: DIAGNOSIS ONLY (which part of the N>1 step
+        # costs what, profiles/r2_notes.md §6); recorded in config.ablate, never a bench value.
+        ablate = sorted(x for x in os.environ.get("MEB200_BENCH_ABLATE", "").split(",") if x)
+        if world > 1 and "nosyncbn" not in ablate:
             net = ME.MinkowskiSyncBatchNorm.convert_sync_batchnorm(net)
+        if world > 1 and "noddp" not in ablate:
             # SyncBN keeps the running statistics identical on every rank, so DDP's per-step
             # buffer broadcast is redundant; gradients live in the all-reduce buckets.
             # MEB200_DDP_PLAIN=1 restores the reference example's plain DDP
@@ -411,7 +416,8 @@ def run_ours(args):
             net = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], **ddp_kw)
         opt = torch.optim.SGD(net.parameters(), lr=1e-2)
         crit = torch.nn.CrossEntropyLoss()
-        coords_h, feats_h, labels_h = make_batch(args.clouds, args.voxels, seed0=rank * args.clouds)
+        seed0 = 0 if "samedata" in ablate else rank * args.clouds
+        coords_h, feats_h, labels_h = make_batch(args.clouds, args.voxels, seed0=seed0)
         host = [coords_h.pin_memory(), feats_h.pin_memory(), labels_h.pin_memory()]
         coords_d, labels_d = host[0].to(dev), host[2].to(dev)
         feats_d = host[1].to(dev).to(dtype)
@@ -641,7 +647,8 @@ def run_ours(args):
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": workload,
                        "global_batch_clouds": args.clouds * world, "voxels_per_step": total_vox,
-                       "parallelism": f"dp{world}" if is_net else f"replicas{world}", "l2": l2},
+                       "parallelism": f"dp{world}" if is_net else f"replicas{world}", "l2": l2,
+                       **({"ablate": ablate} if ablate else {})},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),

@@ -268,6 +268,15 @@ int meb200_bn_backward_apply_fused(const void *dy, const void *x, const void *y_
 int meb200_peer_allreduce_f64(const void *peer_bases_dev, uint64_t slot_offset_bytes, uint32_t n,
                               uint32_t seq, uint32_t rank, uint32_t world, double *out,
                               void *stream);
+/* The forward exchange with meb200_bn_finalize fused in.  The slot holds this rank's
+ * [sum x (C) | sum x^2 (C) | rows (1)] as meb200_bn_stats leaves the first 2C entries; the
+ * kernel stores `local_rows` as entry 2C, exchanges as above and writes mean / 1/std (and the
+ * momentum update of the running statistics, unbiased variance) from the totals, plus the
+ * total row count (the backward pass divides by it). */
+int meb200_peer_bn_finalize(const void *peer_bases_dev, uint64_t slot_offset_bytes, uint32_t C,
+                            uint32_t seq, uint32_t rank, uint32_t world, double local_rows,
+                            float eps, float momentum, float *running_mean, float *running_var,
+                            float *mean, float *invstd, double *total_rows, void *stream);
 
 #ifdef __cplusplus
 }

@@ -9,10 +9,11 @@ normalisation, unbiased for the running estimate, momentum update, per-channel a
 synchronised variant all-reduces (sum, sum of squares, count) forward and (sum dy, sum dy*xhat)
 backward over the process group, exactly the exchange torch.nn.SyncBatchNorm performs.
 `MEB200_TORCH_BN=1` routes everything through torch's own kernels (A/B comparisons).
-`MEB200_SYNCBN_PEER=1` (experimental, written at the end of round 1 and not yet run on GPUs)
-replaces the two NCCL all-reduces per layer by libmeb200's one-shot exchange over NVLink peer
-memory (`meb200_peer_allreduce_f64`, csrc/peer.cu): one single-CTA kernel on the compute stream,
-no NCCL launch and no cross-stream hand-off.
+The exchange runs over NVLink peer memory by default (`meb200_peer_bn_finalize` forward,
+`meb200_peer_allreduce_f64` backward, csrc/peer.cu): one single-CTA kernel on the compute stream
+per exchange, no NCCL launch and no cross-stream hand-off; the forward one also does the work of
+`meb200_bn_finalize`, so a synchronised forward launches exactly what a local one does.
+`MEB200_SYNCBN_PEER=0` (or symmetric memory being unavailable) selects NCCL all-reduces.
 """
 import contextlib
 import os
@@ -24,7 +25,7 @@ from . import _lib
 from .sparse_tensor import SparseTensor
 
 _USE_TORCH = os.environ.get("MEB200_TORCH_BN", "0") not in ("", "0")
-_USE_PEER = os.environ.get("MEB200_SYNCBN_PEER", "0") not in ("", "0")
+_USE_PEER = os.environ.get("MEB200_SYNCBN_PEER", "1") not in ("", "0")
 
 
 class _PeerExchange:
@@ -77,6 +78,14 @@ class _PeerExchange:
         _lib.check(lib.meb200_peer_allreduce_f64(self.bases_dev, off, n, self.seq, self.rank,
                                                  self.world, _lib.ptr(out), _lib.current_stream()))
 
+    def bn_finalize(self, off, C, rows, eps, momentum, running_mean, running_var, mean, invstd,
+                    total_rows):
+        lib = _lib.load()
+        _lib.check(lib.meb200_peer_bn_finalize(
+            self.bases_dev, off, C, self.seq, self.rank, self.world, float(rows), float(eps),
+            float(momentum), _lib.ptr(running_mean), _lib.ptr(running_var), _lib.ptr(mean),
+            _lib.ptr(invstd), _lib.ptr(total_rows), _lib.current_stream()))
+
 
 def _device_guard(dev):
     """Native launches go to the CURRENT device's stream: make the tensor's device current."""
@@ -110,21 +119,21 @@ class _BatchNormFunction(torch.autograd.Function):
                 else:
                     sums = torch.empty(2 * C + 1, dtype=torch.float64, device=dev)
                 _lib.check(lib.meb200_bn_stats(_lib.ptr(x), code, n, C, _lib.ptr(sums), stream))
-                if group is not None:
-                    sums[2 * C] = float(n)
-                    if peer is not None:
-                        total = torch.empty(2 * C + 1, dtype=torch.float64, device=dev)
-                        peer.allreduce(off, 2 * C + 1, total)
-                        sums = total
-                    else:
-                        torch.distributed.all_reduce(sums, group=group)
-                    d_count = sums[2 * C:]
                 mean = torch.empty(C, dtype=torch.float32, device=dev)
                 invstd = torch.empty(C, dtype=torch.float32, device=dev)
-                _lib.check(lib.meb200_bn_finalize(
-                    _lib.ptr(sums), float(max(n, 1)), _lib.ptr(d_count), C, float(eps),
-                    float(momentum), _lib.ptr(running_mean), _lib.ptr(running_var),
-                    _lib.ptr(mean), _lib.ptr(invstd), stream))
+                if peer is not None:      # exchange + finalize in one single-CTA kernel
+                    d_count = torch.empty(1, dtype=torch.float64, device=dev)
+                    peer.bn_finalize(off, C, n, eps, momentum, running_mean, running_var, mean,
+                                     invstd, d_count)
+                else:
+                    if group is not None:
+                        sums[2 * C] = float(n)
+                        torch.distributed.all_reduce(sums, group=group)
+                        d_count = sums[2 * C:]
+                    _lib.check(lib.meb200_bn_finalize(
+                        _lib.ptr(sums), float(max(n, 1)), _lib.ptr(d_count), C, float(eps),
+                        float(momentum), _lib.ptr(running_mean), _lib.ptr(running_var),
+                        _lib.ptr(mean), _lib.ptr(invstd), stream))
             if residual is not None:
                 residual = residual.contiguous()
             y = torch.empty_like(x)
