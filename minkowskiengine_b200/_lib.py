@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmeb200.so")
+# MEB200_LIB=libmeb200_g4.so picks an A/B build of the same sources (csrc/build.py)
+LIB_PATH = os.path.join(_HERE, "csrc", os.environ.get("MEB200_LIB", "libmeb200.so"))
 
 OK = 0
 F32, BF16, F16 = 0, 1, 2

@@ -9,6 +9,7 @@ work happens in libmeb200.so on torch's current CUDA stream; the only host<->dev
 synchronisation is the unique-row count read when a NEW coordinate map is created.
 """
 import ctypes
+import os
 import random
 import string
 import weakref
@@ -162,7 +163,8 @@ class _KernelMap:
 
     __slots__ = ("out_nbr", "in_nbr", "stride_pairs", "_n_pairs", "_pairs", "_pair_src")
     PAIR_STAGE = 64   # pairs per pipeline stage of the wgrad kernel (k_wgrad_pairs)
-    PAIR_CHUNK_ROWS = 65536   # table rows per chunk of the pair lists (multiple of 2048)
+    # table rows per chunk of the pair lists (multiple of 2048)
+    PAIR_CHUNK_ROWS = int(os.environ.get("MEB200_PAIR_CHUNK_ROWS", "65536"))
 
     def __init__(self, out_nbr, in_nbr, stride_pairs=None):
         self.out_nbr, self.in_nbr = out_nbr, in_nbr

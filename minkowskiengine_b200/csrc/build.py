@@ -13,8 +13,12 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "libmeb200.so")
-OBJ = os.path.join(HERE, "build")
+# A/B builds for kernel experiments: MEB200_BUILD_SUFFIX=_g4 MEB200_BUILD_DEFINES=-DMEB_TS_GROUPS=4
+# writes libmeb200_g4.so next to the default library (selected at run time with MEB200_LIB).
+SUFFIX = os.environ.get("MEB200_BUILD_SUFFIX", "")
+DEFINES = os.environ.get("MEB200_BUILD_DEFINES", "").split()
+SO = os.path.join(HERE, f"libmeb200{SUFFIX}.so")
+OBJ = os.path.join(HERE, f"build{SUFFIX}")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC",
@@ -40,7 +44,7 @@ def build(force=False, verbose=False):
     def cc(job):
         s, o, stale = job
         if stale:
-            cmd = [NVCC, *ARCH, *FLAGS, "-c", s, "-o", o]
+            cmd = [NVCC, *ARCH, *FLAGS, *DEFINES, "-c", s, "-o", o]
             if verbose:
                 print(" ".join(cmd), flush=True)
             r = subprocess.run(cmd, capture_output=True, text=True)

@@ -888,9 +888,9 @@ struct TaPos {
 // 128-bit reads back), runs up to kTsDepth stages ahead, and only then moves a landed stage
 // smem -> registers -> tensor memory.  Two groups of 4 warps alternate stages; missing rows take
 // no ring space, so the ring holds ~8 stages of useful bytes per group.
-constexpr int kTsGroups = 3;
+constexpr int kTsGroups = (int)tc::kTsGroupsCfg;
 constexpr int kTsProducerWarps = 4 * kTsGroups;
-constexpr int kTsThreads = (kTsProducerWarps + kEpilogueWarps + 3) * 32;
+constexpr int kTsThreads = (kTsProducerWarps + kEpilogueWarps + 2) * 32;   // + MMA warp, weights loader
 constexpr uint32_t kTsDepth = 8;             // stage descriptors / landing barriers per warp
 constexpr int kTsPf = 4;                     // neighbour indices are copied this many of the group's stages ahead
 
@@ -915,7 +915,6 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
   uint64_t *bars = reinterpret_cast<uint64_t *>(tail);
   const uint32_t bar0 = smem_u32(bars);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * kMaxStages + 4);
-  volatile uint32_t *consumed = reinterpret_cast<volatile uint32_t *>(tail + tc::kBarBytes);
   uint64_t *landed_all = reinterpret_cast<uint64_t *>(tail + tc::kBarBytes + 64);   // [NP][kTsDepth]
   uint32_t *desc_all = reinterpret_cast<uint32_t *>(landed_all + NP * kTsDepth);    // [NP][kTsDepth][32]
   int32_t *idx_all = reinterpret_cast<int32_t *>(desc_all + NP * kTsDepth * 32);     // [NP][kTsPf][G][32]
@@ -933,7 +932,6 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
     for (uint32_t i = 0; i < 2; ++i) { mbar_init(bar_tfull(bar0, i), 1); mbar_init(bar_tempty(bar0, i), kEpilogueWarps * 32); }
     for (uint32_t i = 0; i < NP * kTsDepth; ++i) mbar_init(smem_u32(landed_all + i), 32);
     mbar_fence_init();
-    consumed[0] = 0;
   }
   if (warp < NP) {
     // slot RS of every block of this warp's ring holds zeros for good: rows without a neighbour
@@ -1103,7 +1101,7 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
     ta_epilogue<T>(p, bar0, tmem_base, warp & 3u, lane);
   } else if (warp == NP + kEpilogueWarps) {
     ta_mma<T, NB, BK>(p, sB, bar0, tmem_base);
-  } else if (warp == NP + kEpilogueWarps + 2) {
+  } else if (warp == NP + kEpilogueWarps + 1) {
     if (lane == 0) ta_bload<NB, BK, G>(&mapB, p, sB, bar0);
   }
 

@@ -100,7 +100,10 @@ struct TaCfg {
   uint32_t rs;            // row slots per producer thread's ring
   uint32_t g;             // offsets per stage (narrow layers); 1 otherwise
 };
-constexpr uint32_t kTsGroupsCfg = 3;            // k_conv_ts: producer groups of 4 warps
+#ifndef MEB_TS_GROUPS
+#define MEB_TS_GROUPS 3
+#endif
+constexpr uint32_t kTsGroupsCfg = MEB_TS_GROUPS;   // k_conv_ts: producer groups of 4 warps
 constexpr uint32_t kTsProducerWarpsCfg = 4 * kTsGroupsCfg;
 // counters, landing barriers (8 per warp), descriptors (8 x 128 B per warp), index rings
 // (4 stages x g offsets x 128 B per warp)
@@ -131,7 +134,7 @@ inline TaCfg ta_try(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, uint32_t n
   c.n_super = cdiv_u(tiles, c.R);
   c.a_col0 = c.acc_sets * c.R * c_cols;
   c.nA = (kTmemCols - c.a_col0) / a_cols;
-  if (c.nA > 9) c.nA = 9;
+  if (c.nA > 3 * kTsGroupsCfg) c.nA = 3 * kTsGroupsCfg;
   c.nA = c.nA / kTsGroupsCfg * kTsGroupsCfg;   // a slot always belongs to the same producer group
   if (c.nA < kTsGroupsCfg) return c;
   c.b_sub_bytes = ((c_cols * (uint32_t)c.bk * 2 + 1023) / 1024) * 1024;
