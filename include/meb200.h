@@ -85,6 +85,22 @@ int meb200_insert_and_map(const int32_t *coords, const uint8_t *valid, uint32_t 
                           int32_t *unique_coords, int64_t *unique_index,
                           int64_t *inverse_map, void *scratch, uint32_t *h_num_unique,
                           void *stream);
+/* The same insert WITHOUT the blocking count read, for maps that can be enqueued before they
+ * are needed (the stride pyramid of a network: every level is a function of the input
+ * coordinates alone, reference call sites coordinate_map_manager.cpp:406-429).  `n` is an UPPER
+ * bound of the candidate count; `d_n` (device, may be NULL = all n) holds the actual count, so
+ * a level can be enqueued while its parent's size is still only known on the device.  The unique
+ * count is left in `d_num_unique` (DEVICE); `table` is dedup scratch here — build the real table
+ * over the first m unique rows with meb200_map_build_table once m is known on the host.
+ * Row numbering is identical to meb200_insert_and_map (rows past *d_n never win). */
+int meb200_insert_and_map_enqueue(const int32_t *coords, const uint8_t *valid,
+                                  const uint32_t *d_n, uint32_t n, uint32_t ncols,
+                                  uint32_t *table, uint32_t capacity, int32_t *unique_coords,
+                                  int64_t *unique_index, int64_t *inverse_map, void *scratch,
+                                  uint32_t *d_num_unique, void *stream);
+/* Row-index table over m DISTINCT coordinate rows (what meb200_insert_and_map leaves in `table`). */
+int meb200_map_build_table(const int32_t *unique_coords, uint32_t m, uint32_t ncols,
+                           uint32_t *table, uint32_t capacity, void *stream);
 
 /* Candidate generation for a strided map: out[i] = floor(c / ts_out) * ts_out per
  * spatial axis, batch kept (reference a3: detail::stride_coordinate

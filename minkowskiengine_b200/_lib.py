@@ -26,6 +26,9 @@ PROTOTYPES = {
     "meb200_tc_launch_count": (_u64, []),
     "meb200_hash_capacity": (_u32, [_u32]),
     "meb200_insert_scratch_bytes": (_u64, [_u32]),
+    "meb200_insert_and_map_enqueue": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp, _u32, _vp, _vp, _vp,
+                                             _vp, _vp, _vp]),
+    "meb200_map_build_table": (_i32, [_vp, _u32, _u32, _vp, _u32, _vp]),
     "meb200_insert_and_map": (_i32, [_vp, _vp, _u32, _u32, _vp, _u32, _vp, _vp, _vp, _vp,
                                      C.POINTER(_u32), _vp]),
     "meb200_stride_coords": (_i32, [_vp, _u32, _u32, C.POINTER(C.c_int32), _vp, _vp]),

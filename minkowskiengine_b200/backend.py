@@ -153,6 +153,20 @@ class _CoordinateMap:
         return cmap, uidx[:m], inv
 
 
+class _PendingLevel:
+    """One level of a stride pyramid whose kernels are enqueued but whose size has not been read
+    yet (see CoordinateMapManagerGPU_c10._prefetch_pyramid)."""
+
+    __slots__ = ("parent_key", "tensor_stride", "uniq", "inverse", "count_dev", "count_host",
+                 "event")
+
+
+# kernel strides requested along the stride chain below the first inserted map of the previous
+# coordinate manager, per coordinate width: the prediction for the next manager's pyramid
+_PYRAMID_HINT = {}
+_PREFETCH = os.environ.get("MEB200_MAP_PREFETCH", "1") not in ("", "0")
+
+
 class _KernelMap:
     """k-major neighbour tables of one (in map, out map, kernel) triple.
 
@@ -271,6 +285,9 @@ class CoordinateMapManagerGPU_c10:
         self._maps = {}         # (tuple tensor_stride, str id) -> _CoordinateMap
         self._kernel_maps = {}  # 8-tuple (types.hpp:183-192) -> _KernelMap
         self._parents = {}      # out key -> (in key, int64 row of every in row in out map)
+        self._pending = {}      # out key -> _PendingLevel (enqueued, size not yet read)
+        self._chain_tip = None  # last map of the stride chain below the first inserted map
+        self._chain = []        # kernel strides requested along that chain
         _lib.load()             # fail at construction if the native library is missing
 
     # -- keys ------------------------------------------------------------------------
@@ -324,7 +341,11 @@ class CoordinateMapManagerGPU_c10:
         if key in self._maps:
             key = self.get_random_string_id(ts, string_id)
         cmap, unique_index, inverse_map = _CoordinateMap.build(coordinates, ts)
+        first = not self._maps
         self._maps[key] = cmap
+        if first:
+            self._chain_tip = key
+            self._prefetch_pyramid(key, cmap)
         if cmap.size == coordinates.size(0):
             # no duplicates: the reference GPU path returns an empty inverse map here
             # (coordinate_map_manager.cu:94-112) and Python substitutes arange
@@ -340,6 +361,12 @@ class CoordinateMapManagerGPU_c10:
         out_key = (out_ts, string_id if string_id else in_key[1])
         if out_key in self._maps:
             return out_key, False
+        if in_key == self._chain_tip:       # remember the pyramid for the next manager
+            self._chain_tip = out_key
+            self._chain.append(tuple(int(s) for s in kernel_stride))
+            _PYRAMID_HINT[len(in_key[0]) + 1] = tuple(self._chain)
+        if self._take_pending(in_key, out_key):
+            return out_key, True
         in_map = self._maps[in_key]
         lib = _lib.load()
         cand = torch.empty_like(in_map.coords)
@@ -350,6 +377,74 @@ class CoordinateMapManagerGPU_c10:
         self._maps[out_key] = out_map
         self._parents[out_key] = (in_key, inverse)
         return out_key, True
+
+    # A strided map is a function of the input coordinates alone, but creating it where the
+    # network first asks for it costs a blocking read of its size with the whole forward pass
+    # queued in front (the host's lead over the GPU is lost at every down-sampling layer, and the
+    # coarse levels — 10-30 us kernels — then run launch bound).  So the pyramid the PREVIOUS
+    # manager was asked for (_PYRAMID_HINT) is enqueued right behind the input map, on upper-bound
+    # buffers with device-side row counts (meb200_insert_and_map_enqueue); its sizes reach the
+    # host long before the layers that need them.  A wrong prediction is only wasted work: a
+    # level that is never requested, or requested with another stride, is dropped.
+    def _prefetch_pyramid(self, key, cmap):
+        hint = _PYRAMID_HINT.get(cmap.ncols) if _PREFETCH else None
+        if not hint or cmap.size == 0:
+            return
+        lib = _lib.load()
+        dev = cmap.coords.device
+        n, ncols = cmap.size, cmap.ncols
+        stream = _lib.current_stream()
+        cap = int(lib.meb200_hash_capacity(n))
+        scratch_bytes = int(lib.meb200_insert_scratch_bytes(n))
+        parent_key, parent_coords, parent_count = key, cmap.coords, None
+        for ks in hint:
+            if len(ks) != len(parent_key[0]):
+                return
+            out_ts = tuple(t * s for t, s in zip(parent_key[0], ks))
+            out_key = (out_ts, parent_key[1])
+            if out_key in self._maps or out_key in self._pending:
+                return
+            lv = _PendingLevel()
+            lv.parent_key, lv.tensor_stride = parent_key, out_ts
+            cand = torch.empty((n, ncols), dtype=torch.int32, device=dev)
+            ts_arr = (ctypes.c_int32 * len(out_ts))(*out_ts)
+            # rows past the parent's (device-side) count are whatever the buffer holds: they are
+            # strided like the others and then ignored by the insert
+            _lib.check(lib.meb200_stride_coords(_lib.ptr(parent_coords), n, ncols, ts_arr,
+                                                _lib.ptr(cand), stream))
+            table = torch.empty(cap, dtype=torch.int32, device=dev)
+            lv.uniq = torch.empty((n, ncols), dtype=torch.int32, device=dev)
+            uidx = torch.empty(n, dtype=torch.int64, device=dev)
+            lv.inverse = torch.empty(n, dtype=torch.int64, device=dev)
+            scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
+            lv.count_dev = torch.empty(1, dtype=torch.int32, device=dev)
+            _lib.check(lib.meb200_insert_and_map_enqueue(
+                _lib.ptr(cand), None, _lib.ptr(parent_count), n, ncols, _lib.ptr(table), cap,
+                _lib.ptr(lv.uniq), _lib.ptr(uidx), _lib.ptr(lv.inverse), _lib.ptr(scratch),
+                _lib.ptr(lv.count_dev), stream))
+            lv.count_host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+            lv.count_host.copy_(lv.count_dev, non_blocking=True)
+            lv.event = torch.cuda.Event()
+            lv.event.record()
+            self._pending[out_key] = lv
+            parent_key, parent_coords, parent_count = out_key, lv.uniq, lv.count_dev
+
+    def _take_pending(self, in_key, out_key):
+        """Turns the enqueued level `out_key` into a map if it was built from `in_key`."""
+        lv = self._pending.pop(out_key, None)
+        if lv is None or lv.parent_key != in_key:
+            return False
+        lib = _lib.load()
+        lv.event.synchronize()          # normally long past: enqueued before the first layer
+        m = int(lv.count_host.item())
+        cap = int(lib.meb200_hash_capacity(m))
+        table = torch.empty(cap, dtype=torch.int32, device=lv.uniq.device)
+        coords = lv.uniq[:m]
+        _lib.check(lib.meb200_map_build_table(_lib.ptr(coords), m, coords.shape[1],
+                                              _lib.ptr(table), cap, _lib.current_stream()))
+        self._maps[out_key] = _CoordinateMap(coords, table, cap, lv.tensor_stride)
+        self._parents[out_key] = (in_key, lv.inverse[:self._maps[in_key].size])
+        return True
 
     def stride(self, key, stride, string_id=""):
         out_key, _ = self._stride(key, [int(s) for s in stride], string_id)

@@ -41,11 +41,14 @@ static InsertScratch carve(void *scratch, uint32_t n) {
 
 template <int NC>
 __global__ void __launch_bounds__(256)
-k_insert(const int32_t *__restrict__ coords, const uint8_t *__restrict__ valid, uint32_t n,
-         uint32_t *__restrict__ table, uint32_t mask, uint32_t *__restrict__ slot_of) {
+k_insert(const int32_t *__restrict__ coords, const uint8_t *__restrict__ valid,
+         const uint32_t *__restrict__ d_n, uint32_t n, uint32_t *__restrict__ table, uint32_t mask,
+         uint32_t *__restrict__ slot_of) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  if (valid != nullptr && valid[i] == 0) {
+  // d_n: the number of meaningful rows lives on the device (a map enqueued before its parent's
+  // size reached the host); rows past it take no part
+  if ((valid != nullptr && valid[i] == 0) || (d_n != nullptr && i >= *d_n)) {
     slot_of[i] = kEmpty;
     return;
   }
@@ -283,7 +286,7 @@ int meb200_insert_and_map(const int32_t *coords, const uint8_t *valid, uint32_t 
   MEB_CUDA(cudaMemsetAsync(s.ticket, 0, 8, stream));
   uint32_t mask = capacity - 1;
   MEB_DISPATCH_NCOLS(ncols, k_insert<NC><<<cdiv(n, 256), 256, 0, stream>>>(
-                                coords, valid, n, table, mask, s.slot_of));
+                                coords, valid, nullptr, n, table, mask, s.slot_of));
   MEB_LAUNCH_OK();
   k_count<<<nb, kScanThreads, 0, stream>>>(table, s.slot_of, n, s.block_sums, s.ticket, s.total);
   MEB_LAUNCH_OK();
@@ -304,6 +307,55 @@ int meb200_insert_and_map(const int32_t *coords, const uint8_t *valid, uint32_t 
       MEB_LAUNCH_OK();
     }
   }
+  return MEB200_OK;
+}
+
+int meb200_insert_and_map_enqueue(const int32_t *coords, const uint8_t *valid,
+                                  const uint32_t *d_n, uint32_t n, uint32_t ncols,
+                                  uint32_t *table, uint32_t capacity, int32_t *unique_coords,
+                                  int64_t *unique_index, int64_t *inverse_map, void *scratch,
+                                  uint32_t *d_num_unique, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MEB_CHECK_ARG(d_num_unique != nullptr && n > 0, "enqueue: count pointer / empty input");
+  MEB_CHECK_ARG(table != nullptr && capacity >= 2 && (capacity & (capacity - 1)) == 0,
+                "capacity must be a power of two (got %u)", capacity);
+  MEB_CHECK_ARG((uint64_t)capacity >= 2ull * n || capacity == 0x80000000u,
+                "table too small for %u rows", n);
+  MEB_CHECK_ARG(coords && unique_coords && unique_index && inverse_map && scratch, "null buffer");
+  MEB_CUDA(cudaMemsetAsync(table, 0xFF, (size_t)capacity * 4, stream));
+  InsertScratch s = carve(scratch, n);
+  uint32_t nb = scan_blocks(n);
+  MEB_CUDA(cudaMemsetAsync(s.ticket, 0, 8, stream));
+  uint32_t mask = capacity - 1;
+  MEB_DISPATCH_NCOLS(ncols, k_insert<NC><<<cdiv(n, 256), 256, 0, stream>>>(
+                                coords, valid, d_n, n, table, mask, s.slot_of));
+  MEB_LAUNCH_OK();
+  k_count<<<nb, kScanThreads, 0, stream>>>(table, s.slot_of, n, s.block_sums, s.ticket, s.total);
+  MEB_LAUNCH_OK();
+  MEB_DISPATCH_NCOLS(ncols, k_fill<NC><<<nb, kScanThreads, 0, stream>>>(
+                                coords, table, s.slot_of, n, s.block_sums, s.rank_of,
+                                unique_coords, unique_index));
+  MEB_LAUNCH_OK();
+  k_inverse<<<cdiv(n, 256), 256, 0, stream>>>(table, s.slot_of, s.rank_of, n, inverse_map);
+  MEB_LAUNCH_OK();
+  MEB_CUDA(cudaMemcpyAsync(d_num_unique, s.total, 4, cudaMemcpyDeviceToDevice, stream));
+  return MEB200_OK;
+}
+
+int meb200_map_build_table(const int32_t *unique_coords, uint32_t m, uint32_t ncols,
+                           uint32_t *table, uint32_t capacity, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MEB_CHECK_ARG(table != nullptr && capacity >= 2 && (capacity & (capacity - 1)) == 0,
+                "capacity must be a power of two (got %u)", capacity);
+  MEB_CHECK_ARG((uint64_t)capacity >= 2ull * m || capacity == 0x80000000u,
+                "table too small for %u rows", m);
+  MEB_CUDA(cudaMemsetAsync(table, 0xFF, (size_t)capacity * 4, stream));
+  if (m == 0) return MEB200_OK;
+  MEB_CHECK_ARG(unique_coords != nullptr, "null coordinates");
+  uint32_t mask = capacity - 1;
+  MEB_DISPATCH_NCOLS(ncols, k_insert_unique<NC><<<cdiv(m, 256), 256, 0, stream>>>(
+                                unique_coords, m, table, mask));
+  MEB_LAUNCH_OK();
   return MEB200_OK;
 }
 
