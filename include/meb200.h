@@ -270,6 +270,27 @@ int meb200_bn_backward_apply_fused(const void *dy, const void *x, const void *y_
                                    const double *d_count, void *dx, void *d_residual,
                                    void *stream);
 
+/* Launch-lean forms (two launches per pass, no memset): the reductions take a WORKSPACE of
+ * meb200_bn_workspace_bytes() bytes, zero-filled once by the caller and shared by every layer
+ * that runs on the same stream; the last CTA of a reduction consumes the totals (finalize /
+ * parameter gradients / copy-out) and leaves the workspace zero again.
+ *   meb200_bn_forward_train      = stats + finalize (one launch) + apply_fused; n > 0
+ *   meb200_bn_stats_to           = stats, totals [sum x | sum x^2] copied to sums_out[2C]
+ *                                  (the exchange slot of a synchronised layer)
+ *   meb200_bn_backward_reduce_to = backward reduce, totals [sum dy | sum dy*xhat] copied to
+ *                                  sums_out[2C] and, when non-NULL, to fp32 grad_bias / grad_weight */
+uint64_t meb200_bn_workspace_bytes(void);
+int meb200_bn_forward_train(const void *x, int dtype, uint32_t n, uint32_t C, const float *weight,
+                            const float *bias, const void *residual, int relu, float eps,
+                            float momentum, float *running_mean, float *running_var,
+                            void *workspace, float *mean, float *invstd, void *y, void *stream);
+int meb200_bn_stats_to(const void *x, int dtype, uint32_t n, uint32_t C, void *workspace,
+                       double *sums_out, void *stream);
+int meb200_bn_backward_reduce_to(const void *dy, const void *x, const void *y_mask, int dtype,
+                                 uint32_t n, uint32_t C, const float *mean, const float *invstd,
+                                 void *workspace, double *sums_out, float *grad_weight,
+                                 float *grad_bias, void *stream);
+
 /* ---- synchronised batch norm: statistics exchange over NVLink peer memory ----------------
  * Replaces the per-layer NCCL all-reduce of torch.nn.SyncBatchNorm (reference:
  * MinkowskiEngine/MinkowskiNormalization.py:101-192, examples/multigpu_ddp.py:91-95) by one

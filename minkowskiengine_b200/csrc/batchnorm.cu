@@ -92,12 +92,27 @@ __device__ __forceinline__ BnGeom bn_geom(uint32_t C) {
   return g;
 }
 
+// What the LAST CTA of a reduction does with the totals (ticket != NULL): the work of the
+// separate finalize launch / gradient conversion, and it leaves `sums` and the ticket zero again,
+// so one workspace serves every layer of a stream without a memset per use (a MinkUNet34C step
+// spent ~250 of its ~1030 launches on 2 KB memsets and 1-CTA finalize kernels).
+struct BnTail {
+  uint32_t *ticket;
+  double *totals_out;                                   // [2C] copy of the totals, or NULL
+  float *mean, *invstd, *running_mean, *running_var;    // MODE 0: finalize (mean NULL = skip)
+  double count;
+  float eps, momentum;
+  float *grad_weight, *grad_bias;                       // MODE 1: fp32 parameter gradients, or NULL
+};
+constexpr uint32_t kBnMaxC = 2048;
+constexpr size_t kBnWorkspaceBytes = 2 * kBnMaxC * sizeof(double) + 64;   // sums, then the ticket
+
 // TWO per-channel sums: MODE 0: (x, x^2); MODE 1: (dy, dy * xhat)
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kBnThreads)
 k_bn_reduce(const T *__restrict__ a, const T *__restrict__ x, const T *__restrict__ ymask,
             const float *__restrict__ mean, const float *__restrict__ invstd, uint32_t n,
-            uint32_t C, uint32_t rows_per_cta, double *__restrict__ sums) {
+            uint32_t C, uint32_t rows_per_cta, double *sums, const BnTail tail) {
   extern __shared__ float s_acc[];   // [2C]
   for (uint32_t i = threadIdx.x; i < 2 * C; i += kBnThreads) s_acc[i] = 0.f;
   __syncthreads();
@@ -158,6 +173,40 @@ k_bn_reduce(const T *__restrict__ a, const T *__restrict__ x, const T *__restric
   }
   __syncthreads();
   for (uint32_t i = threadIdx.x; i < 2 * C; i += kBnThreads) atomicAdd(&sums[i], (double)s_acc[i]);
+  if (tail.ticket == nullptr) return;
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(tail.ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (uint32_t c = threadIdx.x; c < C; c += kBnThreads) {
+    const double t1 = __ldcg(sums + c), t2 = __ldcg(sums + C + c);
+    sums[c] = 0.0;
+    sums[C + c] = 0.0;
+    if (tail.totals_out != nullptr) { tail.totals_out[c] = t1; tail.totals_out[C + c] = t2; }
+    if (MODE == 0) {
+      if (tail.mean != nullptr) {
+        const double count = tail.count;
+        const double mu = t1 / count;
+        double var = t2 / count - mu * mu;
+        if (var < 0) var = 0;
+        tail.mean[c] = (float)mu;
+        tail.invstd[c] = (float)(1.0 / sqrt(var + (double)tail.eps));
+        if (tail.running_mean != nullptr) {
+          const double unbiased = count > 1 ? var * count / (count - 1) : var;
+          const double mom = tail.momentum;
+          tail.running_mean[c] = (float)((1.0 - mom) * tail.running_mean[c] + mom * mu);
+          tail.running_var[c] = (float)((1.0 - mom) * tail.running_var[c] + mom * unbiased);
+        }
+      }
+    } else {
+      if (tail.grad_bias != nullptr) tail.grad_bias[c] = (float)t1;
+      if (tail.grad_weight != nullptr) tail.grad_weight[c] = (float)t2;
+    }
+  }
+  if (threadIdx.x == 0) *tail.ticket = 0u;
 }
 
 __global__ void k_bn_finalize(const double *__restrict__ sums, double count,
@@ -288,9 +337,9 @@ int meb200_bn_stats(const void *x, int dtype, uint32_t n, uint32_t C, double *su
   uint32_t rows = bn_rows_per_cta(n, C, &grid);
   size_t smem = 2 * (size_t)C * sizeof(float);
   switch (dtype) {
-    case MEB200_F32: k_bn_reduce<float, 0><<<grid, kBnThreads, smem, s>>>((const float *)x, nullptr, nullptr, nullptr, nullptr, n, C, rows, sums); break;
-    case MEB200_BF16: k_bn_reduce<__nv_bfloat16, 0><<<grid, kBnThreads, smem, s>>>((const __nv_bfloat16 *)x, nullptr, nullptr, nullptr, nullptr, n, C, rows, sums); break;
-    case MEB200_F16: k_bn_reduce<__half, 0><<<grid, kBnThreads, smem, s>>>((const __half *)x, nullptr, nullptr, nullptr, nullptr, n, C, rows, sums); break;
+    case MEB200_F32: k_bn_reduce<float, 0><<<grid, kBnThreads, smem, s>>>((const float *)x, nullptr, nullptr, nullptr, nullptr, n, C, rows, sums, BnTail{}); break;
+    case MEB200_BF16: k_bn_reduce<__nv_bfloat16, 0><<<grid, kBnThreads, smem, s>>>((const __nv_bfloat16 *)x, nullptr, nullptr, nullptr, nullptr, n, C, rows, sums, BnTail{}); break;
+    case MEB200_F16: k_bn_reduce<__half, 0><<<grid, kBnThreads, smem, s>>>((const __half *)x, nullptr, nullptr, nullptr, nullptr, n, C, rows, sums, BnTail{}); break;
     default: set_error("batch norm: unsupported dtype %d", dtype); return MEB200_ERR_UNSUPPORTED;
   }
   MEB_LAUNCH_OK();
@@ -325,6 +374,93 @@ int meb200_bn_apply_fused(const void *x, int dtype, uint32_t n, uint32_t C, cons
   return MEB200_OK;
 }
 
+static int bn_launch_reduce(int mode, const void *a, const void *x, const void *ymask, int dtype,
+                            uint32_t n, uint32_t C, const float *mean, const float *invstd,
+                            double *sums, const BnTail &tail, cudaStream_t s) {
+  unsigned grid;
+  uint32_t rows = bn_rows_per_cta(n, C, &grid);
+  size_t smem = 2 * (size_t)C * sizeof(float);
+#define MEB_BN_RED(TT)                                                                            \
+  do {                                                                                            \
+    if (mode == 0)                                                                                \
+      k_bn_reduce<TT, 0><<<grid, kBnThreads, smem, s>>>((const TT *)a, nullptr, nullptr, nullptr, \
+                                                       nullptr, n, C, rows, sums, tail);          \
+    else                                                                                          \
+      k_bn_reduce<TT, 1><<<grid, kBnThreads, smem, s>>>((const TT *)a, (const TT *)x,             \
+                                                       (const TT *)ymask, mean, invstd, n, C,     \
+                                                       rows, sums, tail);                         \
+  } while (0)
+  switch (dtype) {
+    case MEB200_F32: MEB_BN_RED(float); break;
+    case MEB200_BF16: MEB_BN_RED(__nv_bfloat16); break;
+    case MEB200_F16: MEB_BN_RED(__half); break;
+    default: set_error("batch norm: unsupported dtype %d", dtype); return MEB200_ERR_UNSUPPORTED;
+  }
+#undef MEB_BN_RED
+  MEB_LAUNCH_OK();
+  return MEB200_OK;
+}
+
+uint64_t meb200_bn_workspace_bytes(void) { return kBnWorkspaceBytes; }
+
+static inline uint32_t *bn_ticket(void *workspace) {
+  return reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(workspace) + 2 * kBnMaxC * sizeof(double));
+}
+
+int meb200_bn_forward_train(const void *x, int dtype, uint32_t n, uint32_t C, const float *weight,
+                            const float *bias, const void *residual, int relu, float eps,
+                            float momentum, float *running_mean, float *running_var,
+                            void *workspace, float *mean, float *invstd, void *y, void *stream_) {
+  cudaStream_t s = (cudaStream_t)stream_;
+  MEB_BN_CHECK(C);
+  MEB_CHECK_ARG(n > 0 && workspace && mean && invstd && y, "bn forward: empty input / null buffer");
+  BnTail tail{};
+  tail.ticket = bn_ticket(workspace);
+  tail.mean = mean; tail.invstd = invstd; tail.running_mean = running_mean; tail.running_var = running_var;
+  tail.count = (double)n; tail.eps = eps; tail.momentum = momentum;
+  int rc = bn_launch_reduce(0, x, nullptr, nullptr, dtype, n, C, nullptr, nullptr,
+                            (double *)workspace, tail, s);
+  if (rc != MEB200_OK) return rc;
+  return meb200_bn_apply_fused(x, dtype, n, C, mean, invstd, weight, bias, residual, relu, y, stream_);
+}
+
+int meb200_bn_stats_to(const void *x, int dtype, uint32_t n, uint32_t C, void *workspace,
+                       double *sums_out, void *stream_) {
+  cudaStream_t s = (cudaStream_t)stream_;
+  MEB_BN_CHECK(C);
+  MEB_CHECK_ARG(workspace && sums_out, "bn stats: null buffer");
+  if (n == 0) {
+    MEB_CUDA(cudaMemsetAsync(sums_out, 0, 2 * (size_t)C * sizeof(double), s));
+    return MEB200_OK;
+  }
+  BnTail tail{};
+  tail.ticket = bn_ticket(workspace);
+  tail.totals_out = sums_out;
+  return bn_launch_reduce(0, x, nullptr, nullptr, dtype, n, C, nullptr, nullptr,
+                          (double *)workspace, tail, s);
+}
+
+int meb200_bn_backward_reduce_to(const void *dy, const void *x, const void *y_mask, int dtype,
+                                 uint32_t n, uint32_t C, const float *mean, const float *invstd,
+                                 void *workspace, double *sums_out, float *grad_weight,
+                                 float *grad_bias, void *stream_) {
+  cudaStream_t s = (cudaStream_t)stream_;
+  MEB_BN_CHECK(C);
+  MEB_CHECK_ARG(workspace && sums_out, "bn backward reduce: null buffer");
+  if (n == 0) {
+    MEB_CUDA(cudaMemsetAsync(sums_out, 0, 2 * (size_t)C * sizeof(double), s));
+    if (grad_weight) MEB_CUDA(cudaMemsetAsync(grad_weight, 0, (size_t)C * sizeof(float), s));
+    if (grad_bias) MEB_CUDA(cudaMemsetAsync(grad_bias, 0, (size_t)C * sizeof(float), s));
+    return MEB200_OK;
+  }
+  BnTail tail{};
+  tail.ticket = bn_ticket(workspace);
+  tail.totals_out = sums_out;
+  tail.grad_weight = grad_weight;
+  tail.grad_bias = grad_bias;
+  return bn_launch_reduce(1, dy, x, y_mask, dtype, n, C, mean, invstd, (double *)workspace, tail, s);
+}
+
 int meb200_bn_apply(const void *x, int dtype, uint32_t n, uint32_t C, const float *mean,
                     const float *invstd, const float *weight, const float *bias, int relu,
                     void *y, void *stream_) {
@@ -342,9 +478,9 @@ int meb200_bn_backward_reduce_fused(const void *dy, const void *x, const void *y
   uint32_t rows = bn_rows_per_cta(n, C, &grid);
   size_t smem = 2 * (size_t)C * sizeof(float);
   switch (dtype) {
-    case MEB200_F32: k_bn_reduce<float, 1><<<grid, kBnThreads, smem, s>>>((const float *)dy, (const float *)x, (const float *)y_mask, mean, invstd, n, C, rows, sums); break;
-    case MEB200_BF16: k_bn_reduce<__nv_bfloat16, 1><<<grid, kBnThreads, smem, s>>>((const __nv_bfloat16 *)dy, (const __nv_bfloat16 *)x, (const __nv_bfloat16 *)y_mask, mean, invstd, n, C, rows, sums); break;
-    case MEB200_F16: k_bn_reduce<__half, 1><<<grid, kBnThreads, smem, s>>>((const __half *)dy, (const __half *)x, (const __half *)y_mask, mean, invstd, n, C, rows, sums); break;
+    case MEB200_F32: k_bn_reduce<float, 1><<<grid, kBnThreads, smem, s>>>((const float *)dy, (const float *)x, (const float *)y_mask, mean, invstd, n, C, rows, sums, BnTail{}); break;
+    case MEB200_BF16: k_bn_reduce<__nv_bfloat16, 1><<<grid, kBnThreads, smem, s>>>((const __nv_bfloat16 *)dy, (const __nv_bfloat16 *)x, (const __nv_bfloat16 *)y_mask, mean, invstd, n, C, rows, sums, BnTail{}); break;
+    case MEB200_F16: k_bn_reduce<__half, 1><<<grid, kBnThreads, smem, s>>>((const __half *)dy, (const __half *)x, (const __half *)y_mask, mean, invstd, n, C, rows, sums, BnTail{}); break;
     default: set_error("batch norm: unsupported dtype %d", dtype); return MEB200_ERR_UNSUPPORTED;
   }
   MEB_LAUNCH_OK();

@@ -930,10 +930,15 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
     for (uint32_t i = 0; i < p.nA; ++i) { mbar_init(bar_fullA(bar0, i), 4); mbar_init(bar_emptyA(bar0, i), 1); }
     for (uint32_t i = 0; i < p.nB; ++i) { mbar_init(bar_fullB(bar0, i), 1); mbar_init(bar_emptyB(bar0, i), 1); }
     for (uint32_t i = 0; i < 2; ++i) { mbar_init(bar_tfull(bar0, i), 1); mbar_init(bar_tempty(bar0, i), kEpilogueWarps * 32); }
-    for (uint32_t i = 0; i < NP * kTsDepth; ++i) mbar_init(smem_u32(landed_all + i), 32);
     mbar_fence_init();
   }
   if (warp < NP) {
+    // each producer warp initialises its own landing barriers (one thread doing all ~100
+    // barriers of the CTA was a visible serial prologue on the 30-60 us layers)
+    if (lane < kTsDepth) {
+      mbar_init(smem_u32(landed_all + warp * kTsDepth + lane), 32);
+      mbar_fence_init();
+    }
     // slot RS of every block of this warp's ring holds zeros for good: rows without a neighbour
     // point there, so the read-back path has no branches and no register zeroing
     const uint32_t zbase = smem_u32(rings + warp * ring_bytes) + lane * 16 + p.rs * 512u;

@@ -87,6 +87,20 @@ class _PeerExchange:
             _lib.ptr(invstd), _lib.ptr(total_rows), _lib.current_stream()))
 
 
+_WORKSPACES = {}
+
+
+def _workspace(dev, stream):
+    """The zero-filled reduction workspace of (device, stream) — csrc/batchnorm.cu BnTail: the
+    last CTA of every reduction leaves it zero again, so all layers of a stream share one."""
+    key = (dev.index, stream)
+    ws = _WORKSPACES.get(key)
+    if ws is None:
+        ws = torch.zeros(int(_lib.load().meb200_bn_workspace_bytes()), dtype=torch.uint8, device=dev)
+        _WORKSPACES[key] = ws
+    return ws
+
+
 def _device_guard(dev):
     """Native launches go to the CURRENT device's stream: make the tensor's device current."""
     return torch.cuda.device(dev) if dev.type == "cuda" else contextlib.nullcontext()
@@ -109,37 +123,48 @@ class _BatchNormFunction(torch.autograd.Function):
             w32 = None if weight is None else weight.detach().float().contiguous()
             b32 = None if bias is None else bias.detach().float().contiguous()
             d_count = None
+            if residual is not None:
+                residual = residual.contiguous()
+            y = torch.empty_like(x)
             if use_running:
                 mean = running_mean.detach().float().contiguous()
                 invstd = torch.rsqrt(running_var.detach().float() + eps)
             else:
-                peer = _PeerExchange.get(group, dev) if (group is not None and _USE_PEER) else None
-                if peer is not None:
-                    off, sums = peer.next_slot(2 * C + 1)   # statistics land in symmetric memory
-                else:
-                    sums = torch.empty(2 * C + 1, dtype=torch.float64, device=dev)
-                _lib.check(lib.meb200_bn_stats(_lib.ptr(x), code, n, C, _lib.ptr(sums), stream))
                 mean = torch.empty(C, dtype=torch.float32, device=dev)
                 invstd = torch.empty(C, dtype=torch.float32, device=dev)
-                if peer is not None:      # exchange + finalize in one single-CTA kernel
-                    d_count = torch.empty(1, dtype=torch.float64, device=dev)
-                    peer.bn_finalize(off, C, n, eps, momentum, running_mean, running_var, mean,
-                                     invstd, d_count)
-                else:
-                    if group is not None:
-                        sums[2 * C] = float(n)
-                        torch.distributed.all_reduce(sums, group=group)
-                        d_count = sums[2 * C:]
-                    _lib.check(lib.meb200_bn_finalize(
-                        _lib.ptr(sums), float(max(n, 1)), _lib.ptr(d_count), C, float(eps),
-                        float(momentum), _lib.ptr(running_mean), _lib.ptr(running_var),
-                        _lib.ptr(mean), _lib.ptr(invstd), stream))
-            if residual is not None:
-                residual = residual.contiguous()
-            y = torch.empty_like(x)
-            _lib.check(lib.meb200_bn_apply_fused(
-                _lib.ptr(x), code, n, C, _lib.ptr(mean), _lib.ptr(invstd), _lib.ptr(w32),
-                _lib.ptr(b32), _lib.ptr(residual), 1 if relu else 0, _lib.ptr(y), stream))
+                ws = _workspace(dev, stream)
+            if not use_running and group is None and n > 0:
+                # statistics + finalize in one launch, then the apply pass
+                _lib.check(lib.meb200_bn_forward_train(
+                    _lib.ptr(x), code, n, C, _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(residual),
+                    1 if relu else 0, float(eps), float(momentum), _lib.ptr(running_mean),
+                    _lib.ptr(running_var), _lib.ptr(ws), _lib.ptr(mean), _lib.ptr(invstd),
+                    _lib.ptr(y), stream))
+            else:
+                if not use_running:
+                    peer = _PeerExchange.get(group, dev) if (group is not None and _USE_PEER) else None
+                    if peer is not None:
+                        off, sums = peer.next_slot(2 * C + 1)   # statistics land in symmetric memory
+                    else:
+                        sums = torch.empty(2 * C + 1, dtype=torch.float64, device=dev)
+                    _lib.check(lib.meb200_bn_stats_to(_lib.ptr(x), code, n, C, _lib.ptr(ws),
+                                                      _lib.ptr(sums), stream))
+                    if peer is not None:      # exchange + finalize in one single-CTA kernel
+                        d_count = torch.empty(1, dtype=torch.float64, device=dev)
+                        peer.bn_finalize(off, C, n, eps, momentum, running_mean, running_var,
+                                         mean, invstd, d_count)
+                    else:
+                        if group is not None:
+                            sums[2 * C] = float(n)
+                            torch.distributed.all_reduce(sums, group=group)
+                            d_count = sums[2 * C:]
+                        _lib.check(lib.meb200_bn_finalize(
+                            _lib.ptr(sums), float(max(n, 1)), _lib.ptr(d_count), C, float(eps),
+                            float(momentum), _lib.ptr(running_mean), _lib.ptr(running_var),
+                            _lib.ptr(mean), _lib.ptr(invstd), stream))
+                _lib.check(lib.meb200_bn_apply_fused(
+                    _lib.ptr(x), code, n, C, _lib.ptr(mean), _lib.ptr(invstd), _lib.ptr(w32),
+                    _lib.ptr(b32), _lib.ptr(residual), 1 if relu else 0, _lib.ptr(y), stream))
         ctx.save_for_backward(x, mean, invstd, w32 if w32 is not None else mean.new_empty(0),
                               d_count if d_count is not None else mean.new_empty(0, dtype=torch.float64),
                               y if relu else x.new_empty(0))
@@ -167,12 +192,18 @@ class _BatchNormFunction(torch.autograd.Function):
                 off, gs = peer.next_slot(2 * C)
             else:
                 gs = torch.empty(2 * C, dtype=torch.float64, device=x.device)
-            _lib.check(lib.meb200_bn_backward_reduce_fused(
-                _lib.ptr(dy), _lib.ptr(x), _lib.ptr(ymask), code, n, C, _lib.ptr(mean),
-                _lib.ptr(invstd), _lib.ptr(gs), stream))
             grad_w = grad_b = None
+            g32 = None
             if ctx.has_affine:   # local sums; DDP averages parameter gradients across ranks
-                g32 = gs.to(ctx.param_dtype, copy=True)        # one conversion for both halves
+                g32 = torch.empty(2 * C, dtype=torch.float32, device=x.device)
+                grad_b, grad_w = g32[:C], g32[C:]
+            # one launch: the reduction, its totals into `gs` and the fp32 parameter gradients
+            _lib.check(lib.meb200_bn_backward_reduce_to(
+                _lib.ptr(dy), _lib.ptr(x), _lib.ptr(ymask), code, n, C, _lib.ptr(mean),
+                _lib.ptr(invstd), _lib.ptr(_workspace(x.device, stream)), _lib.ptr(gs),
+                _lib.ptr(grad_w), _lib.ptr(grad_b), stream))
+            if g32 is not None and ctx.param_dtype != torch.float32:
+                g32 = g32.to(ctx.param_dtype)
                 grad_b, grad_w = g32[:C], g32[C:]
             if ctx.use_running:
                 gs = torch.zeros_like(gs)      # statistics are constants: dx = dy' * invstd * w

@@ -93,3 +93,32 @@ def test_fused_bn_relu_matches_torch(ME, cuda, dtype, tol, n, C, with_res, train
     assert (ours.bn.bias.grad - ref.bias.grad).abs().max().item() / ref.bias.grad.abs().max().item() < max(4 * tol, 1e-4)
     if with_res:
         assert ((rs.F.grad.float() - rr.grad).abs() * agree).max().item() / rr.grad.abs().max().item() < 4 * tol
+
+
+def test_reduction_workspace_is_left_clean(ME, cuda):
+    """The launch-lean passes share one workspace per stream (csrc/batchnorm.cu BnTail): after any
+    sequence of layers of different widths it must read all zeros, and results must not depend on
+    what ran before."""
+    from minkowskiengine_b200 import _lib, normalization as N
+    torch.manual_seed(3)
+    outs = []
+    for rep in range(2):
+        for n, C in [(4000, 256), (12345, 96), (50, 8), (30000, 32), (777, 2048)]:
+            x = torch.randn(n, C, device=cuda).to(torch.bfloat16) if rep == 0 else outs[0][(n, C)][0]
+            bn = ME.MinkowskiBatchNorm(C).to(cuda)
+            coords = torch.cat([torch.zeros(n, 1, dtype=torch.int32),
+                                torch.arange(n, dtype=torch.int32).unsqueeze(1).repeat(1, 3)], 1).to(cuda)
+            st = ME.SparseTensor(x.clone().requires_grad_(True), coords)
+            y = bn(st)
+            y.F.backward(torch.ones_like(y.F))
+            if rep == 0:
+                outs.append({}) if not outs else None
+                outs[0][(n, C)] = (x, y.F.detach().clone(), st.F.grad.clone())
+            else:
+                _, y0, g0 = outs[0][(n, C)]
+                assert torch.equal(y.F, y0) or (y.F.float() - y0.float()).abs().max() < 1e-2
+                assert (st.F.grad.float() - g0.float()).abs().max() < 1e-2
+    torch.cuda.synchronize()
+    assert N._WORKSPACES, "the launch-lean path did not run"
+    for ws in N._WORKSPACES.values():
+        assert int(ws.count_nonzero()) == 0

@@ -198,17 +198,21 @@ def test_batchnorm_host_path_runs_against_a_stub_library(monkeypatch):
 
     monkeypatch.setattr(_lib, "load", lambda: Stub())
     monkeypatch.setattr(_lib, "current_stream", lambda: None)
+    monkeypatch.setattr(N, "_USE_PEER", False)
+    N._WORKSPACES.clear()
     x = torch.randn(10, 16, requires_grad=True)
     w, b = torch.ones(16, requires_grad=True), torch.zeros(16, requires_grad=True)
     rm, rv = torch.zeros(16), torch.ones(16)
     y = N._BatchNormFunction.apply(x, w, b, rm, rv, 0.1, 1e-5, None, False, None, False)
     y.sum().backward()
     names = [c[0] for c in calls]
-    assert names == ["meb200_bn_stats", "meb200_bn_finalize", "meb200_bn_apply_fused",
-                     "meb200_bn_backward_reduce_fused", "meb200_bn_backward_apply_fused"]
-    assert calls[1][1][2] is None and calls[4][1][11] is None        # no device-side count
-    assert calls[2][1][8] is None and calls[2][1][9] == 0            # no residual, no ReLU
-    assert calls[3][1][2] is None and calls[4][1][13] is None        # no ReLU mask, no d_residual
+    # one workspace query, then two launches-worth of calls per pass
+    assert names == ["meb200_bn_workspace_bytes", "meb200_bn_forward_train",
+                     "meb200_bn_backward_reduce_to", "meb200_bn_backward_apply_fused"]
+    assert calls[3][1][11] is None                                   # no device-side count
+    assert calls[1][1][6] is None and calls[1][1][7] == 0            # no residual, no ReLU
+    assert calls[2][1][2] is None and calls[3][1][13] is None        # no ReLU mask, no d_residual
+    assert calls[2][1][10] is not None and calls[2][1][11] is not None   # fp32 parameter gradients
     assert x.grad.shape == x.shape and w.grad.shape == (16,) and b.grad.shape == (16,)
     # fused tail of a residual block: relu(bn(x) + residual), gradient of the residual returned
     calls.clear()
@@ -216,15 +220,17 @@ def test_batchnorm_host_path_runs_against_a_stub_library(monkeypatch):
     res = torch.randn(10, 16, requires_grad=True)
     y3 = N._BatchNormFunction.apply(x3, w, b, rm, rv, 0.1, 1e-5, None, True, res, False)
     y3.sum().backward()
-    assert calls[2][1][8] is not None and calls[2][1][9] == 1
-    assert calls[3][1][2] is not None and calls[4][1][2] is not None and calls[4][1][13] is not None
+    assert [c[0] for c in calls] == ["meb200_bn_forward_train", "meb200_bn_backward_reduce_to",
+                                     "meb200_bn_backward_apply_fused"]
+    assert calls[0][1][6] is not None and calls[0][1][7] == 1
+    assert calls[1][1][2] is not None and calls[2][1][2] is not None and calls[2][1][13] is not None
     assert res.grad is not None and res.grad.shape == res.shape
     # inference under autograd: running statistics, no statistics pass, gradients still flow
     calls.clear()
     x4 = torch.randn(10, 16, requires_grad=True)
     y4 = N._BatchNormFunction.apply(x4, w, b, rm, rv, 0.1, 1e-5, None, False, None, True)
     y4.sum().backward()
-    assert [c[0] for c in calls] == ["meb200_bn_apply_fused", "meb200_bn_backward_reduce_fused",
+    assert [c[0] for c in calls] == ["meb200_bn_apply_fused", "meb200_bn_backward_reduce_to",
                                      "meb200_bn_backward_apply_fused"]
     assert x4.grad is not None
     # synchronised: the count travels with the sums and is read on the device
@@ -235,5 +241,7 @@ def test_batchnorm_host_path_runs_against_a_stub_library(monkeypatch):
     y2 = N._BatchNormFunction.apply(x2, w, b, rm, rv, 0.1, 1e-5, object(), False, None, False)
     y2.sum().backward()
     assert reduced == [2 * 16 + 1, 2 * 16]
+    assert [c[0] for c in calls] == ["meb200_bn_stats_to", "meb200_bn_finalize", "meb200_bn_apply_fused",
+                                     "meb200_bn_backward_reduce_to", "meb200_bn_backward_apply_fused"]
     assert calls[1][1][2] is not None and calls[4][1][11] is not None
     assert isinstance(ME.MinkowskiSyncBatchNorm(16).bn, torch.nn.SyncBatchNorm)
