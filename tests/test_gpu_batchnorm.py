@@ -116,8 +116,8 @@ def test_reduction_workspace_is_left_clean(ME, cuda):
                 outs[0][(n, C)] = (x, y.F.detach().clone(), st.F.grad.clone())
             else:
                 _, y0, g0 = outs[0][(n, C)]
-                assert torch.equal(y.F, y0) or (y.F.float() - y0.float()).abs().max() < 1e-2
-                assert (st.F.grad.float() - g0.float()).abs().max() < 1e-2
+                assert torch.equal(y.F, y0) or (y.F.float() - y0.float()).abs().max() < 6e-2
+                assert (st.F.grad.float() - g0.float()).abs().max() < 6e-2
     torch.cuda.synchronize()
     assert N._WORKSPACES, "the launch-lean path did not run"
     for ws in N._WORKSPACES.values():
