@@ -189,6 +189,25 @@ int meb200_conv_pack_weights(const float *weight, uint32_t K, uint32_t c_in, uin
                              int dtype, void *w_cast, void *w_t, void *w_cp, void *w_tp,
                              void *stream);
 
+/* Network stem (the first layer of a network: c_in <= 4 input channels, e.g. RGB; reference
+ * call site examples/minkunet.py:113-116 conv0p1s1, kernel 5 -> K = 125).  Rows of 8 bytes defeat
+ * the 64-byte-block gather of the general kernels, so the layer is run as a K = 1 convolution over
+ * VIRTUAL channels v = 4 k + c (offset k < 16 ceil(K / 16), channel c < 4):
+ *   in4            [n_in, 4]   the features zero-padded to 4 channels
+ *   weight_v       [c_out, V]  V = meb200_conv_stem_virtual_channels(K); the `w_tp` output of
+ *                              meb200_conv_pack_weights(Wv, K=1, c_in=V, c_out) where
+ *                              Wv[4 k + c][n] = W[k][c][n] (zero for padded k, c)
+ *   grad_weight_v  [V, c_out]  fp32, same indexing (zero-filled by the call)
+ * bf16 / fp16 only; c_out a multiple of 16, <= 256; K <= 128. */
+uint32_t meb200_conv_stem_virtual_channels(uint32_t K);
+int meb200_conv_stem_supported(int dtype, uint32_t K, uint32_t c_out);
+int meb200_conv_stem_forward(const void *in4, int dtype, uint32_t K, const void *weight_v,
+                             uint32_t c_out, const int32_t *out_nbr, uint32_t n_out, void *out,
+                             int out_dtype, void *stream);
+int meb200_conv_stem_wgrad(const void *in4, const void *grad_out, int dtype, uint32_t K,
+                           uint32_t c_out, const int32_t *out_nbr, uint32_t n_out,
+                           float *grad_weight_v, void *stream);
+
 /* meb200_conv_forward with the weight already packed (tensor-core path only: returns
  * MEB200_ERR_UNSUPPORTED for shapes/dtypes outside it, the caller then uses
  * meb200_conv_forward).  Same result, no per-call cast/transpose, no workspace.

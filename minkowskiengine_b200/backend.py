@@ -710,6 +710,44 @@ def _packed_weights(kernel, dtype):
     return packed
 
 
+_STEM = os.environ.get("MEB200_STEM_TC", "1") not in ("", "0")
+
+
+def _is_stem(kernel, feat_dtype):
+    """Layers with <= 4 input channels (the stem of a network) on the bf16/fp16 path: run over
+    virtual channels (offset, channel) by the stem kernels (include/meb200.h)."""
+    if not (_STEM and kernel.dim() == 3 and kernel.shape[1] <= 4 and _can_pack(kernel, feat_dtype)):
+        return False
+    return bool(_lib.load().meb200_conv_stem_supported(_lib.dtype_code(feat_dtype), kernel.shape[0],
+                                                       kernel.shape[2]))
+
+
+def _stem_weights(kernel, dtype):
+    """Packed weights of the stem's virtual K = 1 layer, [c_out, V] (cached like _packed_weights)."""
+    key = (id(kernel), "stem")
+    ent = _PACKED.get(key)
+    if ent is not None and ent[0]() is kernel and ent[1] == kernel._version \
+            and ent[2] == kernel.data_ptr() and ent[3] == dtype:
+        return ent[4]
+    lib = _lib.load()
+    K, c_in, c_out = kernel.shape
+    V = int(lib.meb200_conv_stem_virtual_channels(K))
+    wv = torch.zeros((V // 4, 4, c_out), dtype=torch.float32, device=kernel.device)
+    wv[:K, :c_in] = kernel.detach()
+    buf = torch.empty((4, V * c_out), dtype=dtype, device=kernel.device)
+    _lib.check(lib.meb200_conv_pack_weights(
+        _lib.ptr(wv), 1, V, c_out, _lib.dtype_code(dtype), _lib.ptr(buf[0]), _lib.ptr(buf[1]),
+        _lib.ptr(buf[2]) if c_out % 32 == 0 else None, _lib.ptr(buf[3]), _lib.current_stream()))
+    w_v = buf[3].view(c_out, V)
+    _PACKED[key] = (weakref.ref(kernel), kernel._version, kernel.data_ptr(), dtype, w_v)
+    return w_v
+
+
+def _pad4(feat):
+    c = feat.shape[1]
+    return feat.contiguous() if c == 4 else torch.nn.functional.pad(feat, (0, 4 - c))
+
+
 def _can_pack(kernel, feat_dtype):
     return (kernel.dtype == torch.float32 and feat_dtype in (torch.bfloat16, torch.float16)
             and kernel.is_contiguous() and kernel.dim() == 3)
@@ -718,6 +756,18 @@ def _can_pack(kernel, feat_dtype):
 def _conv_forward_impl(in_feat, kernel, km, out_dtype=None):
     lib = _lib.load()
     code = _lib.dtype_code(in_feat.dtype)
+    if _is_stem(kernel, in_feat.dtype):
+        K, c_in, c_out = kernel.shape
+        _assert(K == km.K, "kernel volume", K, "does not match the kernel map", km.K)
+        out = torch.empty((km.n_out, c_out), dtype=out_dtype or in_feat.dtype,
+                          device=in_feat.device)
+        rc = lib.meb200_conv_stem_forward(
+            _lib.ptr(_pad4(in_feat)), code, K, _lib.ptr(_stem_weights(kernel, in_feat.dtype)), c_out,
+            _lib.ptr(km.out_nbr), km.n_out, _lib.ptr(out), _lib.dtype_code(out.dtype),
+            _lib.current_stream())
+        if rc != _ERR_UNSUPPORTED:
+            _lib.check(rc)
+            return out
     if _can_pack(kernel, in_feat.dtype):
         K, c_in, c_out = kernel.shape
         _assert(K == km.K, "kernel volume", K, "does not match the kernel map", km.K)
@@ -777,6 +827,16 @@ def _conv_backward_impl(in_feat, grad_out, kernel, km, need_in=True, need_w=True
         if need_in else None
     grad_w = torch.empty((K, c_in, c_out), dtype=torch.float32, device=in_feat.device) \
         if need_w else None
+    if need_w and not need_in and _is_stem(kernel, in_feat.dtype):
+        # the stem's input needs no gradient (it is the network input): wgrad alone
+        V = int(lib.meb200_conv_stem_virtual_channels(K))
+        gwv = torch.empty((V // 4, 4, c_out), dtype=torch.float32, device=in_feat.device)
+        rc = lib.meb200_conv_stem_wgrad(
+            _lib.ptr(_pad4(in_feat)), _lib.ptr(grad_out), code, K, c_out, _lib.ptr(km.out_nbr),
+            n_out, _lib.ptr(gwv), _lib.current_stream())
+        if rc != _ERR_UNSUPPORTED:
+            _lib.check(rc)
+            return None, gwv[:K, :c_in].contiguous()
     if _can_pack(kernel, in_feat.dtype):
         w, _, w_cp, _ = _packed_weights(kernel, in_feat.dtype)
         pin = pout = seg = None

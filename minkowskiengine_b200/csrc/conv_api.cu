@@ -63,6 +63,39 @@ int meb200_conv_pack_weights(const float *weight, uint32_t K, uint32_t c_in, uin
                            (cudaStream_t)stream_);
 }
 
+uint32_t meb200_conv_stem_virtual_channels(uint32_t K) { return 4u * ((K + 15u) / 16u * 16u); }
+
+int meb200_conv_stem_supported(int dtype, uint32_t K, uint32_t c_out) {
+  if (tc_disabled()) return 0;
+  return conv_stem_tc_supported(dtype, K, c_out) && conv_stem_wgrad_tc_supported(dtype, K, c_out) ? 1 : 0;
+}
+
+int meb200_conv_stem_forward(const void *in4, int dtype, uint32_t K, const void *weight_v,
+                             uint32_t c_out, const int32_t *out_nbr, uint32_t n_out, void *out,
+                             int out_dtype, void *stream_) {
+  if (n_out == 0) return MEB200_OK;
+  MEB_CHECK_ARG(out_dtype == MEB200_F32 || out_dtype == dtype, "output dtype must be fp32 or the input dtype");
+  MEB_CHECK_ARG(in4 && weight_v && out_nbr && out, "null buffer");
+  if (tc_disabled() || !conv_stem_tc_supported(dtype, K, c_out)) {
+    set_error("stem forward: shape/dtype outside the tensor-core path (K=%u c_out=%u)", K, c_out);
+    return MEB200_ERR_UNSUPPORTED;
+  }
+  return conv_stem_forward_tc(in4, dtype, K, weight_v, c_out, out_nbr, n_out, out, out_dtype,
+                              (cudaStream_t)stream_);
+}
+
+int meb200_conv_stem_wgrad(const void *in4, const void *grad_out, int dtype, uint32_t K,
+                           uint32_t c_out, const int32_t *out_nbr, uint32_t n_out,
+                           float *grad_weight_v, void *stream_) {
+  MEB_CHECK_ARG(grad_weight_v && (n_out == 0 || (in4 && grad_out && out_nbr)), "null buffer");
+  if (tc_disabled() || !conv_stem_wgrad_tc_supported(dtype, K, c_out)) {
+    set_error("stem wgrad: shape/dtype outside the tensor-core path (K=%u c_out=%u)", K, c_out);
+    return MEB200_ERR_UNSUPPORTED;
+  }
+  return conv_stem_wgrad_tc(in4, grad_out, dtype, K, c_out, out_nbr, n_out, grad_weight_v,
+                            (cudaStream_t)stream_);
+}
+
 int meb200_conv_forward_packed(const void *in, int in_dtype, uint32_t n_in, uint32_t c_in,
                                const void *weight_t, const void *weight_tp, uint32_t K,
                                uint32_t c_out, const int32_t *out_nbr, uint32_t n_out, void *out,

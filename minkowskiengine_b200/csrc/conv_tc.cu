@@ -901,9 +901,15 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
   // mc of c_red).  G > 1 (c_red = 32 NB / G): the stage concatenates the rows of G consecutive
   // offsets along the reduction axis — out = sum_k A_k W_k = [A_k0 .. A_k(G-1)] [W_k0; ..] — so
   // the narrow layers get stages as fat as the wide ones instead of G times as many thin ones.
+  // G = 0 (STEM, rows of 4 channels = 8 bytes, e.g. the 3-channel input of a network): the
+  // reduction axis is (offset, channel) with 8 offsets per 32-channel block, a stage covers
+  // GI = 8 NB offsets of one row tile; everything downstream of the producers sees a K = 1
+  // convolution over c_red = 4 * (padded K) virtual channels (p.Kg = 1, p.n_macro = chunks).
+  constexpr bool STEM = (G == 0);
+  constexpr int GI = STEM ? 8 * NB : G;        // offsets whose indices a stage needs
   constexpr uint32_t KC = 32u * NB;
   constexpr uint32_t kACols = 16u * NB;
-  constexpr int NBo = NB / G;                  // 32-channel blocks per offset
+  constexpr int NBo = STEM ? 1 : NB / (STEM ? 1 : G);   // 32-channel blocks per offset
   constexpr int NP = kTsProducerWarps;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>(
@@ -917,7 +923,7 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * kMaxStages + 4);
   uint64_t *landed_all = reinterpret_cast<uint64_t *>(tail + tc::kBarBytes + 64);   // [NP][kTsDepth]
   uint32_t *desc_all = reinterpret_cast<uint32_t *>(landed_all + NP * kTsDepth);    // [NP][kTsDepth][32]
-  int32_t *idx_all = reinterpret_cast<int32_t *>(desc_all + NP * kTsDepth * 32);     // [NP][kTsPf][G][32]
+  int32_t *idx_all = reinterpret_cast<int32_t *>(desc_all + NP * kTsDepth * 32);     // [NP][kTsPf][GI][32]
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t R = p.R;
@@ -973,15 +979,15 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
     // use, r2_run4) — so the indices of stage j + kTsPf are copied by cp.async (4 bytes per lane,
     // one coalesced 128-byte row of the table per warp and offset) into a per-warp ring in shared
     // memory, one commit group per issued stage.
-    const uint32_t iring = smem_u32(idx_all + warp * kTsPf * G * 32);
+    const uint32_t iring = smem_u32(idx_all + warp * kTsPf * GI * 32);
     auto copy_idx = [&](const TaPos &q, uint32_t j) {
       if (j < n_j) {
         const uint32_t grow = (q.st * R + q.r) * kTileM + quad * 32 + lane;
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const uint32_t k = q.k * G + g;
+        for (int g = 0; g < GI; ++g) {
+          const uint32_t k = (STEM ? q.mc : q.k) * GI + g;
           const bool ok = grow < p.n_rows && k < p.K;
-          cp_async4(iring + (((j % kTsPf) * G + g) * 32 + lane) * 4,
+          cp_async4(iring + (((j % kTsPf) * GI + g) * 32 + lane) * 4,
                     p.nbr + (ok ? (size_t)k * p.n_rows + grow : 0), ok ? 4u : 0u);
         }
       }
@@ -1001,20 +1007,49 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
         // indices of stage tail_j: copied kTsPf issued stages ago (or in the prologue)
         cp_async_wait<kTsPf - 1>();
         __syncwarp();
-        int32_t srow[4][G];
-        uint32_t nv = 0;
+        uint32_t nv = 0, dw = 0;
         const uint32_t grow0 = (pis.st * R + pis.r) * kTileM + quad * 32 + rsub;
+        const uint32_t d = tail_j % kTsDepth;
+        const uint32_t bstride = (RS + 1) * 512u;
+        if constexpr (STEM) {
+          // every row takes a slot (with 16 offsets per stage a row without any neighbour is
+          // rare); a 16-byte piece = the 4-channel rows of TWO offsets, 8 bytes each
+          nv = 4;
+          if (!__all_sync(0xffffffffu, used + nv <= RS)) break;
+          const T *A4 = reinterpret_cast<const T *>(p.A);
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const uint32_t rq = (m >> 1) * 16 + (m & 1) * 8;
+            const bool row_ok = grow0 + rq < p.n_rows;
+            const uint32_t dst = ring + wr * 512u;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const uint32_t o = b * 8 + piece * 2 + e;
+                int32_t v;
+                asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v)
+                             : "r"(iring + (((tail_j % kTsPf) * GI + o) * 32 + rq + rsub) * 4));
+                const bool ok = row_ok && pis.mc * GI + o < p.K && v >= 0;
+                cp_async8(dst + b * bstride + e * 8, A4 + (ok ? (size_t)v * 4 : 0), ok ? 8u : 0u);
+              }
+            }
+            dw |= wr << (8 * m);
+            if (++wr == RS) wr = 0;
+          }
+        } else {
+        int32_t srow[4][GI];
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
           const uint32_t rq = (m >> 1) * 16 + (m & 1) * 8;
           bool any = false;
 #pragma unroll
-          for (int g = 0; g < G; ++g) {
+          for (int g = 0; g < GI; ++g) {
             int32_t v;
             asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v)
-                         : "r"(iring + (((tail_j % kTsPf) * G + g) * 32 + rq + rsub) * 4));
+                         : "r"(iring + (((tail_j % kTsPf) * GI + g) * 32 + rq + rsub) * 4));
             // rows past the end and offsets past K were zero-filled, not -1
-            const bool in_range = grow0 + rq < p.n_rows && pis.k * G + g < p.K;
+            const bool in_range = grow0 + rq < p.n_rows && pis.k * GI + g < p.K;
             srow[m][g] = in_range ? v : -1;
             any |= srow[m][g] >= 0;
           }
@@ -1022,10 +1057,7 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
           nv += any;
         }
         if (!__all_sync(0xffffffffu, used + nv <= RS)) break;
-        const uint32_t d = tail_j % kTsDepth;
         const T *src0 = A + pis.mc * KC;
-        const uint32_t bstride = (RS + 1) * 512u;
-        uint32_t dw = 0;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
           uint32_t code = RS;                 // the zero slot
@@ -1037,13 +1069,14 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
               const int32_t sr = srow[m][b / NBo];
               // G > 1: block b = channels 32 (b % NBo) of offset b / NBo; a missing offset of a
               // row that has others is zero-filled by the copy engine
-              const T *src = (G == 1 ? src0 : A) + (sr < 0 ? 0 : (size_t)sr * p.c_red) +
-                             (G == 1 ? b : b % NBo) * 32;
+              const T *src = (GI == 1 ? src0 : A) + (sr < 0 ? 0 : (size_t)sr * p.c_red) +
+                             (GI == 1 ? b : b % NBo) * 32;
               cp_async16(dst + b * bstride, src, sr < 0 ? 0u : 16u);
             }
             if (++wr == RS) wr = 0;
           }
           dw |= code << (8 * m);
+        }
         }
         used += nv;
         desc[d * 32] = dw;
@@ -1107,7 +1140,7 @@ k_conv_ts(const __grid_constant__ CUtensorMap mapB, const TaParams p) {
   } else if (warp == NP + kEpilogueWarps) {
     ta_mma<T, NB, BK>(p, sB, bar0, tmem_base);
   } else if (warp == NP + kEpilogueWarps + 1) {
-    if (lane == 0) ta_bload<NB, BK, G>(&mapB, p, sB, bar0);
+    if (lane == 0) ta_bload<NB, BK, (STEM ? 1 : G)>(&mapB, p, sB, bar0);
   }
 
   tc_fence_before();
@@ -1185,6 +1218,44 @@ static int launch_ta_slice(const void *A, int dtype, uint32_t n_a, uint32_t c_re
   if (dtype == MEB200_BF16) { MEB_TA(__nv_bfloat16) } else { MEB_TA(__half) }
 #undef MEB_TA
   return MEB200_ERR_UNSUPPORTED;
+}
+
+// ---- network stem: rows of 4 channels (8 bytes), see k_conv_ts STEM --------------------------
+// A4 = input features padded to 4 channels [n_a, 4]; Wv = permuted packed weights of the virtual
+// K = 1 layer, [c_cols, 4 * 16 * ceil(K / 16)] (reduction axis contiguous, ta_perm order inside
+// each 32-channel block = 8 offsets x 4 channels).
+bool conv_stem_tc_supported(int dtype, uint32_t K, uint32_t c_cols) {
+  if (dtype != MEB200_BF16 && dtype != MEB200_F16) return false;
+  return ts_enabled() && tc::ta_stem_config(K, c_cols, 1u << 20).nb != 0;
+}
+
+int conv_stem_forward_tc(const void *A4, int dtype, uint32_t K, const void *Wv, uint32_t c_cols,
+                         const int32_t *nbr, uint32_t n_rows, void *out, int out_dtype,
+                         cudaStream_t stream) {
+  if (n_rows == 0) return MEB200_OK;
+  const tc::TaCfg cfg = tc::ta_stem_config(K, c_cols, n_rows);
+  if (cfg.nb == 0) {
+    set_error("stem forward: no configuration (K=%u c_out=%u)", K, c_cols);
+    return MEB200_ERR_UNSUPPORTED;
+  }
+  const uint32_t c_virt = tc::stem_virtual_channels(K);
+  TaParams p{};
+  p.A = A4; p.nbr = nbr; p.out = out;
+  p.c_red = c_virt; p.c_cols = c_cols; p.K = K; p.n_rows = n_rows;
+  p.wb_row0 = 0; p.wb_rows_per_k = c_cols;
+  p.n_super = cfg.n_super; p.R = cfg.R; p.acc_sets = cfg.acc_sets; p.nA = cfg.nA; p.nB = cfg.nB;
+  p.n_macro = cfg.n_macro; p.b_stage_bytes = cfg.b_stage_bytes; p.b_sub_bytes = cfg.b_sub_bytes;
+  p.a_col0 = cfg.a_col0; p.out_f32 = out_dtype == MEB200_F32; p.out_ld = c_cols;
+  p.rs = cfg.rs;
+  p.Kg = 1;
+  CUtensorMap mB;
+  memset(&mB, 0, sizeof(mB));
+  int rc = make_map_2d(&mB, dtype, Wv, (uint64_t)c_cols, c_virt, (uint32_t)cfg.bk, c_cols);
+  if (rc != MEB200_OK) return rc;
+  const unsigned grid = p.n_super < (uint32_t)num_sms() ? p.n_super : (unsigned)num_sms();
+  if (dtype == MEB200_BF16)
+    return launch_ts<__nv_bfloat16, (int)tc::kStemNb, 64, 0>(mB, p, cfg.smem_bytes, grid, stream);
+  return launch_ts<__half, (int)tc::kStemNb, 64, 0>(mB, p, cfg.smem_bytes, grid, stream);
 }
 
 bool conv_tc_supported(int dtype, uint32_t c_reduce, uint32_t c_cols) {
@@ -1555,8 +1626,14 @@ struct WpWalk {
 // S = copy slots per thread per operand per 8 rows = ceil(channels / 32), a template parameter so
 // that the slot tables live in registers and no dead slot is ever stepped over (with 8 generic
 // slots the loop was 672 instructions per stage and warp, its tables spilled to local memory).
-template <typename T, int S>
+// RW = pairs per stage (64, or 32 for wide layers: with 64-row stages a 256 + 256 channel layer
+// fits only 3 stages = one per producer group, and a group then runs issue -> landing -> MMA
+// strictly in sequence: 14 k cycles per stage on block4 256->256, r2_run15).
+template <typename T, int S, int RW>
 __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p) {
+  constexpr uint32_t kBlk = RW * 128u;            // one 64-channel block of a stage
+  constexpr uint32_t kHalves = RW / 32;           // 8-row halves per producer warp
+  constexpr uint32_t kRowsPerWarp = RW / 4;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1575,7 +1652,7 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
   const uint32_t mt = (ch_n + 127) / 128;
   const uint32_t n_seg = p.n_chunks * p.K;
 
-  for (uint32_t i = threadIdx.x; i <= n_seg; i += kWpThreads) seg[i] = __ldg(p.seg_start + i) / kWpRows;
+  for (uint32_t i = threadIdx.x; i <= n_seg; i += kWpThreads) seg[i] = __ldg(p.seg_start + i) / RW;
   if (threadIdx.x == 0) {
     for (uint32_t i = 0; i < p.n_stage; ++i) {
       mbar_init(bar_fullA(bar0, i), 4 * 32);       // the four warps of the owning group
@@ -1615,13 +1692,13 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
         const uint32_t rl = c / cprA, chunk = c - rl * cprA;
         const bool ok = (uint32_t)sl < nA && rl < 8;
         a_meta[sl] = ok ? (rl | (chunk << 3)) : 0xffffffffu;
-        a_dst[sl] = (chunk >> 3) * kBlkBytes + (qw * 16 + rl) * 128 + (((chunk & 7u) ^ rl) << 4);
+        a_dst[sl] = (chunk >> 3) * kBlk + (qw * kRowsPerWarp + rl) * 128 + (((chunk & 7u) ^ rl) << 4);
       }
       {
         const uint32_t rl = c / cprB, chunk = c - rl * cprB;
         const bool ok = (uint32_t)sl < nB && rl < 8;
         b_meta[sl] = ok ? (rl | (chunk << 3)) : 0xffffffffu;
-        b_dst[sl] = p.a_bytes + (chunk >> 3) * kBlkBytes + (qw * 16 + rl) * 128 +
+        b_dst[sl] = p.a_bytes + (chunk >> 3) * kBlk + (qw * kRowsPerWarp + rl) * 128 +
                     (((chunk & 7u) ^ rl) << 4);
       }
     }
@@ -1630,7 +1707,8 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
     // rows) into a per-warp ring in shared memory, one commit group per stage (a register ring
     // would make every stage wait for its newest load).
     const int32_t *list = lane < 16 ? p.pin : p.pout;
-    const uint32_t li = qw * 16 + (lane & 15u);
+    const uint32_t li = qw * kRowsPerWarp + (lane & 15u);
+    const bool li_ok = (lane & 15u) < kRowsPerWarp;
     const uint32_t iring = smem_u32(iring_all + warp * kWpPf * 32);
     WpWalk wk, wpf;
     wk.init(seg, p.K, p.n_chunks, split, p.n_splits);
@@ -1643,7 +1721,8 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
       if (!wpf.done()) {                                                                          \
         const uint32_t stage__ = wpf.s;                                                           \
         wpf.skip(kWpGroups);                                                                      \
-        cp_async4(iring + (((nn) % kWpPf) * 32 + lane) * 4, list + (size_t)stage__ * kWpRows + li, 4u); \
+        if (li_ok)                                                                                \
+          cp_async4(iring + (((nn) % kWpPf) * 32 + lane) * 4, list + (size_t)stage__ * RW + li, 4u); \
       }                                                                                           \
       cp_async_commit();                                                                          \
     } while (0)
@@ -1660,7 +1739,7 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
       const uint32_t base = s0 + slot * p.stage_bytes;
       const uint32_t irow = iring + (n % kWpPf) * 128;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < (int)kHalves; ++h) {
 #pragma unroll
         for (int sl = 0; sl < S; ++sl) {
           if ((uint32_t)sl < nA) {
@@ -1752,9 +1831,9 @@ __global__ void __launch_bounds__(kWpThreads, 1) k_wgrad_pairs(const WpParams p)
             const uint32_t abase = s0 + slot * p.stage_bytes, bbase = abase + p.a_bytes;
             for (uint32_t t = 0; t < mt; ++t) {
 #pragma unroll
-              for (int j = 0; j < kWpRows / 16; ++j) {
-                const uint64_t da = umma_desc(abase + t * 2 * kBlkBytes + j * 2048, kBlkBytes, 1024, 2);
-                const uint64_t db = umma_desc(bbase + j * 2048, kBlkBytes, 1024, 2);
+              for (int j = 0; j < RW / 16; ++j) {
+                const uint64_t da = umma_desc(abase + t * 2 * kBlk + j * 2048, kBlk, 1024, 2);
+                const uint64_t db = umma_desc(bbase + j * 2048, kBlk, 1024, 2);
                 umma_f16(d0 + t * p.c_out, da, db, idesc, (!first || j != 0) ? 1u : 0u);
               }
             }
@@ -1806,23 +1885,235 @@ int conv_wgrad_pairs(const void *in, const void *grad_out, int dtype, uint32_t c
   // slots per thread: the wider of the two operands' rows (A: this CTA's channel slice)
   const uint32_t ch_a = c_in < cfg.mt_cta * 128 ? c_in : cfg.mt_cta * 128;
   const uint32_t slots = ((ch_a > c_out ? ch_a : c_out) + 31) / 32;
-#define MEB_WP(SV)                                                                              \
+#define MEB_WP(SV, RWV)                                                                         \
   do {                                                                                          \
     if (dtype == MEB200_BF16) {                                                                 \
-      MEB_BIG_SMEM((k_wgrad_pairs<__nv_bfloat16, SV>));                                         \
-      k_wgrad_pairs<__nv_bfloat16, SV><<<grid, kWpThreads, cfg.smem_bytes, stream>>>(p);        \
+      MEB_BIG_SMEM((k_wgrad_pairs<__nv_bfloat16, SV, RWV>));                                    \
+      k_wgrad_pairs<__nv_bfloat16, SV, RWV><<<grid, kWpThreads, cfg.smem_bytes, stream>>>(p);   \
     } else {                                                                                    \
-      MEB_BIG_SMEM((k_wgrad_pairs<__half, SV>));                                                \
-      k_wgrad_pairs<__half, SV><<<grid, kWpThreads, cfg.smem_bytes, stream>>>(p);               \
+      MEB_BIG_SMEM((k_wgrad_pairs<__half, SV, RWV>));                                           \
+      k_wgrad_pairs<__half, SV, RWV><<<grid, kWpThreads, cfg.smem_bytes, stream>>>(p);          \
     }                                                                                           \
   } while (0)
-  if (slots <= 1) MEB_WP(1);
-  else if (slots == 2) MEB_WP(2);
-  else if (slots == 3) MEB_WP(3);
-  else if (slots == 4) MEB_WP(4);
-  else if (slots <= 6) MEB_WP(6);
-  else MEB_WP(8);
+  if (cfg.rw == 32) {           // wide layers only (the narrow ones fit >= 6 stages of 64 pairs)
+    if (slots <= 4) MEB_WP(4, 32);
+    else if (slots <= 6) MEB_WP(6, 32);
+    else MEB_WP(8, 32);
+  } else if (slots <= 1) MEB_WP(1, 64);
+  else if (slots == 2) MEB_WP(2, 64);
+  else if (slots == 3) MEB_WP(3, 64);
+  else if (slots == 4) MEB_WP(4, 64);
+  else if (slots <= 6) MEB_WP(6, 64);
+  else MEB_WP(8, 64);
 #undef MEB_WP
+  count_tc_launch();
+  MEB_LAUNCH_OK();
+  return MEB200_OK;
+}
+
+// =====================================================================================
+// wgrad of a network STEM (rows of 4 channels, see k_conv_ts STEM): the reduction runs over ALL
+// output rows (dense, output-stationary on dW), the M axis is (offset, channel):
+//   dWv[4 k + c][n] = sum_r in4[nbr[k][r]][c] * dOut[r][n]        k < Kp = 16 ceil(K / 16)
+// A stage = 32 output rows: A = [32 rows x 4 Kp virtual channels] gathered 8 bytes per
+// (row, offset) straight into MN-major 128B-swizzled blocks (missing neighbours zero-filled by
+// the copy engine), B = the 32 dOut rows.  Every CTA keeps ONE accumulator set for its whole row
+// share ([4 Kp x c_out] fp32 in tensor memory) and flushes it once.  Roles as in k_wgrad_pairs:
+// 3 producer groups of 4 warps (a group owns every third stage; lane = row, so the table reads
+// are coalesced; the indices of the next stage are loaded while this stage's copies fly),
+// 4 epilogue warps, 1 MMA warp.  Replaces k_conv_small_cin_wgrad (1.0 ms on 3 -> 32, K = 125,
+// 800k rows) on the bf16/fp16 path.
+// =====================================================================================
+constexpr int kWsRows = 32;
+constexpr uint32_t kWsBlk = kWsRows * 128u;
+constexpr int kWsGroups = 3;
+constexpr int kWsProducerWarps = 4 * kWsGroups;
+constexpr int kWsThreads = (kWsProducerWarps + kEpilogueWarps + 1) * 32;
+constexpr int kWsMaxOffsetsPerThread = 32;     // Kp / 4 <= 32  <=>  K <= 128
+
+struct WsParams {
+  const void *in4;       // [n_in, 4]
+  const void *gout;      // [n_rows, c_out]
+  const int32_t *nbr;    // [K, n_rows]
+  float *dWv;            // [4 Kp, c_out], zero-filled
+  uint32_t K, Kp, n_rows, c_out;
+  uint32_t mt, n_stage, a_bytes, stage_bytes, n_stages_total;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kWsThreads, 1) k_wgrad_stem(const WsParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t s0 = smem_u32(smem);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + p.n_stage * p.stage_bytes);
+  const uint32_t bar0 = smem_u32(bars);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * kMaxStages + 4);
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t n_my = p.n_stages_total > blockIdx.x
+                            ? (p.n_stages_total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (threadIdx.x == 0) {
+    for (uint32_t i = 0; i < p.n_stage; ++i) {
+      mbar_init(bar_fullA(bar0, i), 4 * 32);
+      mbar_init(bar_emptyA(bar0, i), 1);
+    }
+    mbar_init(bar_tfull(bar0, 0), 1);
+    mbar_fence_init();
+  }
+  if (warp == kWsProducerWarps + kEpilogueWarps) {
+    tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kWsProducerWarps) {
+    // =============================== PRODUCERS ======================================
+    const uint32_t grp = warp >> 2, qw = warp & 3u;
+    const T *in4 = reinterpret_cast<const T *>(p.in4);
+    const T *gout = reinterpret_cast<const T *>(p.gout);
+    const uint32_t n_off = p.Kp / 4;               // offsets per thread: k = qw + 4 i
+    const uint32_t cprB = p.c_out / 8;             // 16-byte chunks per dOut row
+    int32_t idx[kWsMaxOffsetsPerThread];
+    auto load_idx = [&](uint32_t stage) {
+      const uint32_t row = stage * kWsRows + lane;
+#pragma unroll
+      for (int i = 0; i < kWsMaxOffsetsPerThread; ++i) {
+        const uint32_t k = qw + 4u * i;
+        idx[i] = ((uint32_t)i < n_off && k < p.K && row < p.n_rows)
+                     ? __ldg(p.nbr + (size_t)k * p.n_rows + row) : -1;
+      }
+    };
+    uint32_t slot = grp, ph = 0;
+    if (grp < n_my) load_idx(blockIdx.x + grp * gridDim.x);
+    for (uint32_t i = grp; i < n_my; i += kWsGroups) {
+      const uint32_t stage = blockIdx.x + i * gridDim.x;
+      if (lane == 0) mbar_wait_park(bar_emptyA(bar0, slot), ph ^ 1u);
+      __syncwarp();
+      const uint32_t base = s0 + slot * p.stage_bytes;
+      const uint32_t rowoff = lane * 128u, rx = lane & 7u;
+#pragma unroll
+      for (int j = 0; j < kWsMaxOffsetsPerThread; ++j) {
+        if ((uint32_t)j < n_off) {
+          const uint32_t k = qw + 4u * j;
+          const int32_t v = idx[j];
+          const uint32_t dst = base + (k >> 4) * kWsBlk + rowoff + ((((k & 15u) >> 1) ^ rx) << 4) + (k & 1u) * 8u;
+          cp_async8(dst, in4 + (v < 0 ? 0 : (size_t)v * 4), v < 0 ? 0u : 8u);
+        }
+      }
+      // the 32 dOut rows of the stage: chunk c of row r, (r, c) dealt over the group's threads
+      for (uint32_t c = qw * 32 + lane; c < kWsRows * cprB; c += 128) {
+        const uint32_t r = c / cprB, ch = c - r * cprB;
+        const uint32_t row = stage * kWsRows + r;
+        const uint32_t dst = base + p.a_bytes + (ch >> 3) * kWsBlk + r * 128u + (((ch & 7u) ^ (r & 7u)) << 4);
+        const bool ok = row < p.n_rows;
+        cp_async16(dst, gout + (ok ? (size_t)row * p.c_out + ch * 8 : 0), ok ? 16u : 0u);
+      }
+      cp_async_mbar_arrive(bar_fullA(bar0, slot));
+      slot += kWsGroups;
+      if (slot >= p.n_stage) { slot -= p.n_stage; ph ^= 1u; }
+      if (i + kWsGroups < n_my) load_idx(blockIdx.x + (i + kWsGroups) * gridDim.x);
+    }
+    cp_async_wait<0>();
+  } else if (warp < kWsProducerWarps + kEpilogueWarps) {
+    // =============================== EPILOGUE: one flush ================================
+    const uint32_t q = warp & 3u;
+    if (n_my > 0) {
+      mbar_wait_park(bar_tfull(bar0, 0), 0);
+      tc_fence_after();
+      for (uint32_t t = 0; t < p.mt; ++t) {
+        const uint32_t v = t * 128 + q * 32 + lane;              // virtual channel = 4 k + c
+        float *dst_row = p.dWv + (size_t)v * p.c_out;
+        for (uint32_t c = 0; c < p.c_out; c += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem_base + ((q * 32u) << 16) + t * p.c_out + c, r);
+          tmem_ld_wait();
+          if (v < 4 * p.Kp) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst_row + c + i),
+                           "f"(__uint_as_float(r[i])), "f"(__uint_as_float(r[i + 1])),
+                           "f"(__uint_as_float(r[i + 2])), "f"(__uint_as_float(r[i + 3]))
+                           : "memory");
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  } else {
+    // =============================== MMA ISSUER =====================================
+    const uint32_t idesc = umma_idesc_f16(Fmt<T>::v, kTileM, p.c_out, 1, 1);
+    uint32_t slot = 0, ph = 0;
+    for (uint32_t i = 0; i < n_my; ++i) {
+      mbar_wait_park(bar_fullA(bar0, slot), ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t abase = s0 + slot * p.stage_bytes, bbase = abase + p.a_bytes;
+        for (uint32_t t = 0; t < p.mt; ++t) {
+#pragma unroll
+          for (int j = 0; j < kWsRows / 16; ++j) {
+            const uint64_t da = umma_desc(abase + t * 2 * kWsBlk + j * 2048, kWsBlk, 1024, 2);
+            const uint64_t db = umma_desc(bbase + j * 2048, kWsBlk, 1024, 2);
+            umma_f16(tmem_base + t * p.c_out, da, db, idesc, (i != 0 || j != 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(bar_emptyA(bar0, slot));
+      }
+      __syncwarp();
+      if (++slot == p.n_stage) { slot = 0; ph ^= 1u; }
+    }
+    if (n_my > 0 && elect_one()) umma_commit(bar_tfull(bar0, 0));
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWsProducerWarps + kEpilogueWarps) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+bool conv_stem_wgrad_tc_supported(int dtype, uint32_t K, uint32_t c_out) {
+  if (dtype != MEB200_BF16 && dtype != MEB200_F16) return false;
+  const uint32_t Kp = (K + 15) / 16 * 16;
+  const uint32_t mt = (4 * Kp + 127) / 128;
+  return K >= 1 && Kp / 4 <= (uint32_t)kWsMaxOffsetsPerThread && c_out % 16 == 0 && c_out >= 16 &&
+         c_out <= 256 && mt * c_out <= kTmemCols && encode_tiled_fn() != nullptr;
+}
+
+// dWv: [4 * 16 ceil(K / 16), c_out] fp32 (virtual channel 4 k + c), zero-filled here.
+int conv_stem_wgrad_tc(const void *in4, const void *grad_out, int dtype, uint32_t K,
+                       uint32_t c_out, const int32_t *nbr, uint32_t n_rows, float *dWv,
+                       cudaStream_t stream) {
+  MEB_CHECK_ARG(conv_stem_wgrad_tc_supported(dtype, K, c_out), "stem wgrad: K=%u c_out=%u", K, c_out);
+  WsParams p{};
+  p.in4 = in4; p.gout = grad_out; p.nbr = nbr; p.dWv = dWv;
+  p.K = K; p.Kp = (K + 15) / 16 * 16; p.n_rows = n_rows; p.c_out = c_out;
+  MEB_CUDA(cudaMemsetAsync(dWv, 0, (size_t)4 * p.Kp * c_out * sizeof(float), stream));
+  if (n_rows == 0) return MEB200_OK;
+  p.mt = (4 * p.Kp + 127) / 128;
+  p.a_bytes = (4 * p.Kp / 64) * kWsBlk;
+  if (p.a_bytes < 2 * kWsBlk) p.a_bytes = 2 * kWsBlk;      // an m-tile always reads two blocks
+  p.stage_bytes = p.a_bytes + ((c_out + 63) / 64) * kWsBlk;
+  const uint32_t budget = tc::kSmemBudget - 1024 - tc::kBarBytes - 64;
+  p.n_stage = budget / p.stage_bytes;
+  if (p.n_stage > 12) p.n_stage = 12;
+  p.n_stage = p.n_stage / kWsGroups * kWsGroups;
+  MEB_CHECK_ARG(p.n_stage >= (uint32_t)kWsGroups, "stem wgrad: stage of %u bytes does not fit", p.stage_bytes);
+  p.n_stages_total = cdiv(n_rows, (uint32_t)kWsRows);
+  const size_t smem_bytes = 1024 + (size_t)p.n_stage * p.stage_bytes + tc::kBarBytes + 64;
+  const unsigned grid = p.n_stages_total < (uint32_t)num_sms() ? p.n_stages_total : (unsigned)num_sms();
+  if (dtype == MEB200_BF16) {
+    MEB_BIG_SMEM((k_wgrad_stem<__nv_bfloat16>));
+    k_wgrad_stem<__nv_bfloat16><<<grid, kWsThreads, smem_bytes, stream>>>(p);
+  } else {
+    MEB_BIG_SMEM((k_wgrad_stem<__half>));
+    k_wgrad_stem<__half><<<grid, kWsThreads, smem_bytes, stream>>>(p);
+  }
   count_tc_launch();
   MEB_LAUNCH_OK();
   return MEB200_OK;

@@ -32,4 +32,16 @@ int conv_wgrad_pairs(const void *in, const void *grad_out, int dtype, uint32_t c
                      const int32_t *seg_start, uint32_t n_chunks, uint32_t n_out,
                      float *grad_weight, cudaStream_t stream);
 
+// ---- network stem: rows of <= 4 channels, padded to 4 (8 bytes) ------------------------------
+// The layer is run as a K = 1 convolution over 4 * 16 ceil(K / 16) VIRTUAL channels (offset k,
+// channel c) -> 4 k + c: forward through k_conv_ts (STEM producers), wgrad through k_wgrad_stem.
+bool conv_stem_tc_supported(int dtype, uint32_t K, uint32_t c_cols);
+int conv_stem_forward_tc(const void *A4, int dtype, uint32_t K, const void *Wv, uint32_t c_cols,
+                         const int32_t *nbr, uint32_t n_rows, void *out, int out_dtype,
+                         cudaStream_t stream);
+bool conv_stem_wgrad_tc_supported(int dtype, uint32_t K, uint32_t c_out);
+int conv_stem_wgrad_tc(const void *in4, const void *grad_out, int dtype, uint32_t K,
+                       uint32_t c_out, const int32_t *nbr, uint32_t n_rows, float *dWv,
+                       cudaStream_t stream);
+
 }  // namespace meb200

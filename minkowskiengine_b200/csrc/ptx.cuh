@@ -71,6 +71,11 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const void *src, uint32_
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
                : "memory");
 }
+// 8-byte variant (4-channel rows of a network stem); src_bytes = 0 zero-fills
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
+               : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() {
   asm volatile("cp.async.commit_group;" ::: "memory");
 }

@@ -112,7 +112,9 @@ inline uint32_t ts_tail_bytes(uint32_t g) {
 }
 // One candidate: nb 32-channel blocks per stage, g offsets per stage.
 inline TaCfg ta_try(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, uint32_t nb, uint32_t g,
-                    int force_R, int force_acc) {
+                    int force_R, int force_acc, uint32_t gi = 0) {
+  // gi: offsets whose neighbour indices one stage needs (index-ring rows); g unless stated
+  if (gi == 0) gi = g;
   TaCfg c{};
   c.g = g;
   c.bk = (nb % 2 == 0 && (g == 1 || (32 * nb / g) % 64 == 0)) ? 64 : 32;
@@ -140,7 +142,8 @@ inline TaCfg ta_try(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, uint32_t n
   c.b_sub_bytes = ((c_cols * (uint32_t)c.bk * 2 + 1023) / 1024) * 1024;
   c.b_stage_bytes = (32 * nb / (uint32_t)c.bk) * c.b_sub_bytes;
   // weights ring of 3 (2 if tight) stages, the rest of shared memory goes to the row rings
-  const uint32_t tail_bytes = ts_tail_bytes(g);
+  const uint32_t tail_bytes = ts_tail_bytes(gi);
+  if (tail_bytes + kBarBytes + 1024 >= kSmemBudget) return c;
   const uint32_t budget = kSmemBudget - kBarBytes - 1024 - tail_bytes;
   const uint32_t per_slot = kTsProducerWarpsCfg * nb * 512;     // bytes one more row slot costs
   for (uint32_t nB = 3; nB >= 2; --nB) {
@@ -169,6 +172,18 @@ inline TaCfg ta_config(uint32_t c_red, uint32_t c_cols, uint32_t n_rows, int for
     if (c.nb != 0) return c;
   }
   return none;   // the caller falls back to k_conv_rs
+}
+
+// Network stem (rows of <= 4 channels, padded to 4 = 8 bytes): k_conv_ts<NB = 2, G = 0> treats the
+// layer as a K = 1 convolution over 4 * 16 * ceil(K / 16) virtual channels, 16 offsets per stage.
+constexpr uint32_t kStemNb = 2, kStemOffsetsPerStage = 8 * kStemNb;
+inline uint32_t stem_virtual_channels(uint32_t K) {
+  return cdiv_u(K, kStemOffsetsPerStage) * kStemOffsetsPerStage * 4;
+}
+inline TaCfg ta_stem_config(uint32_t K, uint32_t c_cols, uint32_t n_rows) {
+  TaCfg none{};
+  if (K == 0 || c_cols % 16 != 0 || c_cols < 16 || c_cols > 256) return none;
+  return ta_try(stem_virtual_channels(K), c_cols, n_rows, kStemNb, 1, 0, 0, kStemOffsetsPerStage);
 }
 
 // ---- wgrad: dW[K, c_in, c_out] reduced over n_out rows --------------------------------------
@@ -231,6 +246,7 @@ inline WgCfg wgrad_config(uint32_t c_in, uint32_t c_out, uint32_t K, uint32_t n_
 struct WpCfg {
   uint32_t mt_cta;        // 128-channel m-tiles per CTA (1 or 2); 0 = unsupported
   uint32_t n_mtgroups, n_splits, blkB, n_stage, a_bytes, stage_bytes, acc_sets, smem_bytes;
+  uint32_t rw;            // pairs per stage: 64, or 32 when fewer than 6 stages of 64 would fit
 };
 inline WpCfg wgrad_pairs_config(uint32_t c_in, uint32_t c_out, uint32_t K, uint32_t n_chunks,
                                 uint32_t n_out, uint32_t n_sms) {
@@ -243,11 +259,19 @@ inline WpCfg wgrad_pairs_config(uint32_t c_in, uint32_t c_out, uint32_t K, uint3
   if (mt == 0) return c;
   c.n_mtgroups = cdiv_u(mt_total, mt);
   c.blkB = cdiv_u(c_out, 64);
-  c.a_bytes = mt * 2 * kBlkBytes;
-  c.stage_bytes = c.a_bytes + c.blkB * kBlkBytes;
   c.acc_sets = 2 * mt * c_out <= kTmemCols ? 2 : 1;
   const uint32_t tail = kBarBytes + 12 * 4 * 32 * 4 + (K * n_chunks + 1) * 4 + 64;   // barriers, index rings (12 warps x 4 stages x 32 indices), segment table
-  c.n_stage = (kSmemBudget - 1024 - tail) / c.stage_bytes;
+  // 64 pairs per stage; 32 when that leaves fewer than two stages per producer group (a group
+  // with one stage cannot overlap its copies with the landing and the MMA of the previous one)
+  c.rw = 64;
+  for (;;) {
+    const uint32_t blk = c.rw * 128;
+    c.a_bytes = mt * 2 * blk;
+    c.stage_bytes = c.a_bytes + c.blkB * blk;
+    c.n_stage = (kSmemBudget - 1024 - tail) / c.stage_bytes;
+    if (c.n_stage >= 6 || c.rw == 32) break;
+    c.rw = 32;
+  }
   if (c.n_stage > 12) c.n_stage = 12;
   c.n_stage = c.n_stage / 3 * 3;       // a multiple of the 3 producer groups (slot ownership)
   if (c.n_stage < 3) return c;

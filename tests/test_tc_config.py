@@ -70,7 +70,9 @@ int main() {
               w.n_stage >= 3 && w.n_stage % 3 == 0 && w.smem_bytes <= 227 * 1024 &&
               w.n_mtgroups * w.mt_cta * 128 >= ci && w.n_splits >= 1 &&
               w.n_splits * w.n_mtgroups <= 2 * 148 + w.n_mtgroups &&
-              w.stage_bytes == w.a_bytes + w.blkB * kBlkBytes && w.blkB * 64 >= co;
+              (w.rw == 64 || w.rw == 32) && w.a_bytes == w.mt_cta * 2 * w.rw * 128 &&
+              w.stage_bytes == w.a_bytes + w.blkB * w.rw * 128 && w.blkB * 64 >= co &&
+              (w.rw == 64 ? w.n_stage >= 6 : true);
     if (!ok) { printf("WP BAD ci=%u co=%u K=%u rows=%u\n", ci, co, K, rows); ++bad; }
     printf("wp %u %u %u %u : mt=%u groups=%u splits=%u stages=%u acc=%u smem=%u\n", ci, co, K, rows, w.mt_cta, w.n_mtgroups, w.n_splits, w.n_stage, w.acc_sets, w.smem_bytes);
   }
