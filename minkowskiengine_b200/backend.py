@@ -164,6 +164,8 @@ class _PendingLevel:
 # kernel strides requested along the stride chain below the first inserted map of the previous
 # coordinate manager, per coordinate width: the prediction for the next manager's pyramid
 _PYRAMID_HINT = {}
+# ... and the kernel maps it was asked for, in order (keys + kernel geometry, no tensors)
+_KMAP_HINT = {}
 _PREFETCH = os.environ.get("MEB200_MAP_PREFETCH", "1") not in ("", "0")
 
 
@@ -288,6 +290,10 @@ class CoordinateMapManagerGPU_c10:
         self._pending = {}      # out key -> _PendingLevel (enqueued, size not yet read)
         self._chain_tip = None  # last map of the stride chain below the first inserted map
         self._chain = []        # kernel strides requested along that chain
+        self._km_seen = set()   # kernel-map cache keys the caller has asked for
+        self._km_requests = []  # ... in order: the prediction for the next manager
+        self._replaying = False
+        self._hint_ncols = None
         _lib.load()             # fail at construction if the native library is missing
 
     # -- keys ------------------------------------------------------------------------
@@ -345,7 +351,9 @@ class CoordinateMapManagerGPU_c10:
         self._maps[key] = cmap
         if first:
             self._chain_tip = key
+            self._hint_ncols = cmap.ncols
             self._prefetch_pyramid(key, cmap)
+            self._prefetch_kernel_maps(cmap.ncols)
         if cmap.size == coordinates.size(0):
             # no duplicates: the reference GPU path returns an empty inverse map here
             # (coordinate_map_manager.cu:94-112) and Python substitutes arange
@@ -359,12 +367,12 @@ class CoordinateMapManagerGPU_c10:
         _assert(len(kernel_stride) == len(in_key[0]), "stride size mismatch.")
         out_ts = tuple(t * int(s) for t, s in zip(in_key[0], kernel_stride))
         out_key = (out_ts, string_id if string_id else in_key[1])
-        if out_key in self._maps:
-            return out_key, False
-        if in_key == self._chain_tip:       # remember the pyramid for the next manager
+        if in_key == self._chain_tip and not self._replaying:   # remember the pyramid for the next manager
             self._chain_tip = out_key
             self._chain.append(tuple(int(s) for s in kernel_stride))
             _PYRAMID_HINT[len(in_key[0]) + 1] = tuple(self._chain)
+        if out_key in self._maps:
+            return out_key, False
         if self._take_pending(in_key, out_key):
             return out_key, True
         in_map = self._maps[in_key]
@@ -428,6 +436,31 @@ class CoordinateMapManagerGPU_c10:
             lv.event.record()
             self._pending[out_key] = lv
             parent_key, parent_coords, parent_count = out_key, lv.uniq, lv.count_dev
+
+    # The kernel maps are functions of the coordinate maps alone as well: the ones the previous
+    # manager was asked for (_KMAP_HINT) are built right here, before the first layer runs.  The
+    # GPU gets ~1.5 ms of table probing to chew on while the host enqueues the layers, instead of
+    # meeting each map where the forward pass first needs it with nothing else queued (the coarse
+    # levels of a U-Net are launch bound: 10-30 us kernels against ~50 us of host work per layer).
+    def _materialize(self, key):
+        if key in self._maps:
+            return True
+        lv = self._pending.get(key)
+        return (lv is not None and self._materialize(lv.parent_key)
+                and self._take_pending(lv.parent_key, key))
+
+    def _prefetch_kernel_maps(self, ncols):
+        hint = _KMAP_HINT.get(ncols) if _PREFETCH else None
+        if not hint:
+            return
+        self._replaying = True
+        try:
+            for ik, ok, ksize, kstride, kdil, region, is_transpose, is_pool in hint:
+                if self._materialize(ik) and self._materialize(ok):
+                    self._kernel_map(ik, ok, ksize, kstride, kdil, region, None, is_transpose,
+                                     is_pool)
+        finally:
+            self._replaying = False
 
     def _take_pending(self, in_key, out_key):
         """Turns the enqueued level `out_key` into a map if it was built from `in_key`."""
@@ -514,6 +547,11 @@ class CoordinateMapManagerGPU_c10:
         kdil = tuple(int(v) for v in kernel_dilation)
         _assert(len(ksize) == len(kstride) == len(kdil), "kernel size mismatch")
         cache_key = (ik, ok, ksize, kstride, kdil, region_type, bool(is_transpose), bool(is_pool))
+        if not self._replaying and cache_key not in self._km_seen:
+            self._km_seen.add(cache_key)
+            if region_type != RegionType.CUSTOM and self._hint_ncols is not None:
+                self._km_requests.append(cache_key)
+                _KMAP_HINT[self._hint_ncols] = tuple(self._km_requests)
         km = self._kernel_maps.get(cache_key)
         if km is not None:
             return km
@@ -761,10 +799,12 @@ def _conv_forward_impl(in_feat, kernel, km, out_dtype=None):
         _assert(K == km.K, "kernel volume", K, "does not match the kernel map", km.K)
         out = torch.empty((km.n_out, c_out), dtype=out_dtype or in_feat.dtype,
                           device=in_feat.device)
+        # (named, so that they outlive the argument list: a temporary freed before the call can
+        # be handed by the allocator to the next temporary and overwritten before the kernel runs)
+        in4, w_v = _pad4(in_feat), _stem_weights(kernel, in_feat.dtype)
         rc = lib.meb200_conv_stem_forward(
-            _lib.ptr(_pad4(in_feat)), code, K, _lib.ptr(_stem_weights(kernel, in_feat.dtype)), c_out,
-            _lib.ptr(km.out_nbr), km.n_out, _lib.ptr(out), _lib.dtype_code(out.dtype),
-            _lib.current_stream())
+            _lib.ptr(in4), code, K, _lib.ptr(w_v), c_out, _lib.ptr(km.out_nbr), km.n_out,
+            _lib.ptr(out), _lib.dtype_code(out.dtype), _lib.current_stream())
         if rc != _ERR_UNSUPPORTED:
             _lib.check(rc)
             return out
@@ -831,8 +871,9 @@ def _conv_backward_impl(in_feat, grad_out, kernel, km, need_in=True, need_w=True
         # the stem's input needs no gradient (it is the network input): wgrad alone
         V = int(lib.meb200_conv_stem_virtual_channels(K))
         gwv = torch.empty((V // 4, 4, c_out), dtype=torch.float32, device=in_feat.device)
+        in4 = _pad4(in_feat)
         rc = lib.meb200_conv_stem_wgrad(
-            _lib.ptr(_pad4(in_feat)), _lib.ptr(grad_out), code, K, c_out, _lib.ptr(km.out_nbr),
+            _lib.ptr(in4), _lib.ptr(grad_out), code, K, c_out, _lib.ptr(km.out_nbr),
             n_out, _lib.ptr(gwv), _lib.current_stream())
         if rc != _ERR_UNSUPPORTED:
             _lib.check(rc)
