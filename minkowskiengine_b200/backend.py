@@ -367,7 +367,8 @@ class CoordinateMapManagerGPU_c10:
         _assert(len(kernel_stride) == len(in_key[0]), "stride size mismatch.")
         out_ts = tuple(t * int(s) for t, s in zip(in_key[0], kernel_stride))
         out_key = (out_ts, string_id if string_id else in_key[1])
-        if in_key == self._chain_tip and not self._replaying:   # remember the pyramid for the next manager
+        if in_key == self._chain_tip and out_key != in_key and not self._replaying:
+            # remember the pyramid for the next manager
             self._chain_tip = out_key
             self._chain.append(tuple(int(s) for s in kernel_stride))
             _PYRAMID_HINT[len(in_key[0]) + 1] = tuple(self._chain)

@@ -25,6 +25,7 @@ def _pyramid(ME, coords, strides):
     cm = x.coordinate_manager
     keys = [x.coordinate_map_key]
     for s in strides:
+        assert cm.stride(keys[-1], [1] * len(s)) == keys[-1]      # stride-1 layers in between
         keys.append(cm.stride(keys[-1], s))
     return x, cm, keys
 
