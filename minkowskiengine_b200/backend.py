@@ -50,16 +50,18 @@ class CoordinateMapKey:
     """(tensor_stride, string_id) handle of a coordinate map
     (reference: src/coordinate_map_key.hpp:44-157, pybind/extern.hpp:744-763)."""
 
-    __slots__ = ("_coordinate_size", "_tensor_stride", "_string_id", "_set")
+    __slots__ = ("_coordinate_size", "_tensor_stride", "_string_id", "_set", "_tup")
 
     def __init__(self, *args):
         if len(args) == 1 and isinstance(args[0], int):
             self._coordinate_size = args[0]
             self._tensor_stride, self._string_id, self._set = None, "", False
+            self._tup = None
         elif len(args) == 2:
             ts = [int(v) for v in args[0]]
             self._coordinate_size = len(ts) + 1
             self._tensor_stride, self._string_id, self._set = ts, str(args[1]), True
+            self._tup = (tuple(ts), self._string_id)     # hashable form, built once
         else:
             raise TypeError("CoordinateMapKey(coordinate_size:int) or "
                             "CoordinateMapKey(tensor_stride:list, string_id:str)")
@@ -86,13 +88,14 @@ class CoordinateMapKey:
         _assert(len(ts) + 1 == self._coordinate_size, "Invalid tensor stride size", ts,
                 "for coordinate size", self._coordinate_size)
         self._tensor_stride, self._string_id, self._set = ts, str(sid), True
+        self._tup = (tuple(ts), self._string_id)
 
     def get_tensor_stride(self):
         _assert(self._set, "CoordinateMapKey: Key Not Set")
         return list(self._tensor_stride)
 
     def _tuple(self):
-        return (tuple(self._tensor_stride), self._string_id)
+        return self._tup
 
     def __eq__(self, other):
         if not isinstance(other, CoordinateMapKey):
@@ -166,6 +169,7 @@ class _PendingLevel:
 _PYRAMID_HINT = {}
 # ... and the kernel maps it was asked for, in order (keys + kernel geometry, no tensors)
 _KMAP_HINT = {}
+_PAIR_HINT = set()      # kernel-map cache keys whose pair lists (wgrad) were asked for
 _PREFETCH = os.environ.get("MEB200_MAP_PREFETCH", "1") not in ("", "0")
 
 
@@ -177,7 +181,8 @@ class _KernelMap:
     Replaces gpu_kernel_map's three flat arrays + host offset table (src/kernel_map.cuh:48-429);
     `swapped()` is the reference's swap_in_out (kernel_map.cuh:191-241)."""
 
-    __slots__ = ("out_nbr", "in_nbr", "stride_pairs", "_n_pairs", "_pairs", "_pair_src")
+    __slots__ = ("out_nbr", "in_nbr", "stride_pairs", "_n_pairs", "_pairs", "_pair_src",
+                 "_hint_key")
     PAIR_STAGE = 64   # pairs per pipeline stage of the wgrad kernel (k_wgrad_pairs)
     # table rows per chunk of the pair lists (multiple of 2048)
     PAIR_CHUNK_ROWS = int(os.environ.get("MEB200_PAIR_CHUNK_ROWS", "65536"))
@@ -188,6 +193,7 @@ class _KernelMap:
         self._n_pairs = None
         self._pairs = None      # (pairs_in, pairs_out, seg_start) once built
         self._pair_src = None   # the map this one is the swapped view of
+        self._hint_key = None   # the manager's cache key (prediction of the next manager's needs)
 
     def pair_lists(self):
         """(pairs_in, pairs_out, seg_start, n_chunks): compacted (input row, output row) lists in
@@ -196,6 +202,8 @@ class _KernelMap:
         that a consumer keeps one chunk's feature rows L2-resident across the offsets.  Built on
         first use; a swapped view shares its source's lists with the two sides exchanged."""
         if self._pairs is None:
+            if self._hint_key is not None:
+                _PAIR_HINT.add(self._hint_key)
             if self._pair_src is not None:
                 pin, pout, seg, nch = self._pair_src.pair_lists()
                 self._pairs = (pout, pin, seg, nch)
@@ -300,8 +308,8 @@ class CoordinateMapManagerGPU_c10:
     @staticmethod
     def _k(key):
         if isinstance(key, CoordinateMapKey):
-            ts, sid = key.get_key()
-            return (tuple(ts), sid)
+            _assert(key._set, "CoordinateMapKey: Key Not Set")
+            return key._tup
         return (tuple(key[0]), key[1])
 
     def exists(self, key):
@@ -458,8 +466,10 @@ class CoordinateMapManagerGPU_c10:
         try:
             for ik, ok, ksize, kstride, kdil, region, is_transpose, is_pool in hint:
                 if self._materialize(ik) and self._materialize(ok):
-                    self._kernel_map(ik, ok, ksize, kstride, kdil, region, None, is_transpose,
-                                     is_pool)
+                    km = self._kernel_map(ik, ok, ksize, kstride, kdil, region, None,
+                                          is_transpose, is_pool)
+                    if (ik, ok, ksize, kstride, kdil, region, is_transpose, is_pool) in _PAIR_HINT:
+                        km.pair_lists()          # the backward pass will want them
         finally:
             self._replaying = False
 
@@ -591,6 +601,7 @@ class CoordinateMapManagerGPU_c10:
                     a, b = self._probe(in_map, out_map, offs)
                     fwd = _KernelMap(a, b)
             km = fwd.swapped()
+        km._hint_key = cache_key
         self._kernel_maps[cache_key] = km
         return km
 

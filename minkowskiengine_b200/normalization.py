@@ -101,9 +101,23 @@ def _workspace(dev, stream):
     return ws
 
 
+_NULL_GUARD = contextlib.nullcontext()
+
+
 def _device_guard(dev):
-    """Native launches go to the CURRENT device's stream: make the tensor's device current."""
-    return torch.cuda.device(dev) if dev.type == "cuda" else contextlib.nullcontext()
+    """Native launches go to the CURRENT device's stream: make the tensor's device current
+    (nothing to do — and nothing spent — when it already is, the usual case)."""
+    if dev.type != "cuda" or dev.index == torch.cuda.current_device():
+        return _NULL_GUARD
+    return torch.cuda.device(dev)
+
+
+def _f32(t):
+    """fp32 contiguous view of a parameter without a copy when it already is one."""
+    if t is None:
+        return None
+    t = t.detach()
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
 
 
 class _BatchNormFunction(torch.autograd.Function):
@@ -120,8 +134,7 @@ class _BatchNormFunction(torch.autograd.Function):
         dev = x.device
         with _device_guard(dev):
             stream = _lib.current_stream()
-            w32 = None if weight is None else weight.detach().float().contiguous()
-            b32 = None if bias is None else bias.detach().float().contiguous()
+            w32, b32 = _f32(weight), _f32(bias)
             d_count = None
             if residual is not None:
                 residual = residual.contiguous()
