@@ -312,27 +312,34 @@ int meb200_bn_backward_reduce_to(const void *dy, const void *x, const void *y_ma
 
 /* ---- synchronised batch norm: statistics exchange over NVLink peer memory ----------------
  * Replaces the per-layer NCCL all-reduce of torch.nn.SyncBatchNorm (reference:
- * MinkowskiEngine/MinkowskiNormalization.py:101-192, examples/multigpu_ddp.py:91-95) by one
- * single-CTA kernel on the compute stream.  Every rank owns a buffer in symmetric memory with
- * the same layout: bytes [0, 1024) hold uint32 flags (flag[r] = last call whose slot of rank r
- * is complete), slots follow.  `peer_bases_dev` is a DEVICE array of `world` device pointers,
- * entry r = base of rank r's buffer as mapped into this process.  The kernel publishes `seq`
- * to every peer, waits for every peer's `seq`, then writes out[i] = sum over ranks (in rank
- * order: bitwise identical on all ranks) of the n doubles at `slot_offset_bytes`.  `seq` must
- * increase by one per call on every rank; consecutive calls must use different slots (a rank
- * can be at most one call ahead of its slowest peer).  Flags must be zero before the first call. */
-int meb200_peer_allreduce_f64(const void *peer_bases_dev, uint64_t slot_offset_bytes, uint32_t n,
-                              uint32_t seq, uint32_t rank, uint32_t world, double *out,
-                              void *stream);
-/* The forward exchange with meb200_bn_finalize fused in.  The slot holds this rank's
- * [sum x (C) | sum x^2 (C) | rows (1)] as meb200_bn_stats leaves the first 2C entries; the
- * kernel stores `local_rows` as entry 2C, exchanges as above and writes mean / 1/std (and the
- * momentum update of the running statistics, unbiased variance) from the totals, plus the
- * total row count (the backward pass divides by it). */
-int meb200_peer_bn_finalize(const void *peer_bases_dev, uint64_t slot_offset_bytes, uint32_t C,
-                            uint32_t seq, uint32_t rank, uint32_t world, double local_rows,
-                            float eps, float momentum, float *running_mean, float *running_var,
-                            float *mean, float *invstd, double *total_rows, void *stream);
+ * MinkowskiEngine/MinkowskiNormalization.py:101-192, examples/multigpu_ddp.py:91-95).  Every rank
+ * owns a buffer in symmetric memory with the same layout: bytes [0, 1024) hold uint32 flags
+ * (flag[r] = last call whose slot of rank r is complete), slots follow.  `peer_bases_dev` is a
+ * DEVICE array of `world` device pointers, entry r = base of rank r's buffer as mapped into this
+ * process.  An exchange publishes `seq` to every peer, waits for every peer's `seq`, then sums
+ * the ranks' slots in rank order (bitwise identical on all ranks).  `seq` must increase by one
+ * per call on every rank; consecutive calls must use different slots (a rank can be at most one
+ * call ahead of its slowest peer).  Flags must be zero before the first call.
+ * The exchange is run by the LAST CTA of the batch-norm reductions themselves (no separate
+ * launch): meb200_bn_forward_train / meb200_bn_backward_reduce_to of a synchronised layer.  The
+ * slot ([sum | sum2 | rows] forward, [sum dy | sum dy*xhat] backward) is filled by the kernel;
+ * mean / 1/std / running statistics come from the global totals and the global row count
+ * (returned in *total_rows, device); the parameter gradients stay LOCAL sums (DDP averages them),
+ * sums_out receives the global ones for meb200_bn_backward_apply_fused.  A rank with n = 0 rows
+ * still takes part. */
+int meb200_bn_forward_train_peer(const void *x, int dtype, uint32_t n, uint32_t C,
+                                 const float *weight, const float *bias, const void *residual,
+                                 int relu, float eps, float momentum, float *running_mean,
+                                 float *running_var, void *workspace, const void *peer_bases_dev,
+                                 uint64_t slot_offset_bytes, uint32_t seq, uint32_t rank,
+                                 uint32_t world, float *mean, float *invstd, double *total_rows,
+                                 void *y, void *stream);
+int meb200_bn_backward_reduce_peer(const void *dy, const void *x, const void *y_mask, int dtype,
+                                   uint32_t n, uint32_t C, const float *mean, const float *invstd,
+                                   void *workspace, const void *peer_bases_dev,
+                                   uint64_t slot_offset_bytes, uint32_t seq, uint32_t rank,
+                                   uint32_t world, double *sums_out, float *grad_weight,
+                                   float *grad_bias, void *stream);
 
 #ifdef __cplusplus
 }

@@ -75,9 +75,11 @@ PROTOTYPES = {
     "meb200_bn_backward_reduce_fused": (_i32, [_vp, _vp, _vp, _i32, _u32, _u32, _vp, _vp, _vp, _vp]),
     "meb200_bn_backward_apply_fused": (_i32, [_vp, _vp, _vp, _i32, _u32, _u32, _vp, _vp, _vp, _vp,
                                               C.c_double, _vp, _vp, _vp, _vp]),
-    "meb200_peer_allreduce_f64": (_i32, [_vp, C.c_uint64, _u32, _u32, _u32, _u32, _vp, _vp]),
-    "meb200_peer_bn_finalize": (_i32, [_vp, C.c_uint64, _u32, _u32, _u32, _u32, C.c_double,
-                                       C.c_float, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "meb200_bn_forward_train_peer": (_i32, [_vp, _i32, _u32, _u32, _vp, _vp, _vp, _i32, C.c_float,
+                                            C.c_float, _vp, _vp, _vp, _vp, C.c_uint64, _u32, _u32,
+                                            _u32, _vp, _vp, _vp, _vp, _vp]),
+    "meb200_bn_backward_reduce_peer": (_i32, [_vp, _vp, _vp, _i32, _u32, _u32, _vp, _vp, _vp, _vp,
+                                              C.c_uint64, _u32, _u32, _u32, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -11,6 +11,7 @@
 //   bwd_reduce : G1[c] = sum_r dy,  G2[c] = sum_r dy * (x - mean) * invstd   (fp64 [2C])
 //   bwd_apply  : dx = (dy - G1/n - xhat * G2/n) * invstd * w
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace meb200 {
 
@@ -103,6 +104,15 @@ struct BnTail {
   double count;
   float eps, momentum;
   float *grad_weight, *grad_bias;                       // MODE 1: fp32 parameter gradients, or NULL
+  // synchronised layers (peer_bases != NULL): the last CTA also runs the exchange of csrc/peer.cu
+  // — local totals into this rank's symmetric-memory slot, publish / wait, sum over the ranks —
+  // so a synchronised pass has the launches of a local one (MODE 0: finalize from the global
+  // totals and the global row count; MODE 1: global totals to totals_out, LOCAL ones to the
+  // parameter gradients, which DDP averages itself)
+  uint8_t *const *peer_bases;
+  uint64_t peer_slot_offset;
+  uint32_t peer_seq, peer_rank, peer_world;
+  double *total_rows_out;                               // MODE 0, synchronised: global row count
 };
 constexpr uint32_t kBnMaxC = 2048;
 constexpr size_t kBnWorkspaceBytes = 2 * kBnMaxC * sizeof(double) + 64;   // sums, then the ticket
@@ -181,14 +191,54 @@ k_bn_reduce(const T *__restrict__ a, const T *__restrict__ x, const T *__restric
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  double count = tail.count;
+  const bool synced = tail.peer_bases != nullptr;
+  if (synced) {
+    double *slot = reinterpret_cast<double *>(tail.peer_bases[tail.peer_rank] + tail.peer_slot_offset);
+    for (uint32_t c = threadIdx.x; c < C; c += kBnThreads) {
+      const double t1 = __ldcg(sums + c), t2 = __ldcg(sums + C + c);
+      sums[c] = 0.0;
+      sums[C + c] = 0.0;
+      slot[c] = t1;
+      slot[C + c] = t2;
+      if (MODE == 1) {
+        if (tail.grad_bias != nullptr) tail.grad_bias[c] = (float)t1;
+        if (tail.grad_weight != nullptr) tail.grad_weight[c] = (float)t2;
+      }
+    }
+    if (MODE == 0 && threadIdx.x == 0) slot[2 * C] = tail.count;
+    peer_publish_and_wait(tail.peer_bases, tail.peer_seq, tail.peer_rank, tail.peer_world);
+    if (MODE == 0) {
+      __shared__ double s_count;
+      if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (uint32_t r = 0; r < tail.peer_world; ++r)
+          t += ld_relaxed_sys_f64(reinterpret_cast<const double *>(tail.peer_bases[r] + tail.peer_slot_offset) + 2 * C);
+        s_count = t;
+        if (tail.total_rows_out != nullptr) *tail.total_rows_out = t;
+      }
+      __syncthreads();
+      count = s_count;
+    }
+  }
   for (uint32_t c = threadIdx.x; c < C; c += kBnThreads) {
-    const double t1 = __ldcg(sums + c), t2 = __ldcg(sums + C + c);
-    sums[c] = 0.0;
-    sums[C + c] = 0.0;
+    double t1, t2;
+    if (synced) {
+      t1 = 0.0; t2 = 0.0;
+      for (uint32_t r = 0; r < tail.peer_world; ++r) {       // rank order: identical on all ranks
+        const double *ps = reinterpret_cast<const double *>(tail.peer_bases[r] + tail.peer_slot_offset);
+        t1 += ld_relaxed_sys_f64(ps + c);
+        t2 += ld_relaxed_sys_f64(ps + C + c);
+      }
+    } else {
+      t1 = __ldcg(sums + c);
+      t2 = __ldcg(sums + C + c);
+      sums[c] = 0.0;
+      sums[C + c] = 0.0;
+    }
     if (tail.totals_out != nullptr) { tail.totals_out[c] = t1; tail.totals_out[C + c] = t2; }
     if (MODE == 0) {
       if (tail.mean != nullptr) {
-        const double count = tail.count;
         const double mu = t1 / count;
         double var = t2 / count - mu * mu;
         if (var < 0) var = 0;
@@ -201,7 +251,7 @@ k_bn_reduce(const T *__restrict__ a, const T *__restrict__ x, const T *__restric
           tail.running_var[c] = (float)((1.0 - mom) * tail.running_var[c] + mom * unbiased);
         }
       }
-    } else {
+    } else if (!synced) {
       if (tail.grad_bias != nullptr) tail.grad_bias[c] = (float)t1;
       if (tail.grad_weight != nullptr) tail.grad_weight[c] = (float)t2;
     }
@@ -379,6 +429,7 @@ static int bn_launch_reduce(int mode, const void *a, const void *x, const void *
                             double *sums, const BnTail &tail, cudaStream_t s) {
   unsigned grid;
   uint32_t rows = bn_rows_per_cta(n, C, &grid);
+  if (grid == 0) grid = 1;          // an empty rank still takes part in the exchange
   size_t smem = 2 * (size_t)C * sizeof(float);
 #define MEB_BN_RED(TT)                                                                            \
   do {                                                                                            \
@@ -458,6 +509,60 @@ int meb200_bn_backward_reduce_to(const void *dy, const void *x, const void *y_ma
   tail.totals_out = sums_out;
   tail.grad_weight = grad_weight;
   tail.grad_bias = grad_bias;
+  return bn_launch_reduce(1, dy, x, y_mask, dtype, n, C, mean, invstd, (double *)workspace, tail, s);
+}
+
+static void bn_tail_peer(BnTail &tail, const void *peer_bases_dev, uint64_t slot_offset,
+                         uint32_t seq, uint32_t rank, uint32_t world) {
+  tail.peer_bases = (uint8_t *const *)peer_bases_dev;
+  tail.peer_slot_offset = slot_offset;
+  tail.peer_seq = seq; tail.peer_rank = rank; tail.peer_world = world;
+}
+#define MEB_PEER_CHECK()                                                                          \
+  MEB_CHECK_ARG(peer_bases_dev != nullptr && world >= 1 && world <= 256 && rank < world &&        \
+                    slot_offset_bytes >= 1024 && slot_offset_bytes % 8 == 0 && seq != 0,         \
+                "peer exchange: bases / rank %u of %u / slot offset / sequence number",          \
+                (unsigned)rank, (unsigned)world)
+
+int meb200_bn_forward_train_peer(const void *x, int dtype, uint32_t n, uint32_t C,
+                                 const float *weight, const float *bias, const void *residual,
+                                 int relu, float eps, float momentum, float *running_mean,
+                                 float *running_var, void *workspace, const void *peer_bases_dev,
+                                 uint64_t slot_offset_bytes, uint32_t seq, uint32_t rank,
+                                 uint32_t world, float *mean, float *invstd, double *total_rows,
+                                 void *y, void *stream_) {
+  cudaStream_t s = (cudaStream_t)stream_;
+  MEB_BN_CHECK(C);
+  MEB_CHECK_ARG(workspace && mean && invstd && total_rows && (y || n == 0), "bn forward: null buffer");
+  MEB_PEER_CHECK();
+  BnTail tail{};
+  tail.ticket = bn_ticket(workspace);
+  tail.mean = mean; tail.invstd = invstd; tail.running_mean = running_mean; tail.running_var = running_var;
+  tail.count = (double)n; tail.eps = eps; tail.momentum = momentum;
+  tail.total_rows_out = total_rows;
+  bn_tail_peer(tail, peer_bases_dev, slot_offset_bytes, seq, rank, world);
+  int rc = bn_launch_reduce(0, x, nullptr, nullptr, dtype, n, C, nullptr, nullptr,
+                            (double *)workspace, tail, s);
+  if (rc != MEB200_OK || n == 0) return rc;
+  return meb200_bn_apply_fused(x, dtype, n, C, mean, invstd, weight, bias, residual, relu, y, stream_);
+}
+
+int meb200_bn_backward_reduce_peer(const void *dy, const void *x, const void *y_mask, int dtype,
+                                   uint32_t n, uint32_t C, const float *mean, const float *invstd,
+                                   void *workspace, const void *peer_bases_dev,
+                                   uint64_t slot_offset_bytes, uint32_t seq, uint32_t rank,
+                                   uint32_t world, double *sums_out, float *grad_weight,
+                                   float *grad_bias, void *stream_) {
+  cudaStream_t s = (cudaStream_t)stream_;
+  MEB_BN_CHECK(C);
+  MEB_CHECK_ARG(workspace && sums_out, "bn backward reduce: null buffer");
+  MEB_PEER_CHECK();
+  BnTail tail{};
+  tail.ticket = bn_ticket(workspace);
+  tail.totals_out = sums_out;
+  tail.grad_weight = grad_weight;
+  tail.grad_bias = grad_bias;
+  bn_tail_peer(tail, peer_bases_dev, slot_offset_bytes, seq, rank, world);
   return bn_launch_reduce(1, dy, x, y_mask, dtype, n, C, mean, invstd, (double *)workspace, tail, s);
 }
 

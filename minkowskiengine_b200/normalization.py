@@ -9,10 +9,10 @@ normalisation, unbiased for the running estimate, momentum update, per-channel a
 synchronised variant all-reduces (sum, sum of squares, count) forward and (sum dy, sum dy*xhat)
 backward over the process group, exactly the exchange torch.nn.SyncBatchNorm performs.
 `MEB200_TORCH_BN=1` routes everything through torch's own kernels (A/B comparisons).
-The exchange runs over NVLink peer memory by default (`meb200_peer_bn_finalize` forward,
-`meb200_peer_allreduce_f64` backward, csrc/peer.cu): one single-CTA kernel on the compute stream
-per exchange, no NCCL launch and no cross-stream hand-off; the forward one also does the work of
-`meb200_bn_finalize`, so a synchronised forward launches exactly what a local one does.
+The exchange runs over NVLink peer memory by default (csrc/peer.cuh), inside the LAST CTA of the
+reduction kernels themselves (`meb200_bn_forward_train_peer`, `meb200_bn_backward_reduce_peer`):
+no NCCL launch, no cross-stream hand-off, no extra kernel — a synchronised pass launches exactly
+what a local one does.
 `MEB200_SYNCBN_PEER=0` (or symmetric memory being unavailable) selects NCCL all-reduces.
 """
 import contextlib
@@ -30,7 +30,7 @@ _USE_PEER = os.environ.get("MEB200_SYNCBN_PEER", "1") not in ("", "0")
 
 class _PeerExchange:
     """Symmetric-memory buffer of one (process group, device) for the statistics exchange.
-    Layout (include/meb200.h, meb200_peer_allreduce_f64): 1024 bytes of flags, then SLOTS
+    Layout (include/meb200.h, csrc/peer.cuh): 1024 bytes of flags, then SLOTS
     rotating slots of SLOT_DOUBLES fp64 each; `seq` counts the exchanges (identical on all ranks
     because every rank runs the same layers in the same order)."""
     SLOTS = 4
@@ -66,25 +66,11 @@ class _PeerExchange:
         self.bases_dev = int(self.handle.buffer_ptrs_dev)   # device array of the ranks' bases
         self.seq = 0
 
-    def next_slot(self, n):
-        """-> (byte offset of the slot, fp64 view of its first n entries) for the next exchange."""
+    def next_slot_offset(self, n):
+        """Byte offset of the slot of the next exchange (advances the sequence number)."""
         assert n <= self.SLOT_DOUBLES
         self.seq = self.seq + 1 if self.seq < 0x7FFFFFFF else 1
-        off = 1024 + (self.seq % self.SLOTS) * self.SLOT_DOUBLES * 8
-        return off, self.buf[off:off + 8 * n].view(torch.float64)
-
-    def allreduce(self, off, n, out):
-        lib = _lib.load()
-        _lib.check(lib.meb200_peer_allreduce_f64(self.bases_dev, off, n, self.seq, self.rank,
-                                                 self.world, _lib.ptr(out), _lib.current_stream()))
-
-    def bn_finalize(self, off, C, rows, eps, momentum, running_mean, running_var, mean, invstd,
-                    total_rows):
-        lib = _lib.load()
-        _lib.check(lib.meb200_peer_bn_finalize(
-            self.bases_dev, off, C, self.seq, self.rank, self.world, float(rows), float(eps),
-            float(momentum), _lib.ptr(running_mean), _lib.ptr(running_var), _lib.ptr(mean),
-            _lib.ptr(invstd), _lib.ptr(total_rows), _lib.current_stream()))
+        return 1024 + (self.seq % self.SLOTS) * self.SLOT_DOUBLES * 8
 
 
 _WORKSPACES = {}
@@ -146,6 +132,9 @@ class _BatchNormFunction(torch.autograd.Function):
                 mean = torch.empty(C, dtype=torch.float32, device=dev)
                 invstd = torch.empty(C, dtype=torch.float32, device=dev)
                 ws = _workspace(dev, stream)
+            peer = None
+            if not use_running and group is not None and _USE_PEER:
+                peer = _PeerExchange.get(group, dev)
             if not use_running and group is None and n > 0:
                 # statistics + finalize in one launch, then the apply pass
                 _lib.check(lib.meb200_bn_forward_train(
@@ -153,28 +142,30 @@ class _BatchNormFunction(torch.autograd.Function):
                     1 if relu else 0, float(eps), float(momentum), _lib.ptr(running_mean),
                     _lib.ptr(running_var), _lib.ptr(ws), _lib.ptr(mean), _lib.ptr(invstd),
                     _lib.ptr(y), stream))
+            elif peer is not None:
+                # the same two launches: the last CTA of the reduction exchanges the statistics
+                # with the other ranks over NVLink peer memory before it finalizes
+                off = peer.next_slot_offset(2 * C + 1)
+                d_count = torch.empty(1, dtype=torch.float64, device=dev)
+                _lib.check(lib.meb200_bn_forward_train_peer(
+                    _lib.ptr(x), code, n, C, _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(residual),
+                    1 if relu else 0, float(eps), float(momentum), _lib.ptr(running_mean),
+                    _lib.ptr(running_var), _lib.ptr(ws), peer.bases_dev, off, peer.seq, peer.rank,
+                    peer.world, _lib.ptr(mean), _lib.ptr(invstd), _lib.ptr(d_count), _lib.ptr(y),
+                    stream))
             else:
                 if not use_running:
-                    peer = _PeerExchange.get(group, dev) if (group is not None and _USE_PEER) else None
-                    if peer is not None:
-                        off, sums = peer.next_slot(2 * C + 1)   # statistics land in symmetric memory
-                    else:
-                        sums = torch.empty(2 * C + 1, dtype=torch.float64, device=dev)
+                    sums = torch.empty(2 * C + 1, dtype=torch.float64, device=dev)
                     _lib.check(lib.meb200_bn_stats_to(_lib.ptr(x), code, n, C, _lib.ptr(ws),
                                                       _lib.ptr(sums), stream))
-                    if peer is not None:      # exchange + finalize in one single-CTA kernel
-                        d_count = torch.empty(1, dtype=torch.float64, device=dev)
-                        peer.bn_finalize(off, C, n, eps, momentum, running_mean, running_var,
-                                         mean, invstd, d_count)
-                    else:
-                        if group is not None:
-                            sums[2 * C] = float(n)
-                            torch.distributed.all_reduce(sums, group=group)
-                            d_count = sums[2 * C:]
-                        _lib.check(lib.meb200_bn_finalize(
-                            _lib.ptr(sums), float(max(n, 1)), _lib.ptr(d_count), C, float(eps),
-                            float(momentum), _lib.ptr(running_mean), _lib.ptr(running_var),
-                            _lib.ptr(mean), _lib.ptr(invstd), stream))
+                    if group is not None:
+                        sums[2 * C] = float(n)
+                        torch.distributed.all_reduce(sums, group=group)
+                        d_count = sums[2 * C:]
+                    _lib.check(lib.meb200_bn_finalize(
+                        _lib.ptr(sums), float(max(n, 1)), _lib.ptr(d_count), C, float(eps),
+                        float(momentum), _lib.ptr(running_mean), _lib.ptr(running_var),
+                        _lib.ptr(mean), _lib.ptr(invstd), stream))
                 _lib.check(lib.meb200_bn_apply_fused(
                     _lib.ptr(x), code, n, C, _lib.ptr(mean), _lib.ptr(invstd), _lib.ptr(w32),
                     _lib.ptr(b32), _lib.ptr(residual), 1 if relu else 0, _lib.ptr(y), stream))
@@ -201,30 +192,32 @@ class _BatchNormFunction(torch.autograd.Function):
             stream = _lib.current_stream()
             group = None if ctx.use_running else ctx.group
             peer = _PeerExchange.get(group, x.device) if (group is not None and _USE_PEER) else None
-            if peer is not None:
-                off, gs = peer.next_slot(2 * C)
-            else:
-                gs = torch.empty(2 * C, dtype=torch.float64, device=x.device)
+            gs = torch.empty(2 * C, dtype=torch.float64, device=x.device)
             grad_w = grad_b = None
             g32 = None
             if ctx.has_affine:   # local sums; DDP averages parameter gradients across ranks
                 g32 = torch.empty(2 * C, dtype=torch.float32, device=x.device)
                 grad_b, grad_w = g32[:C], g32[C:]
-            # one launch: the reduction, its totals into `gs` and the fp32 parameter gradients
-            _lib.check(lib.meb200_bn_backward_reduce_to(
-                _lib.ptr(dy), _lib.ptr(x), _lib.ptr(ymask), code, n, C, _lib.ptr(mean),
-                _lib.ptr(invstd), _lib.ptr(_workspace(x.device, stream)), _lib.ptr(gs),
-                _lib.ptr(grad_w), _lib.ptr(grad_b), stream))
+            ws = _workspace(x.device, stream)
+            if peer is not None:
+                # one launch: reduction, exchange over peer memory by its last CTA (global totals
+                # into `gs`), local totals into the fp32 parameter gradients
+                off = peer.next_slot_offset(2 * C)
+                _lib.check(lib.meb200_bn_backward_reduce_peer(
+                    _lib.ptr(dy), _lib.ptr(x), _lib.ptr(ymask), code, n, C, _lib.ptr(mean),
+                    _lib.ptr(invstd), _lib.ptr(ws), peer.bases_dev, off, peer.seq, peer.rank,
+                    peer.world, _lib.ptr(gs), _lib.ptr(grad_w), _lib.ptr(grad_b), stream))
+            else:
+                _lib.check(lib.meb200_bn_backward_reduce_to(
+                    _lib.ptr(dy), _lib.ptr(x), _lib.ptr(ymask), code, n, C, _lib.ptr(mean),
+                    _lib.ptr(invstd), _lib.ptr(ws), _lib.ptr(gs), _lib.ptr(grad_w),
+                    _lib.ptr(grad_b), stream))
             if g32 is not None and ctx.param_dtype != torch.float32:
                 g32 = g32.to(ctx.param_dtype)
                 grad_b, grad_w = g32[:C], g32[C:]
             if ctx.use_running:
                 gs = torch.zeros_like(gs)      # statistics are constants: dx = dy' * invstd * w
-            elif peer is not None:
-                total = torch.empty(2 * C, dtype=torch.float64, device=x.device)
-                peer.allreduce(off, 2 * C, total)
-                gs = total
-            elif group is not None:
+            elif peer is None and group is not None:
                 torch.distributed.all_reduce(gs, group=group)
             dx = torch.empty_like(x)
             dres = torch.empty_like(x) if ctx.has_residual else None

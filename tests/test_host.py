@@ -174,7 +174,8 @@ def test_argument_errors_carry_location_condition_and_values():
     assert rc != 0
     msg = lib.meb200_last_error().decode()
     assert "coords.cu" in msg and "ncols >= 2" in msg and msg.rstrip().endswith("ncols=1"), msg
-    rc = lib.meb200_peer_allreduce_f64(None, 1024, 4, 1, 0, 2, None, None)
+    rc = lib.meb200_bn_backward_reduce_peer(None, None, None, 1, 4, 32, None, None, None, None,
+                                            1024, 1, 0, 2, None, None, None, None)
     assert rc != 0 and "null buffer" in lib.meb200_last_error().decode()
     with pytest.raises(_lib.BackendError):
         _lib.check(rc)
