@@ -411,6 +411,8 @@ def run_ours(args):
             # MEB200_DDP_PLAIN=1 restores the reference example's plain DDP
             # (examples/multigpu_ddp.py).
             ddp_kw = dict(broadcast_buffers=False, gradient_as_bucket_view=True)
+            if os.environ.get("MEB200_DDP_BUCKET_MB"):      # A/B: all-reduce bucket size
+                ddp_kw["bucket_cap_mb"] = int(os.environ["MEB200_DDP_BUCKET_MB"])
             if os.environ.get("MEB200_DDP_PLAIN", "0") not in ("", "0"):
                 ddp_kw = {}
             net = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], **ddp_kw)

@@ -293,7 +293,8 @@ int meb200_bn_backward_apply_fused(const void *dy, const void *x, const void *y_
  * meb200_bn_workspace_bytes() bytes, zero-filled once by the caller and shared by every layer
  * that runs on the same stream; the last CTA of a reduction consumes the totals (finalize /
  * parameter gradients / copy-out) and leaves the workspace zero again.
- *   meb200_bn_forward_train      = stats + finalize (one launch) + apply_fused; n > 0
+ *   meb200_bn_forward_train      = stats + finalize (one launch) + apply_fused; n > 0;
+ *                                  *num_batches_tracked (int64, may be NULL) is incremented
  *   meb200_bn_stats_to           = stats, totals [sum x | sum x^2] copied to sums_out[2C]
  *                                  (the exchange slot of a synchronised layer)
  *   meb200_bn_backward_reduce_to = backward reduce, totals [sum dy | sum dy*xhat] copied to
@@ -302,7 +303,8 @@ uint64_t meb200_bn_workspace_bytes(void);
 int meb200_bn_forward_train(const void *x, int dtype, uint32_t n, uint32_t C, const float *weight,
                             const float *bias, const void *residual, int relu, float eps,
                             float momentum, float *running_mean, float *running_var,
-                            void *workspace, float *mean, float *invstd, void *y, void *stream);
+                            long long *num_batches_tracked, void *workspace, float *mean,
+                            float *invstd, void *y, void *stream);
 int meb200_bn_stats_to(const void *x, int dtype, uint32_t n, uint32_t C, void *workspace,
                        double *sums_out, void *stream);
 int meb200_bn_backward_reduce_to(const void *dy, const void *x, const void *y_mask, int dtype,
@@ -330,7 +332,8 @@ int meb200_bn_backward_reduce_to(const void *dy, const void *x, const void *y_ma
 int meb200_bn_forward_train_peer(const void *x, int dtype, uint32_t n, uint32_t C,
                                  const float *weight, const float *bias, const void *residual,
                                  int relu, float eps, float momentum, float *running_mean,
-                                 float *running_var, void *workspace, const void *peer_bases_dev,
+                                 float *running_var, long long *num_batches_tracked,
+                                 void *workspace, const void *peer_bases_dev,
                                  uint64_t slot_offset_bytes, uint32_t seq, uint32_t rank,
                                  uint32_t world, float *mean, float *invstd, double *total_rows,
                                  void *y, void *stream);

@@ -61,7 +61,7 @@ PROTOTYPES = {
     "meb200_bn_stats": (_i32, [_vp, _i32, _u32, _u32, _vp, _vp]),
     "meb200_bn_workspace_bytes": (_u64, []),
     "meb200_bn_forward_train": (_i32, [_vp, _i32, _u32, _u32, _vp, _vp, _vp, _i32, C.c_float,
-                                       C.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                       C.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "meb200_bn_stats_to": (_i32, [_vp, _i32, _u32, _u32, _vp, _vp, _vp]),
     "meb200_bn_backward_reduce_to": (_i32, [_vp, _vp, _vp, _i32, _u32, _u32, _vp, _vp, _vp, _vp,
                                             _vp, _vp, _vp]),
@@ -76,7 +76,7 @@ PROTOTYPES = {
     "meb200_bn_backward_apply_fused": (_i32, [_vp, _vp, _vp, _i32, _u32, _u32, _vp, _vp, _vp, _vp,
                                               C.c_double, _vp, _vp, _vp, _vp]),
     "meb200_bn_forward_train_peer": (_i32, [_vp, _i32, _u32, _u32, _vp, _vp, _vp, _i32, C.c_float,
-                                            C.c_float, _vp, _vp, _vp, _vp, C.c_uint64, _u32, _u32,
+                                            C.c_float, _vp, _vp, _vp, _vp, _vp, C.c_uint64, _u32, _u32,
                                             _u32, _vp, _vp, _vp, _vp, _vp]),
     "meb200_bn_backward_reduce_peer": (_i32, [_vp, _vp, _vp, _i32, _u32, _u32, _vp, _vp, _vp, _vp,
                                               C.c_uint64, _u32, _u32, _u32, _vp, _vp, _vp, _vp]),

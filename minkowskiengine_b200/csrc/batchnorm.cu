@@ -113,6 +113,7 @@ struct BnTail {
   uint64_t peer_slot_offset;
   uint32_t peer_seq, peer_rank, peer_world;
   double *total_rows_out;                               // MODE 0, synchronised: global row count
+  long long *num_batches_tracked;                       // MODE 0: incremented once (may be NULL)
 };
 constexpr uint32_t kBnMaxC = 2048;
 constexpr size_t kBnWorkspaceBytes = 2 * kBnMaxC * sizeof(double) + 64;   // sums, then the ticket
@@ -256,7 +257,10 @@ k_bn_reduce(const T *__restrict__ a, const T *__restrict__ x, const T *__restric
       if (tail.grad_weight != nullptr) tail.grad_weight[c] = (float)t2;
     }
   }
-  if (threadIdx.x == 0) *tail.ticket = 0u;
+  if (threadIdx.x == 0) {
+    *tail.ticket = 0u;
+    if (MODE == 0 && tail.num_batches_tracked != nullptr) *tail.num_batches_tracked += 1;
+  }
 }
 
 __global__ void k_bn_finalize(const double *__restrict__ sums, double count,
@@ -461,12 +465,14 @@ static inline uint32_t *bn_ticket(void *workspace) {
 int meb200_bn_forward_train(const void *x, int dtype, uint32_t n, uint32_t C, const float *weight,
                             const float *bias, const void *residual, int relu, float eps,
                             float momentum, float *running_mean, float *running_var,
-                            void *workspace, float *mean, float *invstd, void *y, void *stream_) {
+                            long long *num_batches_tracked, void *workspace, float *mean,
+                            float *invstd, void *y, void *stream_) {
   cudaStream_t s = (cudaStream_t)stream_;
   MEB_BN_CHECK(C);
   MEB_CHECK_ARG(n > 0 && workspace && mean && invstd && y, "bn forward: empty input / null buffer");
   BnTail tail{};
   tail.ticket = bn_ticket(workspace);
+  tail.num_batches_tracked = num_batches_tracked;
   tail.mean = mean; tail.invstd = invstd; tail.running_mean = running_mean; tail.running_var = running_var;
   tail.count = (double)n; tail.eps = eps; tail.momentum = momentum;
   int rc = bn_launch_reduce(0, x, nullptr, nullptr, dtype, n, C, nullptr, nullptr,
@@ -527,7 +533,8 @@ static void bn_tail_peer(BnTail &tail, const void *peer_bases_dev, uint64_t slot
 int meb200_bn_forward_train_peer(const void *x, int dtype, uint32_t n, uint32_t C,
                                  const float *weight, const float *bias, const void *residual,
                                  int relu, float eps, float momentum, float *running_mean,
-                                 float *running_var, void *workspace, const void *peer_bases_dev,
+                                 float *running_var, long long *num_batches_tracked,
+                                 void *workspace, const void *peer_bases_dev,
                                  uint64_t slot_offset_bytes, uint32_t seq, uint32_t rank,
                                  uint32_t world, float *mean, float *invstd, double *total_rows,
                                  void *y, void *stream_) {
@@ -540,6 +547,7 @@ int meb200_bn_forward_train_peer(const void *x, int dtype, uint32_t n, uint32_t 
   tail.mean = mean; tail.invstd = invstd; tail.running_mean = running_mean; tail.running_var = running_var;
   tail.count = (double)n; tail.eps = eps; tail.momentum = momentum;
   tail.total_rows_out = total_rows;
+  tail.num_batches_tracked = num_batches_tracked;
   bn_tail_peer(tail, peer_bases_dev, slot_offset_bytes, seq, rank, world);
   int rc = bn_launch_reduce(0, x, nullptr, nullptr, dtype, n, C, nullptr, nullptr,
                             (double *)workspace, tail, s);

@@ -112,7 +112,7 @@ class _BatchNormFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, group, relu,
-                residual, use_running):
+                residual, use_running, num_batches_tracked=None):
         lib = _lib.load()
         x = x.contiguous()
         n, C = x.shape
@@ -140,8 +140,9 @@ class _BatchNormFunction(torch.autograd.Function):
                 _lib.check(lib.meb200_bn_forward_train(
                     _lib.ptr(x), code, n, C, _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(residual),
                     1 if relu else 0, float(eps), float(momentum), _lib.ptr(running_mean),
-                    _lib.ptr(running_var), _lib.ptr(ws), _lib.ptr(mean), _lib.ptr(invstd),
-                    _lib.ptr(y), stream))
+                    _lib.ptr(running_var), _lib.ptr(num_batches_tracked), _lib.ptr(ws),
+                    _lib.ptr(mean), _lib.ptr(invstd), _lib.ptr(y), stream))
+                num_batches_tracked = None
             elif peer is not None:
                 # the same two launches: the last CTA of the reduction exchanges the statistics
                 # with the other ranks over NVLink peer memory before it finalizes
@@ -150,9 +151,10 @@ class _BatchNormFunction(torch.autograd.Function):
                 _lib.check(lib.meb200_bn_forward_train_peer(
                     _lib.ptr(x), code, n, C, _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(residual),
                     1 if relu else 0, float(eps), float(momentum), _lib.ptr(running_mean),
-                    _lib.ptr(running_var), _lib.ptr(ws), peer.bases_dev, off, peer.seq, peer.rank,
-                    peer.world, _lib.ptr(mean), _lib.ptr(invstd), _lib.ptr(d_count), _lib.ptr(y),
-                    stream))
+                    _lib.ptr(running_var), _lib.ptr(num_batches_tracked), _lib.ptr(ws),
+                    peer.bases_dev, off, peer.seq, peer.rank, peer.world, _lib.ptr(mean),
+                    _lib.ptr(invstd), _lib.ptr(d_count), _lib.ptr(y), stream))
+                num_batches_tracked = None
             else:
                 if not use_running:
                     sums = torch.empty(2 * C + 1, dtype=torch.float64, device=dev)
@@ -169,6 +171,8 @@ class _BatchNormFunction(torch.autograd.Function):
                 _lib.check(lib.meb200_bn_apply_fused(
                     _lib.ptr(x), code, n, C, _lib.ptr(mean), _lib.ptr(invstd), _lib.ptr(w32),
                     _lib.ptr(b32), _lib.ptr(residual), 1 if relu else 0, _lib.ptr(y), stream))
+        if num_batches_tracked is not None and not use_running:
+            num_batches_tracked.add_(1)        # paths whose kernels do not count the batch themselves
         ctx.save_for_backward(x, mean, invstd, w32 if w32 is not None else mean.new_empty(0),
                               d_count if d_count is not None else mean.new_empty(0, dtype=torch.float64),
                               y if relu else x.new_empty(0))
@@ -226,7 +230,7 @@ class _BatchNormFunction(torch.autograd.Function):
                 _lib.ptr(invstd), _lib.ptr(w32) if w32.numel() else None, _lib.ptr(gs),
                 float(max(n, 1)), _lib.ptr(d_count) if d_count.numel() else None, _lib.ptr(dx),
                 _lib.ptr(dres), stream))
-        return dx, grad_w, grad_b, None, None, None, None, None, None, dres, None
+        return dx, grad_w, grad_b, None, None, None, None, None, None, dres, None, None
 
 
 def _native_ok(bn, x):
@@ -253,10 +257,12 @@ def _batch_norm(bn, x, group=None, relu=False, residual=None):
     if bn.training:
         if x.shape[0] == 0 and group is None:      # nothing to normalise, statistics untouched
             return x.clone() if residual is None else x + residual
-        if bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
+        nbt = bn.num_batches_tracked
+        if nbt is not None and not (nbt.dtype == torch.int64 and nbt.device == x.device):
+            nbt.add_(1)
+            nbt = None
         return _BatchNormFunction.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                                        bn.momentum, bn.eps, group, relu, residual, False)
+                                        bn.momentum, bn.eps, group, relu, residual, False, nbt)
     return _BatchNormFunction.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                                     bn.momentum, bn.eps, None, relu, residual, True)
 
