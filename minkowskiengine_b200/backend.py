@@ -181,14 +181,18 @@ class _KernelMap:
     Replaces gpu_kernel_map's three flat arrays + host offset table (src/kernel_map.cuh:48-429);
     `swapped()` is the reference's swap_in_out (kernel_map.cuh:191-241)."""
 
-    __slots__ = ("out_nbr", "in_nbr", "stride_pairs", "_n_pairs", "_pairs", "_pair_src",
-                 "_hint_key")
+    __slots__ = ("out_nbr", "_in_nbr", "_in_thunk", "_n_in", "stride_pairs", "_n_pairs", "_pairs",
+                 "_pair_src", "_hint_key")
     PAIR_STAGE = 64   # pairs per pipeline stage of the wgrad kernel (k_wgrad_pairs)
     # table rows per chunk of the pair lists (multiple of 2048)
     PAIR_CHUNK_ROWS = int(os.environ.get("MEB200_PAIR_CHUNK_ROWS", "65536"))
 
-    def __init__(self, out_nbr, in_nbr, stride_pairs=None):
-        self.out_nbr, self.in_nbr = out_nbr, in_nbr
+    def __init__(self, out_nbr, in_nbr, stride_pairs=None, n_in=None, in_thunk=None):
+        # in_nbr may be None with (n_in, in_thunk): the reverse table of a large kernel (the
+        # K = 125 stem: 400 MB at 800k rows) is only built if somebody asks for it — dgrad or a
+        # transposed layer; the stem of a network needs neither
+        self.out_nbr, self._in_nbr, self._in_thunk = out_nbr, in_nbr, in_thunk
+        self._n_in = in_nbr.shape[1] if in_nbr is not None else int(n_in)
         self.stride_pairs = stride_pairs  # (in_rows, out_rows) when built as a stride map
         self._n_pairs = None
         self._pairs = None      # (pairs_in, pairs_out, seg_start) once built
@@ -243,7 +247,14 @@ class _KernelMap:
 
     @property
     def n_in(self):
-        return self.in_nbr.shape[1]
+        return self._n_in
+
+    @property
+    def in_nbr(self):
+        if self._in_nbr is None:
+            self._in_nbr = self._in_thunk()
+            self._in_thunk = None
+        return self._in_nbr
 
     def swapped(self):
         sp = None if self.stride_pairs is None else (self.stride_pairs[1], self.stride_pairs[0])
@@ -525,13 +536,15 @@ class CoordinateMapManagerGPU_c10:
         return out_key, True
 
     # -- kernel maps -----------------------------------------------------------------
-    def _probe(self, x_map, y_map, offsets):
-        """x-stationary probe: returns (x_nbr [K,nx], y_nbr [K,ny])."""
+    LAZY_REVERSE_K = 64      # kernels this large get their reverse table on demand
+
+    def _probe(self, x_map, y_map, offsets, need_y=True):
+        """x-stationary probe: returns (x_nbr [K,nx], y_nbr [K,ny] or None)."""
         lib = _lib.load()
         K = offsets.shape[0]
         dev = x_map.coords.device
         x_nbr = torch.empty((K, x_map.size), dtype=torch.int32, device=dev)
-        y_nbr = torch.full((K, y_map.size), -1, dtype=torch.int32, device=dev)
+        y_nbr = torch.full((K, y_map.size), -1, dtype=torch.int32, device=dev) if need_y else None
 
         def launch():
             _lib.check(lib.meb200_kernel_map(
@@ -543,7 +556,8 @@ class CoordinateMapManagerGPU_c10:
             # + one coordinate row compared per probe, both neighbour tables written
             nc4 = x_map.ncols * 4
             probes = float(K) * x_map.size
-            nbytes = x_map.size * nc4 + probes * (4 + nc4) + probes * 4 + float(K) * y_map.size * 4
+            nbytes = x_map.size * nc4 + probes * (4 + nc4) + probes * 4 + \
+                (float(K) * y_map.size * 4 if need_y else 0.0)
             _record("kernel_map", launch, probes, nbytes, always=True)
         else:
             launch()
@@ -582,8 +596,13 @@ class CoordinateMapManagerGPU_c10:
                 km = _KernelMap(out_nbr, in_nbr, self._stride_pairs(ik, ok, in_map, out_map))
             else:
                 offs = _device_offsets(region_type, ksize, kdil, in_map.tensor_stride, custom, dev)
-                out_nbr, in_nbr = self._probe(out_map, in_map, offs)
-                km = _KernelMap(out_nbr, in_nbr)
+                if offs.shape[0] >= self.LAZY_REVERSE_K:
+                    out_nbr, _ = self._probe(out_map, in_map, offs, need_y=False)
+                    km = _KernelMap(out_nbr, None, n_in=in_map.size,
+                                    in_thunk=lambda: self._probe(out_map, in_map, offs)[1])
+                else:
+                    out_nbr, in_nbr = self._probe(out_map, in_map, offs)
+                    km = _KernelMap(out_nbr, in_nbr)
         else:
             swapped_key = (ok, ik, ksize, kstride, kdil, region_type, False, bool(is_pool))
             fwd = self._kernel_maps.get(swapped_key)
@@ -898,8 +917,8 @@ def _conv_backward_impl(in_feat, grad_out, kernel, km, need_in=True, need_w=True
             pin, pout, seg, nch = km.pair_lists()
         rc = lib.meb200_conv_backward_packed(
             _lib.ptr(in_feat), _lib.ptr(grad_out), code, n_in, c_in, _lib.ptr(w), _lib.ptr(w_cp),
-            K, c_out, _lib.ptr(km.out_nbr), _lib.ptr(km.in_nbr), n_out, _lib.ptr(grad_in), code,
-            _lib.ptr(grad_w), _lib.ptr(pin), _lib.ptr(pout), _lib.ptr(seg), nch,
+            K, c_out, _lib.ptr(km.out_nbr), _lib.ptr(km.in_nbr) if need_in else None, n_out,
+            _lib.ptr(grad_in), code, _lib.ptr(grad_w), _lib.ptr(pin), _lib.ptr(pout), _lib.ptr(seg), nch,
             _lib.current_stream())
         if rc != _ERR_UNSUPPORTED:
             _lib.check(rc)
@@ -910,8 +929,8 @@ def _conv_backward_impl(in_feat, grad_out, kernel, km, need_in=True, need_w=True
     ws, ws_bytes = _workspace(n_in, n_out, c_in, c_out, K, code, in_feat.device)
     _lib.check(lib.meb200_conv_backward(
         _lib.ptr(in_feat), _lib.ptr(grad_out), code, n_in, c_in, _lib.ptr(w), K, c_out,
-        _lib.ptr(km.out_nbr), _lib.ptr(km.in_nbr), n_out, _lib.ptr(grad_in), code,
-        _lib.ptr(grad_w), _lib.ptr(ws), ws_bytes, _lib.current_stream()))
+        _lib.ptr(km.out_nbr), _lib.ptr(km.in_nbr) if need_in else None, n_out, _lib.ptr(grad_in),
+        code, _lib.ptr(grad_w), _lib.ptr(ws), ws_bytes, _lib.current_stream()))
     if grad_w is not None and grad_w.dtype != kernel.dtype:
         grad_w = grad_w.to(kernel.dtype)
     return grad_in, grad_w
