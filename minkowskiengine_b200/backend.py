@@ -619,6 +619,8 @@ class CoordinateMapManagerGPU_c10:
                                            custom, dev)
                     a, b = self._probe(in_map, out_map, offs)
                     fwd = _KernelMap(a, b)
+                fwd._hint_key = swapped_key
+                self._kernel_maps[swapped_key] = fwd
             km = fwd.swapped()
         km._hint_key = cache_key
         self._kernel_maps[cache_key] = km
