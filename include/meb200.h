@@ -249,47 +249,30 @@ int meb200_pool_backward(const void *grad_out, int dtype, uint32_t n_in, uint32_
 /* ---- batch normalisation over [n, C] feature rows (SURVEY.md 8(f) "next" row 1; the
  *      reference applies torch.nn.BatchNorm1d to `.F`: MinkowskiEngine/MinkowskiNormalization.py:51-99).
  *      C must be a multiple of 8.  sums: DEVICE double [2C]; statistics tensors fp32 [C]. ------ */
-/* sums[c] = sum_r x[r,c], sums[C+c] = sum_r x[r,c]^2 (zeroed inside). */
-int meb200_bn_stats(const void *x, int dtype, uint32_t n, uint32_t C, double *sums, void *stream);
-/* mean / invstd (biased variance + eps) from the (possibly all-reduced) sums over `count` rows;
- * running statistics (may be NULL) updated with momentum and the unbiased variance. */
-/* The row count is `count`, or — for synchronised BN, where it is the all-reduced total that
- * only exists on the device — read from *d_count when d_count != NULL. */
+/* mean / invstd (biased variance + eps) from the (possibly all-reduced) sums
+ * [sum x | sum x^2] over `count` rows; running statistics (may be NULL) updated with momentum
+ * and the unbiased variance.  The row count is `count`, or — for synchronised BN over NCCL,
+ * where it is the all-reduced total that only exists on the device — read from *d_count when
+ * d_count != NULL. */
 int meb200_bn_finalize(const double *sums, double count, const double *d_count, uint32_t C,
                        float eps, float momentum, float *running_mean, float *running_var,
                        float *mean, float *invstd, void *stream);
-/* y = (x - mean) * invstd * weight + bias, optionally followed by ReLU (weight/bias may be NULL). */
-int meb200_bn_apply(const void *x, int dtype, uint32_t n, uint32_t C, const float *mean,
-                    const float *invstd, const float *weight, const float *bias, int relu,
-                    void *y, void *stream);
-/* sums[c] = sum_r dy, sums[C+c] = sum_r dy * (x - mean) * invstd  (= grad_bias, grad_weight). */
-int meb200_bn_backward_reduce(const void *dy, const void *x, int dtype, uint32_t n, uint32_t C,
-                              const float *mean, const float *invstd, double *sums, void *stream);
-/* dx = (dy - sums[c]/count - xhat * sums[C+c]/count) * invstd * weight. */
-int meb200_bn_backward_apply(const void *dy, const void *x, int dtype, uint32_t n, uint32_t C,
-                             const float *mean, const float *invstd, const float *weight,
-                             const double *sums, double count, const double *d_count, void *dx,
-                             void *stream);
-
-/* Fused forms (the BasicBlock tail of modules/resnet_block.py:52-68):
- *   apply_fused           y = relu?( bn(x) + residual? )
- *   backward_reduce_fused sums over dy' = relu ? dy * (y > 0) : dy   (y_mask = the fused output y)
- *   backward_apply_fused  dx from dy' as above; d_residual (may be NULL) = dy'
- * residual / y_mask / d_residual may be NULL; the unfused entry points above are these with
- * NULLs. */
+/* The streaming passes, with the BasicBlock tail of modules/resnet_block.py:52-68 folded in:
+ *   apply_fused           y = relu?( bn(x) + residual? ),  bn(x) = (x - mean) * invstd * weight + bias
+ *   backward_apply_fused  with dy' = relu ? dy * (y_mask > 0) : dy  (y_mask = the fused output y):
+ *                         dx = (dy' - sums[c]/count - xhat * sums[C+c]/count) * invstd * weight,
+ *                         d_residual (may be NULL) = dy'
+ * weight / bias / residual / y_mask / d_residual may be NULL. */
 int meb200_bn_apply_fused(const void *x, int dtype, uint32_t n, uint32_t C, const float *mean,
                           const float *invstd, const float *weight, const float *bias,
                           const void *residual, int relu, void *y, void *stream);
-int meb200_bn_backward_reduce_fused(const void *dy, const void *x, const void *y_mask, int dtype,
-                                    uint32_t n, uint32_t C, const float *mean,
-                                    const float *invstd, double *sums, void *stream);
 int meb200_bn_backward_apply_fused(const void *dy, const void *x, const void *y_mask, int dtype,
                                    uint32_t n, uint32_t C, const float *mean, const float *invstd,
                                    const float *weight, const double *sums, double count,
                                    const double *d_count, void *dx, void *d_residual,
                                    void *stream);
 
-/* Launch-lean forms (two launches per pass, no memset): the reductions take a WORKSPACE of
+/* The reductions (two launches per pass, no memset): they take a WORKSPACE of
  * meb200_bn_workspace_bytes() bytes, zero-filled once by the caller and shared by every layer
  * that runs on the same stream; the last CTA of a reduction consumes the totals (finalize /
  * parameter gradients / copy-out) and leaves the workspace zero again.

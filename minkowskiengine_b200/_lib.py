@@ -58,7 +58,6 @@ PROTOTYPES = {
     "meb200_pool_forward": (_i32, [_vp, _i32, _u32, _u32, _vp, _u32, _u32, _i32, _vp, _vp, _vp]),
     "meb200_pool_backward": (_i32, [_vp, _i32, _u32, _u32, _vp, _u32, _u32, _i32, _vp, _vp,
                                     _vp]),
-    "meb200_bn_stats": (_i32, [_vp, _i32, _u32, _u32, _vp, _vp]),
     "meb200_bn_workspace_bytes": (_u64, []),
     "meb200_bn_forward_train": (_i32, [_vp, _i32, _u32, _u32, _vp, _vp, _vp, _i32, C.c_float,
                                        C.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -67,12 +66,7 @@ PROTOTYPES = {
                                             _vp, _vp, _vp]),
     "meb200_bn_finalize": (_i32, [_vp, C.c_double, _vp, _u32, C.c_float, C.c_float, _vp, _vp, _vp,
                                   _vp, _vp]),
-    "meb200_bn_apply": (_i32, [_vp, _i32, _u32, _u32, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
-    "meb200_bn_backward_reduce": (_i32, [_vp, _vp, _i32, _u32, _u32, _vp, _vp, _vp, _vp]),
-    "meb200_bn_backward_apply": (_i32, [_vp, _vp, _i32, _u32, _u32, _vp, _vp, _vp, _vp, C.c_double,
-                                        _vp, _vp, _vp]),
     "meb200_bn_apply_fused": (_i32, [_vp, _i32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
-    "meb200_bn_backward_reduce_fused": (_i32, [_vp, _vp, _vp, _i32, _u32, _u32, _vp, _vp, _vp, _vp]),
     "meb200_bn_backward_apply_fused": (_i32, [_vp, _vp, _vp, _i32, _u32, _u32, _vp, _vp, _vp, _vp,
                                               C.c_double, _vp, _vp, _vp, _vp]),
     "meb200_bn_forward_train_peer": (_i32, [_vp, _i32, _u32, _u32, _vp, _vp, _vp, _i32, C.c_float,

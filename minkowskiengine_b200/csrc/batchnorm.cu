@@ -381,25 +381,6 @@ using namespace meb200;
 
 extern "C" {
 
-int meb200_bn_stats(const void *x, int dtype, uint32_t n, uint32_t C, double *sums, void *stream_) {
-  cudaStream_t s = (cudaStream_t)stream_;
-  MEB_BN_CHECK(C);
-  MEB_CHECK_ARG(sums != nullptr, "sums");
-  MEB_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(double), s));
-  if (n == 0) return MEB200_OK;
-  unsigned grid;
-  uint32_t rows = bn_rows_per_cta(n, C, &grid);
-  size_t smem = 2 * (size_t)C * sizeof(float);
-  switch (dtype) {
-    case MEB200_F32: k_bn_reduce<float, 0><<<grid, kBnThreads, smem, s>>>((const float *)x, nullptr, nullptr, nullptr, nullptr, n, C, rows, sums, BnTail{}); break;
-    case MEB200_BF16: k_bn_reduce<__nv_bfloat16, 0><<<grid, kBnThreads, smem, s>>>((const __nv_bfloat16 *)x, nullptr, nullptr, nullptr, nullptr, n, C, rows, sums, BnTail{}); break;
-    case MEB200_F16: k_bn_reduce<__half, 0><<<grid, kBnThreads, smem, s>>>((const __half *)x, nullptr, nullptr, nullptr, nullptr, n, C, rows, sums, BnTail{}); break;
-    default: set_error("batch norm: unsupported dtype %d", dtype); return MEB200_ERR_UNSUPPORTED;
-  }
-  MEB_LAUNCH_OK();
-  return MEB200_OK;
-}
-
 int meb200_bn_finalize(const double *sums, double count, const double *d_count, uint32_t C,
                        float eps, float momentum, float *running_mean, float *running_var,
                        float *mean, float *invstd, void *stream_) {
@@ -574,37 +555,6 @@ int meb200_bn_backward_reduce_peer(const void *dy, const void *x, const void *y_
   return bn_launch_reduce(1, dy, x, y_mask, dtype, n, C, mean, invstd, (double *)workspace, tail, s);
 }
 
-int meb200_bn_apply(const void *x, int dtype, uint32_t n, uint32_t C, const float *mean,
-                    const float *invstd, const float *weight, const float *bias, int relu,
-                    void *y, void *stream_) {
-  return meb200_bn_apply_fused(x, dtype, n, C, mean, invstd, weight, bias, nullptr, relu, y, stream_);
-}
-
-int meb200_bn_backward_reduce_fused(const void *dy, const void *x, const void *y_mask, int dtype,
-                                    uint32_t n, uint32_t C, const float *mean,
-                                    const float *invstd, double *sums, void *stream_) {
-  cudaStream_t s = (cudaStream_t)stream_;
-  MEB_BN_CHECK(C);
-  MEB_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(double), s));
-  if (n == 0) return MEB200_OK;
-  unsigned grid;
-  uint32_t rows = bn_rows_per_cta(n, C, &grid);
-  size_t smem = 2 * (size_t)C * sizeof(float);
-  switch (dtype) {
-    case MEB200_F32: k_bn_reduce<float, 1><<<grid, kBnThreads, smem, s>>>((const float *)dy, (const float *)x, (const float *)y_mask, mean, invstd, n, C, rows, sums, BnTail{}); break;
-    case MEB200_BF16: k_bn_reduce<__nv_bfloat16, 1><<<grid, kBnThreads, smem, s>>>((const __nv_bfloat16 *)dy, (const __nv_bfloat16 *)x, (const __nv_bfloat16 *)y_mask, mean, invstd, n, C, rows, sums, BnTail{}); break;
-    case MEB200_F16: k_bn_reduce<__half, 1><<<grid, kBnThreads, smem, s>>>((const __half *)dy, (const __half *)x, (const __half *)y_mask, mean, invstd, n, C, rows, sums, BnTail{}); break;
-    default: set_error("batch norm: unsupported dtype %d", dtype); return MEB200_ERR_UNSUPPORTED;
-  }
-  MEB_LAUNCH_OK();
-  return MEB200_OK;
-}
-
-int meb200_bn_backward_reduce(const void *dy, const void *x, int dtype, uint32_t n, uint32_t C,
-                              const float *mean, const float *invstd, double *sums, void *stream_) {
-  return meb200_bn_backward_reduce_fused(dy, x, nullptr, dtype, n, C, mean, invstd, sums, stream_);
-}
-
 int meb200_bn_backward_apply_fused(const void *dy, const void *x, const void *y_mask, int dtype,
                                    uint32_t n, uint32_t C, const float *mean, const float *invstd,
                                    const float *weight, const double *sums, double count,
@@ -624,14 +574,6 @@ int meb200_bn_backward_apply_fused(const void *dy, const void *x, const void *y_
   }
   MEB_LAUNCH_OK();
   return MEB200_OK;
-}
-
-int meb200_bn_backward_apply(const void *dy, const void *x, int dtype, uint32_t n, uint32_t C,
-                             const float *mean, const float *invstd, const float *weight,
-                             const double *sums, double count, const double *d_count, void *dx,
-                             void *stream_) {
-  return meb200_bn_backward_apply_fused(dy, x, nullptr, dtype, n, C, mean, invstd, weight, sums,
-                                        count, d_count, dx, nullptr, stream_);
 }
 
 }
