@@ -185,7 +185,9 @@ class _KernelMap:
                  "_pair_src", "_hint_key")
     PAIR_STAGE = 64   # pairs per pipeline stage of the wgrad kernel (k_wgrad_pairs)
     # table rows per chunk of the pair lists (multiple of 2048)
-    PAIR_CHUNK_ROWS = int(os.environ.get("MEB200_PAIR_CHUNK_ROWS", "65536"))
+    # (measured on block8 96->96 wgrad, 800k rows: 16384 rows 0.64 ms, 65536 0.49, 131072 0.45,
+    #  262144 0.44, one chunk 0.46 — profiles/r2_notes.md §7)
+    PAIR_CHUNK_ROWS = int(os.environ.get("MEB200_PAIR_CHUNK_ROWS", "262144"))
 
     def __init__(self, out_nbr, in_nbr, stride_pairs=None, n_in=None, in_thunk=None):
         # in_nbr may be None with (n_in, in_thunk): the reverse table of a large kernel (the
