@@ -374,6 +374,37 @@ def _golden_loss(args):
     return None
 
 
+def bind_to_gpu_numa_node(index):
+    """Pins this rank's threads to the CPUs NVML reports as local to its GPU (the step is launch
+    bound in places: a rank whose interpreter runs on the other socket pays for it on every
+    launch, and a multi-rank step waits for the slowest rank).  Returns the number of CPUs in the
+    mask, or None when NVML / the mask is unavailable (nothing changes then).
+    MEB200_BENCH_AFFINITY=0 disables it."""
+    if os.environ.get("MEB200_BENCH_AFFINITY", "1") in ("", "0"):
+        return None
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            bus = torch.cuda.get_device_properties(index).pci_bus_id
+            dom = torch.cuda.get_device_properties(index).pci_domain_id
+            dv = torch.cuda.get_device_properties(index).pci_device_id
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{dom:08x}:{bus:02x}:{dv:02x}.0".encode())
+        except Exception:                           # noqa: BLE001
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if len(cpus) >= 4:                          # never squeeze a rank onto a handful of cores
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:                               # noqa: BLE001
+        pass
+    return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -386,6 +417,7 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cpus = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[args.dtype]
@@ -650,6 +682,7 @@ def run_ours(args):
             "config": {"workload": workload,
                        "global_batch_clouds": args.clouds * world, "voxels_per_step": total_vox,
                        "parallelism": f"dp{world}" if is_net else f"replicas{world}", "l2": l2,
+                       "host_cpus_bound": numa_cpus,
                        **({"ablate": ablate} if ablate else {})},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
