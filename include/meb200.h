@@ -189,6 +189,20 @@ int meb200_conv_pack_weights(const float *weight, uint32_t K, uint32_t c_in, uin
                              int dtype, void *w_cast, void *w_t, void *w_cp, void *w_tp,
                              void *stream);
 
+/* The same packing for MANY layers in one launch (all weights of a network change together, at
+ * the optimizer step): `jobs_dev` is a DEVICE array of n_jobs jobs; job j owns the 32x32 tiles
+ * [tile_begin_j, tile_begin_j + K_j * ceil(c_in_j / 32) * ceil(c_out_j / 32)) of the launch,
+ * tile_begin ascending from 0, total_tiles = their sum.  The table only has to be rebuilt when
+ * the set of tensors (or their addresses) changes. */
+typedef struct meb200_pack_job {
+  const void *w;                      /* fp32 [K, c_in, c_out] */
+  void *w_cast, *w_t, *w_cp, *w_tp;   /* as meb200_conv_pack_weights; w_cp / w_tp may be NULL */
+  uint32_t K, c_in, c_out;
+  uint32_t tile_begin;
+} meb200_pack_job;
+int meb200_conv_pack_weights_batched(const meb200_pack_job *jobs_dev, uint32_t n_jobs,
+                                     uint32_t total_tiles, int dtype, void *stream);
+
 /* Network stem (the first layer of a network: c_in <= 4 input channels, e.g. RGB; reference
  * call site examples/minkunet.py:113-116 conv0p1s1, kernel 5 -> K = 125).  Rows of 8 bytes defeat
  * the 64-byte-block gather of the general kernels, so the layer is run as a K = 1 convolution over

@@ -63,6 +63,16 @@ int meb200_conv_pack_weights(const float *weight, uint32_t K, uint32_t c_in, uin
                            (cudaStream_t)stream_);
 }
 
+static_assert(sizeof(meb200_pack_job) == sizeof(PackJob), "meb200_pack_job layout");
+
+int meb200_conv_pack_weights_batched(const meb200_pack_job *jobs_dev, uint32_t n_jobs,
+                                     uint32_t total_tiles, int dtype, void *stream_) {
+  MEB_CHECK_ARG(dtype == MEB200_BF16 || dtype == MEB200_F16, "packed weights are bf16 or fp16");
+  MEB_CHECK_ARG(jobs_dev != nullptr || n_jobs == 0, "null job table");
+  return conv_pack_weights_batched(reinterpret_cast<const PackJob *>(jobs_dev), n_jobs, total_tiles,
+                                   dtype, (cudaStream_t)stream_);
+}
+
 uint32_t meb200_conv_stem_virtual_channels(uint32_t K) { return 4u * ((K + 15u) / 16u * 16u); }
 
 int meb200_conv_stem_supported(int dtype, uint32_t K, uint32_t c_out) {

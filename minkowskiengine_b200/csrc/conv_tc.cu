@@ -495,6 +495,59 @@ k_pack_w(const float *__restrict__ W, T *__restrict__ Wc, T *__restrict__ Wt, T 
   }
 }
 
+// All layers of a network in ONE launch (the weights of every layer change together, at the
+// optimizer step): job j re-packs one [K, c_in, c_out] tensor exactly as k_pack_w does; a CTA
+// finds its job by binary search over the jobs' first-tile indices.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_pack_w_batched(const PackJob *__restrict__ jobs, uint32_t n_jobs) {
+  __shared__ float tile[32][33];
+  uint32_t lo = 0, hi = n_jobs - 1;
+  while (lo < hi) {                       // last job whose tile_begin <= blockIdx.x
+    const uint32_t mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].tile_begin <= blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const PackJob job = jobs[lo];
+  const uint32_t c_in = job.c_in, c_out = job.c_out;
+  const uint32_t tx_n = (c_out + 31u) / 32u, ty_n = (c_in + 31u) / 32u;
+  uint32_t t = blockIdx.x - job.tile_begin;
+  const uint32_t bx = t % tx_n; t /= tx_n;
+  const uint32_t by = t % ty_n, bz = t / ty_n;
+  const float *W = reinterpret_cast<const float *>(job.w);
+  T *Wc = reinterpret_cast<T *>(job.w_cast), *Wt = reinterpret_cast<T *>(job.w_t);
+  T *Wcp = reinterpret_cast<T *>(job.w_cp), *Wtp = reinterpret_cast<T *>(job.w_tp);
+  const size_t base = (size_t)bz * c_in * c_out;
+  const uint32_t ci0 = by * 32, co0 = bx * 32;
+  const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (uint32_t i = ty; i < 32; i += 8)
+    if (ci0 + i < c_in && co0 + tx < c_out) {
+      const float v = W[base + (size_t)(ci0 + i) * c_out + co0 + tx];
+      tile[i][tx] = v;
+      Wc[base + (size_t)(ci0 + i) * c_out + co0 + tx] = from_f32<T>(v);
+    }
+  __syncthreads();
+  const uint32_t px = ta_perm(tx);
+  for (uint32_t i = ty; i < 32; i += 8) {
+    if (co0 + i < c_out && ci0 + tx < c_in)
+      Wt[base + (size_t)(co0 + i) * c_in + ci0 + tx] = from_f32<T>(tile[tx][i]);
+    if (Wtp != nullptr && co0 + i < c_out)
+      Wtp[base + (size_t)(co0 + i) * c_in + ci0 + tx] = from_f32<T>(tile[px][i]);
+    if (Wcp != nullptr && ci0 + i < c_in)
+      Wcp[base + (size_t)(ci0 + i) * c_out + co0 + tx] = from_f32<T>(tile[i][px]);
+  }
+}
+
+int conv_pack_weights_batched(const PackJob *jobs_dev, uint32_t n_jobs, uint32_t total_tiles,
+                              int dtype, cudaStream_t stream) {
+  if (n_jobs == 0 || total_tiles == 0) return MEB200_OK;
+  if (dtype == MEB200_BF16)
+    k_pack_w_batched<__nv_bfloat16><<<total_tiles, 256, 0, stream>>>(jobs_dev, n_jobs);
+  else
+    k_pack_w_batched<__half><<<total_tiles, 256, 0, stream>>>(jobs_dev, n_jobs);
+  MEB_LAUNCH_OK();
+  return MEB200_OK;
+}
+
 int conv_pack_weights(const float *W, uint32_t K, uint32_t c_in, uint32_t c_out, int dtype,
                       void *w_cast, void *w_t, void *w_cp, void *w_tp, cudaStream_t stream) {
   if (c_out % 32 != 0) w_cp = nullptr;

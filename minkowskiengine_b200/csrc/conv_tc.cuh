@@ -21,6 +21,16 @@ int conv_forward_tc(const void *A, int dtype, uint32_t n_a, uint32_t c_reduce, c
 int conv_pack_weights(const float *W, uint32_t K, uint32_t c_in, uint32_t c_out, int dtype,
                       void *w_cast, void *w_t, void *w_cp, void *w_tp, cudaStream_t stream);
 
+// One job of conv_pack_weights_batched == one meb200_pack_job of include/meb200.h.
+struct PackJob {
+  const void *w;                      // fp32 [K, c_in, c_out]
+  void *w_cast, *w_t, *w_cp, *w_tp;   // as conv_pack_weights (w_cp / w_tp may be NULL)
+  uint32_t K, c_in, c_out;
+  uint32_t tile_begin;                // first 32x32 tile of this job in the launch
+};
+int conv_pack_weights_batched(const PackJob *jobs_dev, uint32_t n_jobs, uint32_t total_tiles,
+                              int dtype, cudaStream_t stream);
+
 int conv_wgrad_tc(const void *in, const void *grad_out, int dtype, uint32_t c_in, uint32_t K,
                   uint32_t c_out, const int32_t *out_nbr, uint32_t n_out, float *grad_weight,
                   cudaStream_t stream);

