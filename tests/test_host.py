@@ -246,3 +246,70 @@ def test_batchnorm_host_path_runs_against_a_stub_library(monkeypatch):
                                      "meb200_bn_backward_reduce_to", "meb200_bn_backward_apply_fused"]
     assert calls[1][1][2] is not None and calls[4][1][11] is not None
     assert isinstance(ME.MinkowskiSyncBatchNorm(16).bn, torch.nn.SyncBatchNorm)
+
+
+def test_pack_table_bookkeeping_against_a_stub_library(monkeypatch):
+    """backend._PackTable (one batched re-pack launch for every registered kernel) driven with CPU
+    tensors and the native library replaced by a recorder: first sight packs a kernel alone and
+    registers it; a stale registered kernel triggers ONE batched call that refreshes every entry;
+    dead and re-allocated tensors leave the job table."""
+    import ctypes
+    from minkowskiengine_b200 import _lib, backend as B
+
+    calls = []
+
+    class Stub:
+        def __getattr__(self, name):
+            def fn(*args):
+                calls.append((name, args))
+                return 0
+            return fn
+
+    monkeypatch.setattr(_lib, "load", lambda: Stub())
+    monkeypatch.setattr(_lib, "current_stream", lambda: None)
+    monkeypatch.setattr(B, "_PACK_BATCHED", True)
+    B._PACKED.clear()
+    B._PACK_TABLES.clear()
+    dtype = torch.bfloat16
+    ks = [torch.nn.Parameter(torch.randn(27, 32, 64)), torch.nn.Parameter(torch.randn(8, 5, 7)),
+          torch.nn.Parameter(torch.randn(1, 96, 96))]
+    for k in ks:
+        p = B._packed_weights(k, dtype)
+        assert p[0].shape == k.shape and p[1].shape == (k.shape[0], k.shape[2], k.shape[1])
+    assert [c[0] for c in calls] == ["meb200_conv_pack_weights"] * 3
+    assert (ks[1].shape[2] % 32 != 0) and B._packed_weights(ks[1], dtype)[2] is None   # ragged: no permuted twin
+    tbl = B._PACK_TABLES[(None, dtype)]
+    assert len(tbl.entries) == 3 and tbl.jobs_dev is None                  # table built lazily
+    calls.clear()
+    for k in ks:                                                           # all fresh: no calls at all
+        B._packed_weights(k, dtype)
+    assert calls == []
+    with torch.no_grad():
+        for k in ks:
+            k.add_(1.0)                                                    # the optimizer stepped
+    B._packed_weights(ks[2], dtype)
+    assert [c[0] for c in calls] == ["meb200_conv_pack_weights_batched"]
+    _, n_jobs, total_tiles = calls[0][1][0], calls[0][1][1], calls[0][1][2]
+    assert n_jobs == 3 and total_tiles == 27 * 1 * 2 + 8 * 1 * 1 + 1 * 3 * 3
+    jobs = (B._PackJob * 3).from_buffer_copy(bytes(tbl.jobs_dev.numpy().tobytes()))
+    assert [j.tile_begin for j in jobs] == [0, 54, 62] and [j.K for j in jobs] == [27, 8, 1]
+    assert jobs[1].w_cp is None and jobs[1].w_tp is None and jobs[0].w == ks[0].data_ptr()
+    assert ctypes.sizeof(B._PackJob) == 56
+    calls.clear()
+    for k in ks:                                                           # every entry was refreshed
+        B._packed_weights(k, dtype)
+    assert calls == []
+    # one tensor dies, one moves: the next batched call sees a rebuilt table without them
+    moved = ks[1]
+    dead_id = id(ks[0])
+    del ks[0]
+    import gc
+    gc.collect()
+    with torch.no_grad():
+        moved.data = moved.data.clone()
+        ks[1].add_(1.0)
+    B._packed_weights(moved, dtype)                # re-allocated: first sight again (packed alone)
+    B._packed_weights(ks[1], dtype)                # stale registered kernel: batched
+    names = [c[0] for c in calls]
+    assert names == ["meb200_conv_pack_weights", "meb200_conv_pack_weights_batched"]
+    assert calls[1][1][1] == 2 and dead_id not in tbl.entries
