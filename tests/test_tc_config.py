@@ -76,6 +76,21 @@ int main() {
     if (!ok) { printf("WP BAD ci=%u co=%u K=%u rows=%u\n", ci, co, K, rows); ++bad; }
     printf("wp %u %u %u %u : mt=%u groups=%u splits=%u stages=%u acc=%u smem=%u\n", ci, co, K, rows, w.mt_cta, w.n_mtgroups, w.n_splits, w.n_stage, w.acc_sets, w.smem_bytes);
   }
+  /* network stem (k_conv_ts STEM): K = 1 layer over 4 * 16 ceil(K / 16) virtual channels, 16 offsets
+     per stage; index rings of 16 offsets per warp must fit beside the row rings */
+  for (unsigned K : {1u, 8u, 16u, 27u, 64u, 81u, 125u, 128u}) for (unsigned cc : {16u, 32u, 64u, 96u, 128u, 256u}) for (unsigned rows : {1u, 300u, 800000u}) {
+    TaCfg t = ta_stem_config(K, cc, rows);
+    const unsigned cv = stem_virtual_channels(K);
+    if (cv != 4 * 16 * ((K + 15) / 16)) { printf("STEM BAD virtual channels K=%u\n", K); ++bad; }
+    if (t.nb == 0) { printf("stem %u %u %u : unsupported\n", K, cc, rows); continue; }
+    bool ok = t.nb == kStemNb && t.g == 1 && t.bk == 64 && t.n_macro * 64 == cv &&
+              t.acc_sets * t.R * cc + t.nA * 16 * t.nb <= kTmemCols && t.nA >= 3 && t.nA % 3 == 0 &&
+              t.nB >= 2 && t.rs >= 4 && t.rs <= 8 && t.smem_bytes <= 227 * 1024 &&
+              1024 + t.nB * t.b_stage_bytes + (t.rs + 1) * 12 * t.nb * 512 + kBarBytes +
+                  ts_tail_bytes(kStemOffsetsPerStage) == t.smem_bytes;
+    if (!ok) { printf("STEM BAD K=%u cc=%u rows=%u\n", K, cc, rows); ++bad; }
+    printf("stem %u %u %u : n_macro=%u R=%u acc=%u nA=%u nB=%u rs=%u smem=%u\n", K, cc, rows, t.n_macro, t.R, t.acc_sets, t.nA, t.nB, t.rs, t.smem_bytes);
+  }
   printf("bad=%d\n", bad);
   return bad != 0;
 }
