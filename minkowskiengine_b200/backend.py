@@ -540,8 +540,11 @@ class CoordinateMapManagerGPU_c10:
     # -- kernel maps -----------------------------------------------------------------
     LAZY_REVERSE_K = 64      # kernels this large get their reverse table on demand
 
-    def _probe(self, x_map, y_map, offsets, need_y=True):
-        """x-stationary probe: returns (x_nbr [K,nx], y_nbr [K,ny] or None)."""
+    @staticmethod
+    def _probe(x_map, y_map, offsets, need_y=True):
+        """x-stationary probe: returns (x_nbr [K,nx], y_nbr [K,ny] or None).  (Static: the deferred
+        reverse-table build below must not keep the manager alive through a reference cycle —
+        a manager owns ~1.5 GB of tables on the bench clouds and should die with its tensors.)"""
         lib = _lib.load()
         K = offsets.shape[0]
         dev = x_map.coords.device
@@ -600,8 +603,9 @@ class CoordinateMapManagerGPU_c10:
                 offs = _device_offsets(region_type, ksize, kdil, in_map.tensor_stride, custom, dev)
                 if offs.shape[0] >= self.LAZY_REVERSE_K:
                     out_nbr, _ = self._probe(out_map, in_map, offs, need_y=False)
+                    probe = self._probe
                     km = _KernelMap(out_nbr, None, n_in=in_map.size,
-                                    in_thunk=lambda: self._probe(out_map, in_map, offs)[1])
+                                    in_thunk=lambda: probe(out_map, in_map, offs)[1])
                 else:
                     out_nbr, in_nbr = self._probe(out_map, in_map, offs)
                     km = _KernelMap(out_nbr, in_nbr)

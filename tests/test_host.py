@@ -313,3 +313,47 @@ def test_pack_table_bookkeeping_against_a_stub_library(monkeypatch):
     names = [c[0] for c in calls]
     assert names == ["meb200_conv_pack_weights", "meb200_conv_pack_weights_batched"]
     assert calls[1][1][1] == 2 and dead_id not in tbl.entries
+
+
+def test_lazy_reverse_table_does_not_keep_the_manager_alive(monkeypatch):
+    """A kernel map of a large kernel (K >= 64) defers its reverse neighbour table; the deferred
+    build must work and must not tie the manager into a reference cycle (its tables would then
+    outlive the tensors until a cyclic garbage collection)."""
+    import gc
+    import weakref
+    from minkowskiengine_b200 import _lib, backend as B
+
+    class Stub:
+        def __getattr__(self, name):
+            return lambda *a: 0
+
+    monkeypatch.setattr(_lib, "load", lambda: Stub())
+    monkeypatch.setattr(_lib, "current_stream", lambda: None)
+    mgr = B.CoordinateMapManagerGPU_c10()
+    coords = torch.zeros((10, 4), dtype=torch.int32)
+    cmap = B._CoordinateMap(coords, torch.zeros(64, dtype=torch.int32), 64, (1, 1, 1))
+    mgr._maps[((1, 1, 1), "")] = cmap
+    key = B.CoordinateMapKey([1, 1, 1], "")
+    km = mgr._kernel_map(key, key, [5, 5, 5], [1, 1, 1], [1, 1, 1], B.RegionType.HYPER_CUBE, None,
+                         False, False)
+    assert km.K == 125 and km._in_nbr is None and km.n_in == 10          # reverse table deferred
+    rev = km.in_nbr                                                        # built on demand
+    assert rev.shape == (125, 10) and int((rev == -1).sum()) == 1250 and km._in_thunk is None
+    km2 = mgr._kernel_map(key, key, [5, 5, 5], [1, 1, 1], [1, 1, 1], B.RegionType.HYPER_CUBE, None,
+                          False, False)
+    assert km2 is km
+    small = mgr._kernel_map(key, key, [3, 3, 3], [1, 1, 1], [1, 1, 1], B.RegionType.HYPER_CUBE,
+                            None, False, False)
+    assert small._in_nbr is not None                                       # K = 27: built eagerly
+    # a fresh manager with an UNBUILT deferred table dies by reference counting alone
+    gc.disable()
+    try:
+        mgr2 = B.CoordinateMapManagerGPU_c10()
+        mgr2._maps[((1, 1, 1), "")] = cmap
+        mgr2._kernel_map(key, key, [5, 5, 5], [1, 1, 1], [1, 1, 1], B.RegionType.HYPER_CUBE, None,
+                         False, False)
+        ref = weakref.ref(mgr2)
+        del mgr2
+        assert ref() is None, "the manager is kept alive by a reference cycle"
+    finally:
+        gc.enable()
